@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — world-steps/s (forward step + analytic backward VJP) of the batched differentiable timestep.
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU path on the host cores
+
+Workload (BASELINE.json configs[1]): 65536 independent 5-link pendulums per GPU (no contact), one
+"step" = ddb_forward + ddb_backward over the whole batch (dart_layer forward + backward semantics).
+Weak scaling: every rank owns 65536 worlds; there is no inter-GPU traffic inside a step.
+One JSON line is printed by rank 0 (see the contract in the task description).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "world-steps/sec incl. analytic backprop"
+UNIT = "world-steps/s"
+N_WORLDS = 65536
+N_DOFS = 5
+WORKLOAD = "pendulum5: 65536 five-link revolute pendulums per GPU, no contact (BASELINE configs[1]); step = forward + analytic backward VJP"
+# Algorithmic HBM bytes per world: forward reads q,qd,tau (3n) writes q',qd' (2n) + snapshot
+# q,qd,qdd (3n); backward reads the snapshot (3n) + dL/dq',dL/dqd' (2n), writes dL/dq,dL/dqd,dL/dtau (3n).
+FWD_BYTES = 8 * N_DOFS * 8
+BWD_BYTES = 8 * N_DOFS * 8
+# FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
+FWD_FLOPS = None  # filled from profiles; None -> fp64 roofline omitted
+BWD_FLOPS = None
+
+
+def inputs(N, seed=1234):
+    rng = np.random.default_rng(seed)
+    return [rng.uniform(-1, 1, (N, N_DOFS)) for _ in range(3)]
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8)),
+            "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40)),
+            "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20)),
+            "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)),
+        }
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def cpu_world_steps(n_worlds, threads, reps=1):
+    """Times the CPU path (the oracle's restatement of World::step + BackpropSnapshot::backprop with the
+    reference's own finite-difference recipes) on n_worlds worlds; returns world-steps/s."""
+    from diffdart_b200 import skeletons
+    from oracle.oracle import OracleWorld
+
+    o = OracleWorld(skeletons.create_multiarm_robot(N_DOFS))
+    q, qd, tau = inputs(n_worlds)
+    g = np.random.default_rng(7).normal(size=(2, n_worlds, N_DOFS))
+    o.step_backprop(q[:256], qd[:256], tau[:256], g[0][:256], g[1][:256], threads=threads)  # warm-up
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        o.step_backprop(q, qd, tau, g[0], g[1], mode="reference", threads=threads)
+    dt = time.perf_counter() - t0
+    return n_worlds * reps / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = os.cpu_count() or 1
+    sample = 16384  # worlds per step (bounded sample of the 65536-world batch)
+    for _ in range(max(args.warmup, 0)):
+        cpu_world_steps(2048, threads)
+    t0 = time.perf_counter()
+    total = 0
+    for _ in range(args.steps):
+        cpu_world_steps(sample, threads)
+        total += sample
+    elapsed = time.perf_counter() - t0
+    value = total / elapsed
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": {"workload": WORKLOAD, "sample": "%d of the 65536 worlds per step" % sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": "%d worlds/step x %d steps; CPU restatement of the reference arithmetic (reference not buildable here: no Eigen)" % (sample, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from diffdart_b200 import _abi, skeletons
+
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(N_DOFS)
+    N, n = N_WORLDS, N_DOFS
+    SETS = 8  # rotating buffer sets: 8 x ~34 MB of inputs/outputs/snapshot = 272 MB > 126 MB L2, so every step is cold
+    topo, params, keep = desc.to_ctypes(n_snapshot_slots=SETS)
+    h = _abi._vp()
+    rc = lib.ddb_create(C.byref(topo), C.byref(params), N, local_rank, C.byref(h))
+    if rc:
+        raise RuntimeError("ddb_create failed: %s" % lib.ddb_last_error(h).decode())
+    q, qd, tau = inputs(N, 1234 + rank)
+    g = np.random.default_rng(99 + rank).normal(size=(2, N, n))
+    mk = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    sets = []
+    for s in range(SETS):
+        ins = [mk(np.roll(a, s, axis=0)) for a in (q, qd, tau, g[0], g[1])]
+        outs = [torch.empty(N, n, dtype=torch.float64, device=dev) for _ in range(5)]
+        sets.append((ins, outs))
+    stream = torch.cuda.current_stream(dev)
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def step(s):
+        (a, b, c, d, e), (o0, o1, o2, o3, o4) = sets[s % SETS]
+        lib.ddb_snapshot_select(h, s % SETS)
+        r1 = lib.ddb_forward(h, sp, a.data_ptr(), b.data_ptr(), c.data_ptr(), o0.data_ptr(), o1.data_ptr(), None, None, None, None)
+        r2 = lib.ddb_backward(h, sp, d.data_ptr(), e.data_ptr(), o2.data_ptr(), o3.data_ptr(), o4.data_ptr())
+        if r1 or r2:
+            raise RuntimeError(lib.ddb_last_error(h).decode())
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local_rank)
+    for s in range(max(args.warmup, 3)):
+        step(s)
+    barrier()
+    # ---- timed region: exactly K steps, device-resident inputs ----
+    launches0 = lib.ddb_launch_count(h)
+    sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    barrier()
+    ev[0].record(stream)
+    for s in range(args.steps):
+        step(s)
+    ev[1].record(stream)
+    barrier()
+    elapsed_ms = ev[0].elapsed_time(ev[1])
+    launches = int(lib.ddb_launch_count(h) - launches0)
+    # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
+    t_end = time.time() + (0.3 if elapsed_ms < 300 else 0.0)
+    s = 0
+    while time.time() < t_end:
+        step(s)
+        s += 1
+        if s % 64 == 0:
+            torch.cuda.synchronize(dev)
+    torch.cuda.synchronize(dev)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    # ---- per-kernel durations (same launches, events around each kernel) ----
+    kev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(min(args.steps, 64))]
+    for i, e3 in enumerate(kev):
+        (a, b, c, d, e), (o0, o1, o2, o3, o4) = sets[i % SETS]
+        lib.ddb_snapshot_select(h, i % SETS)
+        e3[0].record(stream)
+        lib.ddb_forward(h, sp, a.data_ptr(), b.data_ptr(), c.data_ptr(), o0.data_ptr(), o1.data_ptr(), None, None, None, None)
+        e3[1].record(stream)
+        lib.ddb_backward(h, sp, d.data_ptr(), e.data_ptr(), o2.data_ptr(), o3.data_ptr(), o4.data_ptr())
+        e3[2].record(stream)
+    torch.cuda.synchronize(dev)
+    fwd_ms = float(np.mean([e3[0].elapsed_time(e3[1]) for e3 in kev]))
+    bwd_ms = float(np.mean([e3[1].elapsed_time(e3[2]) for e3 in kev]))
+    # ---- e2e: host buffers through the C ABI's host entry points, copies inside the timed region ----
+    hin = [torch.tensor(a, dtype=torch.float64).pin_memory() for a in (q, qd, tau, g[0], g[1])]
+    hout = [torch.empty(N, n, dtype=torch.float64).pin_memory() for _ in range(5)]
+    e2e_steps = max(3, min(args.steps, 50))
+
+    def e2e_step():
+        r1 = lib.ddb_forward_host(h, hin[0].data_ptr(), hin[1].data_ptr(), hin[2].data_ptr(), hout[0].data_ptr(), hout[1].data_ptr())
+        r2 = lib.ddb_backward_host(h, hin[3].data_ptr(), hin[4].data_ptr(), hout[2].data_ptr(), hout[3].data_ptr(), hout[4].data_ptr())
+        if r1 or r2:
+            raise RuntimeError(lib.ddb_last_error(h).decode())
+
+    lib.ddb_snapshot_select(h, 0)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize(dev)
+    e2e_s = time.perf_counter() - t0
+    # ---- reduce over ranks (max time) ----
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms = [float(x) for x in t.cpu()]
+    peak = ctypes_double()
+    lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            hbm_peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        value = world_size * N * args.steps / (elapsed_ms * 1e-3)
+        dom = ("k_backward", bwd_ms, BWD_BYTES, BWD_FLOPS) if bwd_ms >= fwd_ms else ("k_forward", fwd_ms, FWD_BYTES, FWD_FLOPS)
+        achieved = dom[2] * N / (dom[1] * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "worlds_per_gpu": N, "n_dofs": n, "dt": 1e-3,
+                       "cache": "8 rotating input/output/snapshot sets (272 MB > 126 MB L2): every step reads cold inputs"},
+            "clocks": sampler.result(),
+            "e2e": {"value": world_size * N * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 5 * N * n * 8,
+                    "d2h_bytes_per_step": 5 * N * n * 8, "steps": e2e_steps,
+                    "path": "ddb_forward_host + ddb_backward_host with pinned host buffers"},
+            "gpu_launches": launches,
+            "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms},
+            "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                         "traffic": None, "peak_source": peak_src,
+                         "note": "FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md §4"},
+            "roofline_fp64": {"peak": peak.value, "unit": "TFLOP/s", "peak_source": "ddb_measure_fp64_peak (DFMA micro-benchmark, this run)",
+                              "achieved": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12,
+                              "frac": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12 / peak.value},
+        }
+        if world_size == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, secs = cpu_world_steps(N_WORLDS, threads)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                    "sample": "one pass over the same 65536-world batch (%.1f s); CPU restatement of the reference arithmetic incl. its finite-difference Jacobian recipes" % secs}
+        print(json.dumps(line))
+    lib.ddb_destroy(h)
+    if world_size > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def ctypes_double():
+    return C.c_double(0.0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if args.steps == 2000:
+            args.steps, args.warmup = 5, 1
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

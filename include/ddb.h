@@ -1,0 +1,192 @@
+/*
+ * ddb.h — C ABI of the B200-native batched differentiable timestep.
+ *
+ * This is the drop-in boundary for the path behind the reference's
+ *   dart::neural::forwardPass            (dart/neural/NeuralUtils.hpp:45-46, NeuralUtils.cpp:26-66)
+ *   dart::neural::BackpropSnapshot       (dart/neural/BackpropSnapshot.hpp:22-803)
+ *   simulation::World::step              (dart/simulation/World.cpp:206-279)
+ * executed for N independent worlds that share one skeleton topology.
+ *
+ * Conventions
+ *  - All arithmetic is FP64, index/flag data is int32.
+ *  - Every pointer named *_dev is a CUDA device pointer on the handle's device;
+ *    the *_host entry points take ordinary host pointers and do the copies
+ *    themselves (that is the "e2e" path a binding with host buffers calls).
+ *  - Batched vectors use the layout chosen in ddb_params.layout:
+ *      DDB_LAYOUT_WORLD_MAJOR  x[world * n_dofs + dof]   (a [N, n] row-major tensor)
+ *      DDB_LAYOUT_DOF_MAJOR    x[dof * n_worlds + world] (structure of arrays)
+ *    Batched matrices are [world][col][row] (column-major per world, as Eigen
+ *    returns them from BackpropSnapshot::get*Jacobian) in both layouts.
+ *  - Every function returns 0 on success, a DDB_ERR_* code otherwise;
+ *    ddb_last_error() returns a human-readable host string.
+ *  - There is no CPU fallback: without a CUDA device ddb_create fails.
+ */
+#ifndef DDB_H_
+#define DDB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DDB_ABI_VERSION 1
+#define DDB_MAX_BODIES 48
+#define DDB_MAX_DOFS 48
+
+enum {
+  DDB_OK = 0,
+  DDB_ERR_INVALID = 1,     /* bad argument / unsupported topology */
+  DDB_ERR_CUDA = 2,        /* a CUDA runtime call failed           */
+  DDB_ERR_NO_DEVICE = 3,   /* no CUDA device: there is no CPU path */
+  DDB_ERR_STATE = 4        /* e.g. backward before forward         */
+};
+
+/* Joint kinds on the hot path (dart/dynamics/{Weld,Revolute,Prismatic,Free}Joint.cpp). */
+enum {
+  DDB_JOINT_WELD = 0,      /* 0 DOF */
+  DDB_JOINT_REVOLUTE = 1,  /* 1 DOF, RevoluteJoint.cpp:140-189 */
+  DDB_JOINT_PRISMATIC = 2, /* 1 DOF, PrismaticJoint.cpp:139-187 */
+  DDB_JOINT_FREE = 3       /* 6 DOF, FreeJoint.cpp:64-81,587-601,673-693 */
+};
+
+/* Collision shapes handled by the in-tree narrow phase (dart/collision/dart/DARTCollide.cpp). */
+enum { DDB_SHAPE_NONE = 0, DDB_SHAPE_BOX = 1, DDB_SHAPE_SPHERE = 2 };
+
+enum { DDB_LAYOUT_WORLD_MAJOR = 0, DDB_LAYOUT_DOF_MAJOR = 1 };
+
+/* A rigid transform: rotation row-major r[0..8], then translation p[0..2]. */
+typedef struct ddb_transform {
+  double r[9];
+  double p[3];
+} ddb_transform;
+
+/*
+ * One BodyNode together with its parent Joint. A superset of the reference's own
+ * flat-array descriptor JointAndBody (dart/dynamics/SimpleFeatherstone.hpp:16-30).
+ * Bodies are listed parent-before-child; all skeletons of the world are
+ * concatenated (parent = -1 marks a skeleton root), DOFs are numbered in that
+ * order exactly as World::getPositions() concatenates them (World.cpp:1027-1040).
+ * Springs and damping do not exist here: World::addSkeleton zeroes them
+ * (World.cpp:698-732).
+ */
+typedef struct ddb_body {
+  int32_t parent;      /* index of the parent body, -1 for a root            */
+  int32_t joint_type;  /* DDB_JOINT_*                                        */
+  int32_t dof_offset;  /* first generalized coordinate of the parent joint   */
+  int32_t skeleton;    /* skeleton id (constraint grouping, mobility)        */
+  int32_t gravity_mode;/* BodyNode gravity mode (BodyNode.cpp:1694)          */
+  int32_t shape_type;  /* DDB_SHAPE_*; collidable iff != NONE                */
+  double axis[3];      /* joint axis in the joint frame (1-DOF joints)       */
+  ddb_transform parent_to_joint; /* Joint::mT_ParentBodyToJoint              */
+  ddb_transform child_to_joint;  /* Joint::mT_ChildBodyToJoint               */
+  double mass;
+  double com[3];       /* Inertia::mCenterOfMass                             */
+  double moment[6];    /* Ixx Iyy Izz Ixy Ixz Iyz (Inertia.cpp:394-409)      */
+  double friction;     /* BodyNodeAspect.hpp:47 default 1.0                  */
+  double restitution;  /* BodyNodeAspect.hpp:48 default 0.0                  */
+  double shape_size[3];/* box: full extents; sphere: radius in [0]           */
+  ddb_transform shape_offset;    /* ShapeNode relative transform             */
+} ddb_body;
+
+typedef struct ddb_topology {
+  int32_t n_bodies;
+  int32_t n_dofs;
+  const ddb_body* bodies;
+  /* per-DOF limits used only by clipLossGradientsToBounds
+     (BackpropSnapshot.cpp:374-428); NULL means +-infinity */
+  const double* position_lower;
+  const double* position_upper;
+  const double* velocity_lower;
+  const double* velocity_upper;
+  const double* force_lower;
+  const double* force_upper;
+} ddb_topology;
+
+/* World-level parameters; ddb_default_params() fills the reference defaults
+   (World.cpp:67-94, ContactConstraint.cpp:43-55). */
+typedef struct ddb_params {
+  double gravity[3];              /* (0,0,-9.81)  World.cpp:71 */
+  double time_step;               /* 1e-3         World.cpp:72 */
+  double contact_clipping_depth;  /* 0.03         World.cpp:84 */
+  int32_t layout;                 /* DDB_LAYOUT_*                */
+  int32_t n_snapshot_slots;       /* >=1; slots retained for T-step rollouts */
+  int32_t reserved[6];
+} ddb_params;
+
+typedef struct ddb_handle ddb_handle;
+
+void ddb_default_params(ddb_params* p);
+int ddb_abi_version(void);
+
+/* Replaces: World construction + World::addSkeleton for N clones (World.cpp:109-157,683-760). */
+int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_worlds,
+               int32_t device, ddb_handle** out);
+int ddb_destroy(ddb_handle* h);
+const char* ddb_last_error(const ddb_handle* h);
+int32_t ddb_num_worlds(const ddb_handle* h);
+int32_t ddb_num_dofs(const ddb_handle* h);
+
+/*
+ * Replaces neural::forwardPass(world, idempotent=false) for every world
+ * (NeuralUtils.cpp:26-66 -> World::step World.cpp:206-279). Inputs are the
+ * pre-step positions, velocities and joint forces; outputs the post-step state.
+ * The snapshot needed by ddb_backward / ddb_jacobians is retained in the
+ * handle's current slot (see ddb_snapshot_select).
+ * lcp_cache_inout / n_rows_inout / active_set_out / status_out may be NULL for
+ * contact-free topologies.
+ */
+int ddb_forward(ddb_handle* h, void* cuda_stream,
+                const double* q_dev, const double* qd_dev, const double* tau_dev,
+                double* q_next_dev, double* qd_next_dev,
+                double* lcp_cache_inout_dev, int32_t* n_rows_inout_dev,
+                int32_t* active_set_out_dev, int32_t* status_out_dev);
+
+/*
+ * Replaces BackpropSnapshot::backprop (BackpropSnapshot.cpp:115-186) including
+ * clipLossGradientsToBounds (:374-428): given dL/dq', dL/dqd' returns
+ * dL/dq, dL/dqd, dL/dtau of the step retained in the current slot.
+ */
+int ddb_backward(ddb_handle* h, void* cuda_stream,
+                 const double* g_q_next_dev, const double* g_qd_next_dev,
+                 double* g_q_dev, double* g_qd_dev, double* g_tau_dev);
+
+/*
+ * Replaces BackpropSnapshot::get{PosPos,PosVel,VelPos,VelVel,ForceVel}Jacobian
+ * (BackpropSnapshot.cpp:432-735,1237-1360). Each output is [N][n][n]
+ * column-major per world; any pointer may be NULL to skip that matrix.
+ */
+int ddb_jacobians(ddb_handle* h, void* cuda_stream,
+                  double* pos_pos_dev, double* pos_vel_dev, double* vel_pos_dev,
+                  double* vel_vel_dev, double* force_vel_dev);
+
+/* Replaces BackpropSnapshot::getInvMassMatrix / getMassMatrix helpers
+   (python/_diffdart/neural/BackpropSnapshot.cpp:42-146): [N][n][n] col-major. */
+int ddb_inv_mass_matrix(ddb_handle* h, void* cuda_stream, double* minv_dev);
+
+/* Snapshot slots for T-step rollouts (the shape of SingleShot::getSnapshots,
+   dart/trajectory/SingleShot.cpp:719-760 and its reverse sweep :650-700). */
+int ddb_snapshot_select(ddb_handle* h, int32_t slot);
+int32_t ddb_snapshot_current(const ddb_handle* h);
+/* grow the slot pool to at least n_slots (never shrinks); returns the pool size in *n_out */
+int ddb_snapshot_reserve(ddb_handle* h, int32_t n_slots, int32_t* n_out);
+
+/* Host-buffer entry points: same semantics, host pointers, copies inside. */
+int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const double* tau,
+                     double* q_next, double* qd_next);
+int ddb_backward_host(ddb_handle* h, const double* g_q_next, const double* g_qd_next,
+                      double* g_q, double* g_qd, double* g_tau);
+int ddb_jacobians_host(ddb_handle* h, double* pos_pos, double* pos_vel, double* vel_pos,
+                       double* vel_vel, double* force_vel);
+
+/* FP64 FMA micro-benchmark (8 independent DFMA chains per thread, every SM busy): the measured
+   FP64-pipe peak of this GPU in TFLOP/s, the denominator of the FP64 roofline fraction. */
+int ddb_measure_fp64_peak(int32_t device, double* tflops_out);
+
+/* Counts kernels launched by this handle since creation (bench "gpu_launches"). */
+int64_t ddb_launch_count(const ddb_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DDB_H_ */

@@ -1,0 +1,153 @@
+// TEST INFRASTRUCTURE ONLY — see dd_spatial.hpp.
+// C entry points of the CPU oracle for ctypes (tests/, smoke(), bench.py cpu_baseline).
+// Batched arrays are world-major: x[world * n + dof]; matrices [world][col][row].
+#include <thread>
+#include <vector>
+#include <functional>
+#include "dd_step.hpp"
+
+using namespace ddo;
+
+struct OracleWorld {
+  std::vector<ddb_body> bodies;
+  Model M;
+};
+
+static void parallelFor(int N, int threads, const std::function<void(int, int)>& fn) {
+  if (threads <= 1 || N < 2) { fn(0, N); return; }
+  std::vector<std::thread> pool;
+  int per = (N + threads - 1) / threads;
+  for (int t = 0; t < threads; t++) {
+    int lo = t * per, hi = std::min(N, lo + per);
+    if (lo >= hi) break;
+    pool.emplace_back(fn, lo, hi);
+  }
+  for (auto& th : pool) th.join();
+}
+
+extern "C" {
+
+void* ddo_create(const ddb_topology* t, const ddb_params* p) {
+  OracleWorld* w = new OracleWorld();
+  w->M = buildModel(*t, *p);
+  return w;
+}
+void ddo_destroy(void* h) { delete (OracleWorld*)h; }
+int ddo_num_dofs(void* h) { return ((OracleWorld*)h)->M.nd; }
+
+void ddo_step(void* h, int N, int threads, const double* q, const double* qd, const double* tau, double* qn, double* qdn) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  parallelFor(N, threads, [&](int lo, int hi) {
+    for (int w = lo; w < hi; w++) stepNoContact<double>(M, q + w * n, qd + w * n, tau + w * n, qn + w * n, qdn + w * n);
+  });
+}
+
+// mode 0: the reference's recipe (its own finite-difference eps); mode 1: exact (long double, Richardson)
+void ddo_jacobians(void* h, int N, int threads, int mode, const double* q, const double* qd, const double* tau, double* posPos,
+                   double* posVel, double* velPos, double* velVel, double* forceVel) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd, nn = n * n;
+  parallelFor(N, threads, [&](int lo, int hi) {
+    Jacobians J;
+    for (int w = lo; w < hi; w++) {
+      if (mode == 0) jacobiansReferenceNoContact(M, q + w * n, qd + w * n, tau + w * n, J);
+      else jacobiansExactNoContact(M, q + w * n, qd + w * n, tau + w * n, J);
+      if (posPos) std::memcpy(posPos + (size_t)w * nn, J.posPos.data(), nn * sizeof(double));
+      if (posVel) std::memcpy(posVel + (size_t)w * nn, J.posVel.data(), nn * sizeof(double));
+      if (velPos) std::memcpy(velPos + (size_t)w * nn, J.velPos.data(), nn * sizeof(double));
+      if (velVel) std::memcpy(velVel + (size_t)w * nn, J.velVel.data(), nn * sizeof(double));
+      if (forceVel) std::memcpy(forceVel + (size_t)w * nn, J.forceVel.data(), nn * sizeof(double));
+    }
+  });
+}
+
+// forward + backprop of one step per world: the CPU "world-step" of the baseline.
+void ddo_step_backprop(void* h, int N, int threads, int mode, const double* q, const double* qd, const double* tau, const double* gqn,
+                       const double* gqdn, double* qn, double* qdn, double* gq, double* gqd, double* gtau) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  parallelFor(N, threads, [&](int lo, int hi) {
+    Jacobians J;
+    for (int w = lo; w < hi; w++) {
+      const double *qw = q + w * n, *qdw = qd + w * n, *tw = tau + w * n;
+      if (qn) stepNoContact<double>(M, qw, qdw, tw, qn + w * n, qdn + w * n);
+      if (mode == 0) jacobiansReferenceNoContact(M, qw, qdw, tw, J);
+      else jacobiansExactNoContact(M, qw, qdw, tw, J);
+      backprop(M, J, qw, qdw, tw, gqn + w * n, gqdn + w * n, gq + w * n, gqd + w * n, gtau + w * n);
+    }
+  });
+}
+
+void ddo_inv_mass_matrix(void* h, int N, const double* q, double* Minv) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  std::vector<double> zero(n, 0.0);
+  for (int w = 0; w < N; w++) {
+    Dyn<double> d(M);
+    d.setState(q + w * n, zero.data());
+    d.invMassMatrix(Minv + (size_t)w * n * n);
+  }
+}
+void ddo_coriolis_gravity(void* h, int N, const double* q, const double* qd, double* C) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  for (int w = 0; w < N; w++) {
+    Dyn<double> d(M);
+    d.setState(q + w * n, qd + w * n);
+    d.coriolisGravity(C + w * n);
+  }
+}
+void ddo_forward_dynamics(void* h, int N, const double* q, const double* qd, const double* tau, double* qdd) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  for (int w = 0; w < N; w++) {
+    Dyn<double> d(M);
+    d.setState(q + w * n, qd + w * n);
+    d.forwardDynamics(tau + w * n, qdd + w * n);
+  }
+}
+// world transforms of every body: out[world][body][12] (R row-major, p)
+void ddo_body_transforms(void* h, int N, const double* q, double* out) {
+  const Model& M = ((OracleWorld*)h)->M;
+  int n = M.nd;
+  std::vector<double> zero(n, 0.0);
+  for (int w = 0; w < N; w++) {
+    Dyn<double> d(M);
+    d.setState(q + w * n, zero.data());
+    for (int i = 0; i < M.nb; i++) {
+      double* o = out + ((size_t)w * M.nb + i) * 12;
+      for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) o[3 * r + c] = d.b[i].W.R.m[r][c]; o[9 + r] = d.b[i].W.p[r]; }
+    }
+  }
+}
+// spatial inertia tensors: out[body][36] row-major
+void ddo_spatial_inertias(void* h, double* out) {
+  const Model& M = ((OracleWorld*)h)->M;
+  for (int i = 0; i < M.nb; i++) for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) out[i * 36 + r * 6 + c] = M.b[i].I.m[r][c];
+}
+// math primitives exposed for the golden-vector tests
+void ddo_transform_inertia(const double* T12, const double* I36, double* out36) {
+  Iso<double> T;
+  Mat6<double> I;
+  for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) T.R.m[r][c] = T12[3 * r + c]; T.p[r] = T12[9 + r]; }
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) I.m[r][c] = I36[6 * r + c];
+  Mat6<double> o = transformInertia(T, I);
+  for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) out36[6 * r + c] = o.m[r][c];
+}
+void ddo_exp_angular(const double* s, double* R9) {
+  Mat3<double> R = expAngular(v3<double>(s[0], s[1], s[2]));
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R9[3 * r + c] = R.m[r][c];
+}
+void ddo_exp_map_rot(const double* s, double* R9) {
+  Mat3<double> R = expMapRot(v3<double>(s[0], s[1], s[2]));
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R9[3 * r + c] = R.m[r][c];
+}
+void ddo_log_map_rot(const double* R9, double* w) {
+  Mat3<double> R;
+  for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R.m[r][c] = R9[3 * r + c];
+  Vec3<double> o = logMapRot(R);
+  for (int r = 0; r < 3; r++) w[r] = o[r];
+}
+
+}  // extern "C"

@@ -1,0 +1,178 @@
+"""TEST INFRASTRUCTURE ONLY — ctypes binding of the CPU oracle.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+legs may import this module. It loads
+  oracle/_build/liboracle.so     our restatement of the reference arithmetic
+  oracle/_ref/libodelcp_ref.so   the reference's own, unmodified ODE Dantzig solver
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(HERE, "_build", "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libodelcp_ref.so")
+
+_dp = C.POINTER(C.c_double)
+
+
+def build():
+    """Compile the oracle (and, where /root/reference exists, the reference Dantzig)."""
+    subprocess.run(["make", "-C", HERE, "-s"], check=True, stdout=subprocess.DEVNULL)
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(ORACLE_SO):
+            build()
+        _lib = C.CDLL(ORACLE_SO)
+        _lib.ddo_create.restype = C.c_void_p
+        _lib.ddo_create.argtypes = [C.c_void_p, C.c_void_p]
+        _lib.ddo_destroy.argtypes = [C.c_void_p]
+    return _lib
+
+
+class OracleWorld:
+    """CPU restatement of World::step + BackpropSnapshot for one topology; batched over worlds."""
+
+    def __init__(self, world_description):
+        self._topo, self._params, self._keep = world_description.to_ctypes()
+        self.h = C.c_void_p(lib().ddo_create(C.byref(self._topo), C.byref(self._params)))
+        self.n = self._topo.n_dofs
+        self.nb = self._topo.n_bodies
+        self.dt = self._params.time_step
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ddo_destroy(self.h)
+            self.h = None
+
+    @staticmethod
+    def _c(a):
+        return np.ascontiguousarray(a, dtype=np.float64)
+
+    def step(self, q, qd, tau, threads=1):
+        q, qd, tau = self._c(q), self._c(qd), self._c(tau)
+        N = q.shape[0]
+        qn, qdn = np.empty_like(q), np.empty_like(q)
+        lib().ddo_step(self.h, N, threads, _ptr(q), _ptr(qd), _ptr(tau), _ptr(qn), _ptr(qdn))
+        return qn, qdn
+
+    def jacobians(self, q, qd, tau, mode="reference", threads=1):
+        """mode 'reference': the reference's recipe incl. its finite differences; 'exact': long-double FD."""
+        q, qd, tau = self._c(q), self._c(qd), self._c(tau)
+        N, n = q.shape
+        out = [np.empty((N, n, n)) for _ in range(5)]
+        lib().ddo_jacobians(self.h, N, threads, 0 if mode == "reference" else 1, _ptr(q), _ptr(qd), _ptr(tau),
+                            *[_ptr(o) for o in out])
+        # stored [world][col][row] -> return as [world][row][col]
+        names = ("posPos", "posVel", "velPos", "velVel", "forceVel")
+        return {k: np.ascontiguousarray(o.transpose(0, 2, 1)) for k, o in zip(names, out)}
+
+    def step_backprop(self, q, qd, tau, gqn, gqdn, mode="reference", threads=1, with_step=True):
+        q, qd, tau, gqn, gqdn = map(self._c, (q, qd, tau, gqn, gqdn))
+        N = q.shape[0]
+        qn, qdn = (np.empty_like(q), np.empty_like(q)) if with_step else (None, None)
+        gq, gqd, gtau = np.empty_like(q), np.empty_like(q), np.empty_like(q)
+        lib().ddo_step_backprop(self.h, N, threads, 0 if mode == "reference" else 1, _ptr(q), _ptr(qd), _ptr(tau),
+                                _ptr(gqn), _ptr(gqdn), _ptr(qn), _ptr(qdn), _ptr(gq), _ptr(gqd), _ptr(gtau))
+        return qn, qdn, gq, gqd, gtau
+
+    def inv_mass_matrix(self, q):
+        q = self._c(q)
+        N, n = q.shape
+        out = np.empty((N, n, n))
+        lib().ddo_inv_mass_matrix(self.h, N, _ptr(q), _ptr(out))
+        return np.ascontiguousarray(out.transpose(0, 2, 1))
+
+    def coriolis_gravity(self, q, qd):
+        q, qd = self._c(q), self._c(qd)
+        out = np.empty_like(q)
+        lib().ddo_coriolis_gravity(self.h, q.shape[0], _ptr(q), _ptr(qd), _ptr(out))
+        return out
+
+    def forward_dynamics(self, q, qd, tau):
+        q, qd, tau = self._c(q), self._c(qd), self._c(tau)
+        out = np.empty_like(q)
+        lib().ddo_forward_dynamics(self.h, q.shape[0], _ptr(q), _ptr(qd), _ptr(tau), _ptr(out))
+        return out
+
+    def body_transforms(self, q):
+        q = self._c(q)
+        out = np.empty((q.shape[0], self.nb, 12))
+        lib().ddo_body_transforms(self.h, q.shape[0], _ptr(q), _ptr(out))
+        return out
+
+    def spatial_inertias(self):
+        out = np.empty((self.nb, 6, 6))
+        lib().ddo_spatial_inertias(self.h, _ptr(out))
+        return out
+
+
+def transform_inertia(T12, I66):
+    out = np.empty((6, 6))
+    lib().ddo_transform_inertia(_ptr(np.ascontiguousarray(T12, dtype=np.float64)), _ptr(np.ascontiguousarray(I66, dtype=np.float64)), _ptr(out))
+    return out
+
+
+def exp_angular(s):
+    out = np.empty((3, 3))
+    lib().ddo_exp_angular(_ptr(np.ascontiguousarray(s, dtype=np.float64)), _ptr(out))
+    return out
+
+
+def exp_map_rot(s):
+    out = np.empty((3, 3))
+    lib().ddo_exp_map_rot(_ptr(np.ascontiguousarray(s, dtype=np.float64)), _ptr(out))
+    return out
+
+
+def log_map_rot(R):
+    out = np.empty(3)
+    lib().ddo_log_map_rot(_ptr(np.ascontiguousarray(R, dtype=np.float64)), _ptr(out))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# the reference's own Dantzig solver
+# ---------------------------------------------------------------------------
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        if not os.path.exists(REF_SO):
+            build()
+        if not os.path.exists(REF_SO):
+            raise RuntimeError("oracle/_ref/libodelcp_ref.so is missing and /root/reference is not present to build it")
+        _ref = C.CDLL(REF_SO)
+    return _ref
+
+
+def ref_dantzig(A, b, lo, hi, findex, early_termination=False):
+    """Run the reference's dSolveLCP exactly as DantzigBoxedLcpSolver::solve calls it.
+    A (n x n), returns (ok, x). Inputs are copied (the solver destroys A, b, lo, hi)."""
+    r = ref_lib()
+    n = len(b)
+    pad = r.ddref_dpad(n)
+    Ap = np.zeros((n, pad))
+    Ap[:, :n] = A
+    x = np.zeros(n)
+    b = np.array(b, dtype=np.float64)
+    lo = np.array(lo, dtype=np.float64)
+    hi = np.array(hi, dtype=np.float64)
+    fi = np.array(findex, dtype=np.int32)
+    ok = r.ddref_dantzig_solve(n, _ptr(Ap), _ptr(x), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(C.POINTER(C.c_int)),
+                               1 if early_termination else 0)
+    return bool(ok), x
