@@ -78,7 +78,7 @@ def default_params():
 
 
 _LIB = None
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libddb.so")
+LIB_PATH = os.environ.get("DDB_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib", "libddb.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)

@@ -2,6 +2,7 @@
 // kernel dispatch. No torch types, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -13,30 +14,37 @@ using namespace ddb;
 
 namespace {
 
-constexpr int kBlock = 64;
+#ifndef DDB_BLOCK
+#define DDB_BLOCK 64
+#endif
+#ifndef DDB_MINB
+#define DDB_MINB 1
+#endif
+constexpr int kBlock = DDB_BLOCK;
+constexpr int kMinB = DDB_MINB;
 
 struct KernelTable {
   void (*fwd)(cudaStream_t, int, const double*, const double*, const double*, double*, double*, double*);
-  void (*bwd)(cudaStream_t, int, const double*, const double*, const double*, double*, double*, double*, Limits);
-  void (*jac)(cudaStream_t, int, const double*, double*, double*, double*, double*, double*);
-  void (*minv)(cudaStream_t, int, const double*, double*);
+  void (*bwd)(cudaStream_t, int, double*, const double*, const double*, double*, double*, double*, Limits);
+  void (*jac)(cudaStream_t, int, double*, double*, double*, double*, double*, double*);
+  void (*minv)(cudaStream_t, int, double*, double*);
 };
 
 template <int NB, bool CHAIN>
 struct Launch {
   static int grid(int N) { return (N + kBlock - 1) / kBlock; }
   static void fwd(cudaStream_t s, int N, const double* q, const double* qd, const double* tau, double* qn, double* qdn, double* snap) {
-    k_forward<NB, CHAIN, kBlock, 1><<<grid(N), kBlock, 0, s>>>(N, q, qd, tau, qn, qdn, snap);
+    k_forward<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, q, qd, tau, qn, qdn, snap);
   }
-  static void bwd(cudaStream_t s, int N, const double* snap, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
+  static void bwd(cudaStream_t s, int N, double* snap, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
                   Limits lim) {
-    k_backward<NB, CHAIN, kBlock, 1><<<grid(N), kBlock, 0, s>>>(N, snap, gqn, gqdn, gq, gqd, gtau, lim);
+    k_backward<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, gqn, gqdn, gq, gqd, gtau, lim);
   }
-  static void jac(cudaStream_t s, int N, const double* snap, double* pp, double* pv, double* vp, double* vv, double* fv) {
-    k_jacobians<NB, CHAIN, kBlock, 1><<<grid(N), kBlock, 0, s>>>(N, snap, pp, pv, vp, vv, fv);
+  static void jac(cudaStream_t s, int N, double* snap, double* pp, double* pv, double* vp, double* vv, double* fv) {
+    k_jacobians<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, pp, pv, vp, vv, fv);
   }
-  static void minv(cudaStream_t s, int N, const double* snap, double* out) {
-    k_inv_mass<NB, CHAIN, kBlock, 1><<<grid(N), kBlock, 0, s>>>(N, snap, out);
+  static void minv(cudaStream_t s, int N, double* snap, double* out) {
+    k_inv_mass<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, out);
   }
   static KernelTable table() { return KernelTable{fwd, bwd, jac, minv}; }
 };
@@ -238,7 +246,7 @@ int enter(ddb_handle* h, cudaStream_t s) {
   return bindTopology(h, s);
 }
 
-size_t snapDoubles(const ddb_handle* h) { return (size_t)(h->topo.has_limits ? 4 : 3) * h->n * h->N; }
+size_t snapDoubles(const ddb_handle* h) { return snapDoublesPerWorld(h->nb, h->n, h->topo.has_limits != 0) * (size_t)h->N; }
 
 }  // namespace
 
@@ -314,6 +322,9 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
   if (rc != DDB_OK) return rc;
   h->n = h->topo.nd; h->nb = h->topo.nb;
   if (h->n == 0) return fail(h, DDB_ERR_INVALID, "world has no degrees of freedom");
+  // DDB_FORCE_GENERIC=1 routes chains through the generic tree kernels (used by the tests to cover both)
+  const char* fg = getenv("DDB_FORCE_GENERIC");
+  if (fg && fg[0] == '1') h->chain = false;
   h->k = pickTable(h->nb, h->chain);
   DDB_CUDA(h, cudaSetDevice(device));
   int slots = params->n_snapshot_slots < 1 ? 1 : params->n_snapshot_slots;

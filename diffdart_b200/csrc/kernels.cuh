@@ -3,8 +3,8 @@
 //   k_backward   BackpropSnapshot::backprop as a vector-Jacobian product (BackpropSnapshot.cpp:115-186,374-428)
 //   k_jacobians  BackpropSnapshot::get{PosPos,PosVel,VelPos,VelVel,ForceVel}Jacobian (:432-735,1237-1360)
 //   k_inv_mass   Skeleton::getInvMassMatrix (Skeleton.cpp:2899-2905,4035-4098)
-// Snapshot kept between forward and backward (per slot, DOF-major so that it is coalesced
-// whatever the user layout is): q, qd, qdd  (+ tau when joint limits are finite).
+// The snapshot kept between forward and backward (per slot) is described in dynamics.cuh (struct Snap);
+// q, qd, tau are appended only when joint limits are finite (clipLossGradientsToBounds needs them).
 #pragma once
 #include "dynamics.cuh"
 
@@ -14,6 +14,11 @@ struct Limits {  // device arrays of length n (valid only when c_topo.has_limits
   const double *pos_lo, *pos_hi, *vel_lo, *vel_hi, *frc_lo, *frc_hi;
 };
 
+// doubles per world in one snapshot slot
+__host__ __device__ inline size_t snapDoublesPerWorld(int nb, int n, bool limits) { return (size_t)2 * kSnapPairs * nb + (limits ? 3 * n : 0); }
+// the clip section (q, qd, tau as [3n][N]) sits behind the per-body pairs
+DDB_DI double* clipSection(double* snap, int nb, int N) { return snap + (size_t)2 * kSnapPairs * nb * N; }
+
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
@@ -22,7 +27,8 @@ k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, co
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  TreeState<NB, CHAIN> st;
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  double* clip = clipSection(snap, nb, N);
   if (CHAIN) {
     double ql[NB], qdl[NB], tl[NB], acc[NB];
 #pragma unroll
@@ -31,7 +37,7 @@ k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, co
       ql[d] = q[ix]; qdl[d] = qd[ix]; tl[d] = tau[ix];
     }
     forwardDynamics<NB, CHAIN>(
-        st, nb, [&](int d) { return ql[d]; }, [&](int d) { return qdl[d]; }, [&](int d) { return tl[d]; },
+        sn, nb, [&](int d) { return ql[d]; }, [&](int d) { return qdl[d]; }, [&](int d) { return tl[d]; },
         [&](int d, double a) { acc[d] = a; });
 #pragma unroll
     for (int d = 0; d < NB; d++) {
@@ -39,25 +45,30 @@ k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, co
       // explicit position update with the pre-step velocity (World.cpp:262-274); qd += dt*qdd
       qn[ix] = fma(dt, qdl[d], ql[d]);
       qdn[ix] = fma(dt, acc[d], qdl[d]);
-      snap[(size_t)d * N + w] = ql[d];
-      snap[(size_t)(n + d) * N + w] = qdl[d];
-      snap[(size_t)(2 * n + d) * N + w] = acc[d];
-      if (c_topo.has_limits) snap[(size_t)(3 * n + d) * N + w] = tl[d];
+      if (c_topo.has_limits) {
+        clip[(size_t)d * N + w] = ql[d];
+        clip[(size_t)(n + d) * N + w] = qdl[d];
+        clip[(size_t)(2 * n + d) * N + w] = tl[d];
+      }
     }
   } else {
     forwardDynamics<NB, CHAIN>(
-        st, nb, [&](int d) { return q[vidx(layout, N, n, w, d)]; }, [&](int d) { return qd[vidx(layout, N, n, w, d)]; },
+        sn, nb, [&](int d) { return q[vidx(layout, N, n, w, d)]; }, [&](int d) { return qd[vidx(layout, N, n, w, d)]; },
         [&](int d) { return tau[vidx(layout, N, n, w, d)]; },
-        [&](int d, double a) { snap[(size_t)(2 * n + d) * N + w] = a; });
+        [&](int d, double a) {
+          size_t ix = vidx(layout, N, n, w, d);
+          qdn[ix] = fma(dt, a, qd[ix]);
+        });
 #pragma unroll 1
     for (int d = 0; d < n; d++) {
       size_t ix = vidx(layout, N, n, w, d);
-      double qv = q[ix], qdv = qd[ix], a = snap[(size_t)(2 * n + d) * N + w];
+      double qv = q[ix], qdv = qd[ix];
       qn[ix] = fma(dt, qdv, qv);
-      qdn[ix] = fma(dt, a, qdv);
-      snap[(size_t)d * N + w] = qv;
-      snap[(size_t)(n + d) * N + w] = qdv;
-      if (c_topo.has_limits) snap[(size_t)(3 * n + d) * N + w] = tau[ix];
+      if (c_topo.has_limits) {
+        clip[(size_t)d * N + w] = qv;
+        clip[(size_t)(n + d) * N + w] = qdv;
+        clip[(size_t)(2 * n + d) * N + w] = tau[ix];
+      }
     }
   }
 }
@@ -71,20 +82,17 @@ DDB_DI double clipGrad(double g, double x, double lo, double hi) {
 
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_backward(int N, const double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
+k_backward(int N, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
            double* __restrict__ gq, double* __restrict__ gqd, double* __restrict__ gtau, Limits lim) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  TreeState<NB, CHAIN> st;
-  SV U[NB];
-  double mu[NB];
-  recomputeState<NB, CHAIN>(
-      st, nb, [&](int d) { return snap[(size_t)d * N + w]; }, [&](int d) { return snap[(size_t)(n + d) * N + w]; },
-      [&](int d) { return snap[(size_t)(2 * n + d) * N + w]; });
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  BwdScratch<NB> ws;
+  const double* mu = ws.mu;
   // lambda = dL/dqd'
-  solveInvMass<NB, CHAIN>(st, nb, [&](int d) { return gqdn[vidx(layout, N, n, w, d)]; }, mu, U);
+  solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return gqdn[vidx(layout, N, n, w, d)]; }, ws);
   if (CHAIN) {
 #pragma unroll
     for (int i = 0; i < NB; i++) gtau[vidx(layout, N, n, w, i)] = dt * mu[i];
@@ -93,7 +101,7 @@ k_backward(int N, const double* __restrict__ snap, const double* __restrict__ gq
     for (int i = 0; i < nb; i++)
       if (c_topo.b[i].type != DDB_JOINT_WELD) gtau[vidx(layout, N, n, w, c_topo.b[i].dof)] = dt * mu[i];
   }
-  idAdjoint<NB, CHAIN>(st, nb, U, [&](int d, double dq, double dqd) {
+  idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
     size_t ix = vidx(layout, N, n, w, d);
     double a = gqn[ix], l = gqdn[ix];
     // pos-pos = I, vel-pos = dt I for R^1 joints; pos-vel^T l = -dt dPhi/dq; vel-vel^T l = l - dt dPhi/dqd
@@ -101,12 +109,13 @@ k_backward(int N, const double* __restrict__ snap, const double* __restrict__ gq
     gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
   });
   if (c_topo.has_limits) {
+    const double* clip = clipSection(snap, nb, N);
 #pragma unroll 1
     for (int d = 0; d < n; d++) {
       size_t ix = vidx(layout, N, n, w, d);
-      gq[ix] = clipGrad(gq[ix], snap[(size_t)d * N + w], lim.pos_lo[d], lim.pos_hi[d]);
-      gqd[ix] = clipGrad(gqd[ix], snap[(size_t)(n + d) * N + w], lim.vel_lo[d], lim.vel_hi[d]);
-      gtau[ix] = clipGrad(gtau[ix], snap[(size_t)(3 * n + d) * N + w], lim.frc_lo[d], lim.frc_hi[d]);
+      gq[ix] = clipGrad(gq[ix], clip[(size_t)d * N + w], lim.pos_lo[d], lim.pos_hi[d]);
+      gqd[ix] = clipGrad(gqd[ix], clip[(size_t)(n + d) * N + w], lim.vel_lo[d], lim.vel_hi[d]);
+      gtau[ix] = clipGrad(gtau[ix], clip[(size_t)(2 * n + d) * N + w], lim.frc_lo[d], lim.frc_hi[d]);
     }
   }
 }
@@ -115,22 +124,19 @@ k_backward(int N, const double* __restrict__ snap, const double* __restrict__ gq
 // Outputs are [world][col][row] (column-major per world); NULL pointers are skipped.
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_jacobians(int N, const double* __restrict__ snap, double* __restrict__ posPos, double* __restrict__ posVel,
+k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, double* __restrict__ posVel,
             double* __restrict__ velPos, double* __restrict__ velVel, double* __restrict__ forceVel) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
   const double dt = c_topo.dt;
-  TreeState<NB, CHAIN> st;
-  SV U[NB];
-  double mu[NB];
-  recomputeState<NB, CHAIN>(
-      st, nb, [&](int d) { return snap[(size_t)d * N + w]; }, [&](int d) { return snap[(size_t)(n + d) * N + w]; },
-      [&](int d) { return snap[(size_t)(2 * n + d) * N + w]; });
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  BwdScratch<NB> ws;
+  const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(st, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, mu, U);
+    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
     if (forceVel) {
       if (CHAIN) {
 #pragma unroll
@@ -141,10 +147,12 @@ k_jacobians(int N, const double* __restrict__ snap, double* __restrict__ posPos,
           if (c_topo.b[i].type != DDB_JOINT_WELD) forceVel[base + (size_t)c_topo.b[i].dof * n + j] = dt * mu[i];
       }
     }
-    idAdjoint<NB, CHAIN>(st, nb, U, [&](int d, double dq, double dqd) {
-      if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
-      if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
-    });
+    if (posVel || velVel) {
+      idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
+        if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
+        if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
+      });
+    }
     if (posPos || velPos) {
 #pragma unroll 1
       for (int d = 0; d < n; d++) {
@@ -157,20 +165,17 @@ k_jacobians(int N, const double* __restrict__ snap, double* __restrict__ posPos,
 
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_inv_mass(int N, const double* __restrict__ snap, double* __restrict__ minv) {
+k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
-  TreeState<NB, CHAIN> st;
-  SV U[NB];
-  double mu[NB];
-  recomputeState<NB, CHAIN>(
-      st, nb, [&](int d) { return snap[(size_t)d * N + w]; }, [&](int d) { return snap[(size_t)(n + d) * N + w]; },
-      [&](int d) { return snap[(size_t)(2 * n + d) * N + w]; });
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  BwdScratch<NB> ws;
+  const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(st, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, mu, U);
+    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
     if (CHAIN) {
 #pragma unroll
       for (int i = 0; i < NB; i++) minv[base + (size_t)j * n + i] = mu[i];
