@@ -33,8 +33,8 @@ WORKLOAD = "pendulum5: 65536 five-link revolute pendulums per GPU, no contact (B
 FWD_BYTES = 8 * N_DOFS * 8
 BWD_BYTES = 8 * N_DOFS * 8
 # FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
-FWD_FLOPS = None  # filled from profiles; None -> fp64 roofline omitted
-BWD_FLOPS = None
+FWD_FLOPS = 4639
+BWD_FLOPS = 4242
 
 
 def inputs(N, seed=1234):
