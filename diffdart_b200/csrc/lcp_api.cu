@@ -1,0 +1,87 @@
+// lcp_api.cu — batched boxed-LCP entry points of the C ABI (compiled with -fmad=false, see lcp.cuh).
+#include <cstdio>
+#include "../../include/ddb.h"
+#include "lcp.cuh"
+
+using namespace ddb;
+
+namespace {
+
+// one world per thread; inputs world-major [N][n_max]([n_max]); scratch lane-interleaved per warp
+__global__ void __launch_bounds__(64)
+k_lcp_solve(int N, int nmax, const int* __restrict__ n_rows, const double* __restrict__ A, const double* __restrict__ b,
+            const double* __restrict__ lo, const double* __restrict__ hi, const int* __restrict__ findex, int solver, int early,
+            PgsOptions pgs, double* __restrict__ x, int* __restrict__ ok, double* __restrict__ sd, int* __restrict__ si) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  const int n = n_rows ? n_rows[w] : nmax;
+  if (n <= 0) { if (ok) ok[w] = 1; return; }
+  LcpView v;
+  const size_t warp = w >> 5, lane = w & 31;
+  v.init(sd + warp * lcpScratchDoubles(nmax) * 32 + lane, si + warp * lcpScratchInts(nmax) * 32 + lane, n, nmax);
+  const double* Aw = A + (size_t)w * nmax * nmax;
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) v.Araw(i, j) = Aw[(size_t)i * nmax + j];
+    const size_t ix = (size_t)w * nmax + i;
+    v.b(i) = b[ix]; v.lo(i) = lo[ix]; v.hi(i) = hi[ix]; v.findex(i) = findex[ix];
+    v.x(i) = x[ix];  // PGS warm start (Dantzig zeroes it, lcp.cpp:411)
+  }
+  bool good = (solver == DDB_LCP_DANTZIG) ? dantzigSolve(v, 0, early != 0) : pgsSolve(v, pgs);
+  for (int i = 0; i < n; ++i) x[(size_t)w * nmax + i] = v.x(i);
+  if (ok) ok[w] = good ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(128)
+k_lcp_valid(int N, int nmax, const int* __restrict__ n_rows, const double* __restrict__ A, const double* __restrict__ x,
+            const double* __restrict__ b, const double* __restrict__ lo, const double* __restrict__ hi, const int* __restrict__ findex,
+            int ignoreFriction, int* __restrict__ valid) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  const int n = n_rows ? n_rows[w] : nmax;
+  const double* Aw = A + (size_t)w * nmax * nmax;
+  const size_t o = (size_t)w * nmax;
+  valid[w] = lcpValid(n, [&](int i, int j) { return Aw[(size_t)i * nmax + j]; }, [&](int i) { return x[o + i]; },
+                      [&](int i) { return b[o + i]; }, [&](int i) { return hi[o + i]; }, [&](int i) { return lo[o + i]; },
+                      [&](int i) { return findex[o + i]; }, ignoreFriction != 0) ? 1 : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ddb_lcp_solve(int32_t device, void* stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows, const double* A, const double* b,
+                  const double* lo, const double* hi, const int32_t* findex, int32_t solver, int32_t early_termination, double* x,
+                  int32_t* ok) {
+  if (n_problems < 1 || n_max < 1 || !A || !b || !lo || !hi || !findex || !x) return DDB_ERR_INVALID;
+  if (solver != DDB_LCP_DANTZIG && solver != DDB_LCP_PGS) return DDB_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DDB_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return DDB_ERR_CUDA;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t warps = ((size_t)n_problems + 31) / 32;
+  double* sd = nullptr;
+  int* si = nullptr;
+  if (cudaMallocAsync(&sd, warps * lcpScratchDoubles(n_max) * 32 * sizeof(double), s) != cudaSuccess) return DDB_ERR_CUDA;
+  if (cudaMallocAsync(&si, warps * lcpScratchInts(n_max) * 32 * sizeof(int), s) != cudaSuccess) { cudaFreeAsync(sd, s); return DDB_ERR_CUDA; }
+  // PgsBoxedLcpSolver options as BoxedLcpConstraintSolver sets them (BoxedLcpConstraintSolver.cpp:81-83)
+  PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
+  k_lcp_solve<<<(n_problems + 63) / 64, 64, 0, s>>>(n_problems, n_max, n_rows, A, b, lo, hi, findex, solver, early_termination, pgs, x, ok, sd, si);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(sd, s);
+  cudaFreeAsync(si, s);
+  return e == cudaSuccess ? DDB_OK : DDB_ERR_CUDA;
+}
+
+int ddb_lcp_valid(int32_t device, void* stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows, const double* A, const double* x,
+                  const double* b, const double* lo, const double* hi, const int32_t* findex, int32_t ignore_friction_indices,
+                  int32_t* valid_out) {
+  if (n_problems < 1 || n_max < 1 || !A || !x || !b || !lo || !hi || !findex || !valid_out) return DDB_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DDB_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return DDB_ERR_CUDA;
+  k_lcp_valid<<<(n_problems + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_problems, n_max, n_rows, A, x, b, lo, hi, findex,
+                                                                          ignore_friction_indices, valid_out);
+  return cudaGetLastError() == cudaSuccess ? DDB_OK : DDB_ERR_CUDA;
+}
+
+}  // extern "C"

@@ -179,6 +179,28 @@ int ddb_backward_host(ddb_handle* h, const double* g_q_next, const double* g_qd_
 int ddb_jacobians_host(ddb_handle* h, double* pos_pos, double* pos_vel, double* vel_pos,
                        double* vel_vel, double* force_vel);
 
+/*
+ * Batched boxed LCP  A x = b + w  (lo <= x <= hi, friction rows bounded by hi*x[findex]):
+ * replaces BoxedLcpSolver::solve(n, A, x, b, nub, lo, hi, findex, earlyTermination)
+ * (dart/constraint/BoxedLcpSolver.hpp:92-101) for n_problems independent problems, as
+ * BoxedLcpConstraintSolver calls it (nub = 0; BoxedLcpConstraintSolver.cpp:425-486,499-546).
+ *   DDB_LCP_DANTZIG  DantzigBoxedLcpSolver -> ODE dSolveLCP (dart/external/odelcpsolver/lcp.cpp:780-1114),
+ *                    same pivots and the same floating-point operation order: results are bit-identical.
+ *   DDB_LCP_PGS      PgsBoxedLcpSolver::solve (PgsBoxedLcpSolver.cpp:79-262), options (10000, 1e-10, 1e-8, 1e-8);
+ *                    x_inout is the warm start.
+ * A is [n_problems][n_max][n_max] row-major (only the leading n_rows[i] x n_rows[i] block is read; n_rows may be
+ * NULL = n_max everywhere); b, lo, hi, x are [n_problems][n_max]; ok_out[i] = the solver's bool (may be NULL).
+ */
+enum { DDB_LCP_DANTZIG = 0, DDB_LCP_PGS = 1 };
+int ddb_lcp_solve(int32_t device, void* cuda_stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows_dev,
+                  const double* A_dev, const double* b_dev, const double* lo_dev, const double* hi_dev,
+                  const int32_t* findex_dev, int32_t solver, int32_t early_termination,
+                  double* x_inout_dev, int32_t* ok_out_dev);
+/* LCPUtils::isLCPSolutionValid (dart/constraint/LCPUtils.cpp:12-81, tolerance 1e-5) per problem. */
+int ddb_lcp_valid(int32_t device, void* cuda_stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows_dev,
+                  const double* A_dev, const double* x_dev, const double* b_dev, const double* lo_dev, const double* hi_dev,
+                  const int32_t* findex_dev, int32_t ignore_friction_indices, int32_t* valid_out_dev);
+
 /* FP64 FMA micro-benchmark (8 independent DFMA chains per thread, every SM busy): the measured
    FP64-pipe peak of this GPU in TFLOP/s, the denominator of the FP64 roofline fraction. */
 int ddb_measure_fp64_peak(int32_t device, double* tflops_out);

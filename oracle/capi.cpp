@@ -5,6 +5,7 @@
 #include <vector>
 #include <functional>
 #include "dd_step.hpp"
+#include "dd_lcp.hpp"
 
 using namespace ddo;
 
@@ -148,6 +149,17 @@ void ddo_log_map_rot(const double* R9, double* w) {
   for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) R.m[r][c] = R9[3 * r + c];
   Vec3<double> o = logMapRot(R);
   for (int r = 0; r < 3; r++) w[r] = o[r];
+}
+
+// PGS on one problem: A n x n row-major (copied into the padded layout), x warm start in/out
+int ddo_pgs_solve(int n, const double* A, double* x, const double* b, const double* lo, const double* hi, const int* findex) {
+  int ns = dPad(n);
+  std::vector<double> Ap((size_t)n * ns, 0.0), bb(b, b + n);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Ap[(size_t)i * ns + j] = A[i * n + j];
+  return pgs(n, Ap.data(), x, bb.data(), lo, hi, findex) ? 1 : 0;
+}
+int ddo_lcp_valid(int n, const double* A, const double* x, const double* b, const double* hi, const double* lo, const int* findex, int ignoreFriction) {
+  return lcpValid(n, A, x, b, hi, lo, findex, ignoreFriction != 0) ? 1 : 0;
 }
 
 }  // extern "C"

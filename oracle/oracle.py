@@ -143,6 +143,25 @@ def log_map_rot(R):
     return out
 
 
+def pgs_solve(A, b, lo, hi, findex, x0=None):
+    """CPU restatement of PgsBoxedLcpSolver::solve (one problem). Returns (ok, x)."""
+    n = len(b)
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    x = np.zeros(n) if x0 is None else np.array(x0, dtype=np.float64)
+    b, lo, hi = (np.array(a, dtype=np.float64) for a in (b, lo, hi))
+    fi = np.array(findex, dtype=np.int32)
+    ok = lib().ddo_pgs_solve(n, _ptr(A), _ptr(x), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(C.POINTER(C.c_int)))
+    return bool(ok), x
+
+
+def lcp_valid(A, x, b, lo, hi, findex, ignore_friction=False):
+    """CPU restatement of LCPUtils::isLCPSolutionValid."""
+    n = len(b)
+    A, x, b, lo, hi = (np.ascontiguousarray(a, dtype=np.float64) for a in (A, x, b, lo, hi))
+    fi = np.array(findex, dtype=np.int32)
+    return bool(lib().ddo_lcp_valid(n, _ptr(A), _ptr(x), _ptr(b), _ptr(hi), _ptr(lo), fi.ctypes.data_as(C.POINTER(C.c_int)), int(ignore_friction)))
+
+
 # ---------------------------------------------------------------------------
 # the reference's own Dantzig solver
 # ---------------------------------------------------------------------------
