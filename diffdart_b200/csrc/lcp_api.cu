@@ -2,6 +2,7 @@
 #include <cstdio>
 #include "../../include/ddb.h"
 #include "lcp.cuh"
+#include "collide.cuh"
 
 using namespace ddb;
 
@@ -45,9 +46,41 @@ k_lcp_valid(int N, int nmax, const int* __restrict__ n_rows, const double* __res
                       [&](int i) { return findex[o + i]; }, ignoreFriction != 0) ? 1 : 0;
 }
 
+// one shape pair per thread; out: [N][8][26] doubles (8 vectors, depth, type), counts [N]
+__global__ void __launch_bounds__(128)
+k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict__ size1, const double* __restrict__ T1,
+                const int* __restrict__ shape2, const double* __restrict__ size2, const double* __restrict__ T2, double* __restrict__ out,
+                int* __restrict__ counts) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  Pose a, b;
+  for (int i = 0; i < 9; i++) { a.R[i] = T1[(size_t)w * 12 + i]; b.R[i] = T2[(size_t)w * 12 + i]; }
+  for (int i = 0; i < 3; i++) { a.p[i] = T1[(size_t)w * 12 + 9 + i]; b.p[i] = T2[(size_t)w * 12 + 9 + i]; }
+  ContactPoint c[8];
+  const int n = collidePair(shape1[w], size1 + (size_t)w * 3, a, shape2[w], size2 + (size_t)w * 3, b, c);
+  counts[w] = n;
+  for (int k = 0; k < n; k++) {
+    double* o = out + ((size_t)w * 8 + k) * 26;
+    const double* vs[8] = {c[k].point, c[k].normal, c[k].edgeAClosest, c[k].edgeAFixed, c[k].edgeADir, c[k].edgeBClosest, c[k].edgeBFixed, c[k].edgeBDir};
+    for (int v = 0; v < 8; v++) for (int i = 0; i < 3; i++) o[3 * v + i] = vs[v][i];
+    o[24] = c[k].depth;
+    o[25] = (double)c[k].type;
+  }
+}
+
 }  // namespace
 
 extern "C" {
+
+int ddb_collide_pairs(int32_t device, void* stream, int32_t n_pairs, const int32_t* shape1, const double* size1, const double* T1,
+                      const int32_t* shape2, const double* size2, const double* T2, double* contacts_out, int32_t* counts_out) {
+  if (n_pairs < 1 || !shape1 || !size1 || !T1 || !shape2 || !size2 || !T2 || !contacts_out || !counts_out) return DDB_ERR_INVALID;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return DDB_ERR_NO_DEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return DDB_ERR_CUDA;
+  k_collide_pairs<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(n_pairs, shape1, size1, T1, shape2, size2, T2, contacts_out, counts_out);
+  return cudaGetLastError() == cudaSuccess ? DDB_OK : DDB_ERR_CUDA;
+}
 
 int ddb_lcp_solve(int32_t device, void* stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows, const double* A, const double* b,
                   const double* lo, const double* hi, const int32_t* findex, int32_t solver, int32_t early_termination, double* x,

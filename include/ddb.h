@@ -201,6 +201,18 @@ int ddb_lcp_valid(int32_t device, void* cuda_stream, int32_t n_problems, int32_t
                   const double* A_dev, const double* x_dev, const double* b_dev, const double* lo_dev, const double* hi_dev,
                   const int32_t* findex_dev, int32_t ignore_friction_indices, int32_t* valid_out_dev);
 
+/*
+ * Narrow phase for n_pairs independent shape pairs: replaces dart::collision::collide(o1, o2, result)
+ * (dart/collision/dart/DARTCollide.cpp:4675-5183) for box / sphere shapes — collideBoxBox -> dBoxBox (:713-1427, up to
+ * 8 contacts per pair), collideBoxSphere / collideSphereBox (:1429-1733), collideSphereSphere (:1735-1800).
+ * shape: DDB_SHAPE_*; size [n][3] (box extents / radius in [0]); T [n][12] (R row-major, p).
+ * contacts_out [n][8][26]: point, normal, edgeAClosest, edgeAFixed, edgeADir, edgeBClosest, edgeBFixed, edgeBDir (3 each),
+ * penetrationDepth, ContactType (Contact.hpp:43-80); counts_out [n]. Bit-identical to the reference's box-box.
+ */
+int ddb_collide_pairs(int32_t device, void* cuda_stream, int32_t n_pairs, const int32_t* shape1_dev, const double* size1_dev,
+                      const double* T1_dev, const int32_t* shape2_dev, const double* size2_dev, const double* T2_dev,
+                      double* contacts_out_dev, int32_t* counts_out_dev);
+
 /* FP64 FMA micro-benchmark (8 independent DFMA chains per thread, every SM busy): the measured
    FP64-pipe peak of this GPU in TFLOP/s, the denominator of the FP64 roofline fraction. */
 int ddb_measure_fp64_peak(int32_t device, double* tflops_out);

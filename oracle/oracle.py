@@ -195,3 +195,24 @@ def ref_dantzig(A, b, lo, hi, findex, early_termination=False):
     ok = r.ddref_dantzig_solve(n, _ptr(Ap), _ptr(x), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(C.POINTER(C.c_int)),
                                1 if early_termination else 0)
     return bool(ok), x
+
+
+# ---------------------------------------------------------------------------
+# the reference's own box-box narrow phase (DARTCollide.cpp:49-1427 compiled through a small shim)
+# ---------------------------------------------------------------------------
+BOXBOX_SO = os.path.join(HERE, "_ref", "libboxbox_ref.so")
+_bb = None
+
+
+def ref_collide_box_box(size0, T0, size1, T1):
+    """collideBoxBox of the reference. T: 12 doubles (R row-major, p). Returns an [n, 26] array:
+    point, normal, edgeAClosest, edgeAFixed, edgeADir, edgeBClosest, edgeBFixed, edgeBDir, depth, type."""
+    global _bb
+    if _bb is None:
+        if not os.path.exists(BOXBOX_SO):
+            build()
+        _bb = C.CDLL(BOXBOX_SO)
+    out = np.zeros(26 * 16)
+    a = [np.ascontiguousarray(x, dtype=np.float64) for x in (size0, T0, size1, T1)]
+    n = _bb.ddref_collide_box_box(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(out), 16)
+    return out[:26 * n].reshape(n, 26).copy()
