@@ -120,6 +120,10 @@ def load_library():
     lib.ddb_lcp_solve.restype = C.c_int
     lib.ddb_lcp_valid.argtypes = [C.c_int32, _vp, C.c_int32, C.c_int32] + [_vp] * 7 + [C.c_int32, _vp]
     lib.ddb_lcp_valid.restype = C.c_int
+    lib.ddb_contact_capacity.argtypes = [_vp, _ip, _ip]
+    lib.ddb_contact_capacity.restype = C.c_int
+    lib.ddb_contact_debug_host.argtypes = [_vp, _vp, C.c_int32] + [_vp] * 9
+    lib.ddb_contact_debug_host.restype = C.c_int
     lib.ddb_collide_pairs.argtypes = [C.c_int32, _vp, C.c_int32] + [_vp] * 8
     lib.ddb_collide_pairs.restype = C.c_int
     lib.ddb_measure_fp64_peak.argtypes = [C.c_int32, _dp]
@@ -141,5 +145,5 @@ EXPORTED_SYMBOLS = [
     "ddb_default_params", "ddb_abi_version", "ddb_create", "ddb_destroy", "ddb_last_error", "ddb_num_worlds",
     "ddb_num_dofs", "ddb_forward", "ddb_backward", "ddb_jacobians", "ddb_inv_mass_matrix", "ddb_snapshot_select",
     "ddb_snapshot_current", "ddb_snapshot_reserve", "ddb_forward_host", "ddb_backward_host", "ddb_jacobians_host",
-    "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs",
+    "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs", "ddb_contact_capacity", "ddb_contact_debug_host",
 ]

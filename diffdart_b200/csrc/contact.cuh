@@ -1,0 +1,464 @@
+// contact.cuh — the contact half of World::step for one world per thread (FP64, compiled with -fmad=false).
+// Runs after k_forward has written the step snapshot and the unconstrained velocity update:
+//   collision pass          DARTCollisionDetector::collide all-pairs loop + BodyNodeCollisionFilter + postProcess
+//                           de-duplication at 3e-12 (collision/dart/DARTCollisionDetector.cpp:118-179,349-386;
+//                           collision/CollisionFilter.cpp:105-153); narrow phase in collide.cuh
+//   contact constraints     ConstraintSolver::updateConstraints (constraint/ConstraintSolver.cpp:537-610) and
+//                           ContactConstraint (constraint/ContactConstraint.cpp:66-229,349-455,675-683,716-746)
+//   constrained groups      uniteSkeletons / buildConstrainedGroups (ContactConstraint.cpp:861-889, ConstraintSolver.cpp:718-788)
+//   LCP assembly            impulse tests through the articulated-body quantities of the snapshot
+//                           (BoxedLcpConstraintSolver.cpp:227-328; Skeleton.cpp:4859-4894,4990-4994; BodyNode.cpp:1730-1751,1793-1820)
+//   solver chain            LCPUtils::reduce -> Dantzig -> isLCPSolutionValid -> PGS -> removeFriction + PGS
+//                           (BoxedLcpConstraintSolver.cpp:425-616; LCPUtils.cpp:145-248,347-534)
+//   applying the impulses   ContactConstraint::applyImpulse (:618-672) + Skeleton::computeImpulseForwardDynamics (Skeleton.cpp:5009-5033)
+#pragma once
+#include "dynamics.cuh"
+#include "lcp.cuh"
+#include "collide.cuh"
+
+namespace ddb {
+
+struct ShapeDesc {  // per body collision shape (one ShapeNode per body)
+  int shape, skel, reactive, pad;
+  double friction, restitution;
+  double size[3];
+  double offR[9], offP[3];  // ShapeNode relative transform
+};
+struct ContactTopo {
+  int n_pairs, cmax, kmax, nskel;
+  double clip_depth;
+  int pairA[DDB_MAX_BODIES * 4], pairB[DDB_MAX_BODIES * 4];  // collidable pairs in collision-object order
+  ShapeDesc shape[DDB_MAX_BODIES];
+};
+__constant__ ContactTopo c_ctopo;
+
+// per-world scratch layout (doubles / ints), world-major
+struct ContactLayout {
+  int nb, nd, cmax, kmax;
+  __host__ __device__ size_t oContacts() const { return 0; }                         // [cmax][26]
+  __host__ __device__ size_t oNA() const { return oContacts() + (size_t)cmax * 26; }  // [cmax][3][6]
+  __host__ __device__ size_t oNB() const { return oNA() + (size_t)cmax * 18; }
+  __host__ __device__ size_t oMassed() const { return oNB() + (size_t)cmax * 18; }    // [kmax][nd]
+  __host__ __device__ size_t oA() const { return oMassed() + (size_t)kmax * nd; }     // [kmax][kmax] (per group, n x n packed)
+  __host__ __device__ size_t oB() const { return oA() + (size_t)kmax * kmax; }        // b lo hi x0 x xall: 6 x [kmax]
+  __host__ __device__ size_t oW() const { return oB() + (size_t)6 * kmax; }           // [nb][12] world transforms
+  __host__ __device__ size_t oV() const { return oW() + (size_t)nb * 12; }            // [nb][6] body velocities (pre-constraint)
+  __host__ __device__ size_t oImp() const { return oV() + (size_t)nb * 6; }           // [nb][6] constraint impulses
+  __host__ __device__ size_t oBias() const { return oImp() + (size_t)nb * 6; }        // [nb][6]
+  __host__ __device__ size_t oDelV() const { return oBias() + (size_t)nb * 6; }       // [nb][6]
+  __host__ __device__ size_t oU() const { return oDelV() + (size_t)nb * 6; }          // [nb] + dqd [nd]
+  __host__ __device__ size_t doubles() const { return oU() + (size_t)nb + nd; }
+  // ints: bodyA bodyB dim type group [cmax each], findex keep mapTo [kmax each], misc
+  __host__ __device__ size_t ints() const { return (size_t)5 * cmax + (size_t)3 * kmax + 8; }
+};
+
+struct ContactWork {
+  double* d;
+  int* i;
+  ContactLayout L;
+  DDB_LCP_DI double* contact(int c) const { return d + L.oContacts() + (size_t)c * 26; }
+  DDB_LCP_DI double* NA(int c, int k) const { return d + L.oNA() + ((size_t)c * 3 + k) * 6; }
+  DDB_LCP_DI double* NB(int c, int k) const { return d + L.oNB() + ((size_t)c * 3 + k) * 6; }
+  DDB_LCP_DI double* massed(int row) const { return d + L.oMassed() + (size_t)row * L.nd; }
+  DDB_LCP_DI double* A() const { return d + L.oA(); }
+  DDB_LCP_DI double* b() const { return d + L.oB(); }
+  DDB_LCP_DI double* lo() const { return d + L.oB() + L.kmax; }
+  DDB_LCP_DI double* hi() const { return d + L.oB() + 2 * (size_t)L.kmax; }
+  DDB_LCP_DI double* x0() const { return d + L.oB() + 3 * (size_t)L.kmax; }
+  DDB_LCP_DI double* x() const { return d + L.oB() + 4 * (size_t)L.kmax; }
+  DDB_LCP_DI double* xall() const { return d + L.oB() + 5 * (size_t)L.kmax; }  // multipliers of every row of the world
+  DDB_LCP_DI double* W(int body) const { return d + L.oW() + (size_t)body * 12; }
+  DDB_LCP_DI double* V(int body) const { return d + L.oV() + (size_t)body * 6; }
+  DDB_LCP_DI double* imp(int body) const { return d + L.oImp() + (size_t)body * 6; }
+  DDB_LCP_DI double* bias(int body) const { return d + L.oBias() + (size_t)body * 6; }
+  DDB_LCP_DI double* delV(int body) const { return d + L.oDelV() + (size_t)body * 6; }
+  DDB_LCP_DI double* u() const { return d + L.oU(); }
+  DDB_LCP_DI double* dqd() const { return d + L.oU() + L.nb; }
+  DDB_LCP_DI int* bodyA() const { return i; }
+  DDB_LCP_DI int* bodyB() const { return i + L.cmax; }
+  DDB_LCP_DI int* dim() const { return i + 2 * L.cmax; }
+  DDB_LCP_DI int* groupOf() const { return i + 4 * L.cmax; }
+  DDB_LCP_DI int* findex() const { return i + 5 * L.cmax; }
+  DDB_LCP_DI int* keep() const { return i + 5 * L.cmax + L.kmax; }
+  DDB_LCP_DI int* mapTo() const { return i + 5 * L.cmax + 2 * L.kmax; }
+};
+
+DDB_LCP_DI SV ldSV6(const double* p) { return sv(mk(p[0], p[1], p[2]), mk(p[3], p[4], p[5])); }
+DDB_LCP_DI void stSV6(double* p, SV a) { p[0] = a.w.x; p[1] = a.w.y; p[2] = a.w.z; p[3] = a.v.x; p[4] = a.v.y; p[5] = a.v.z; }
+DDB_LCP_DI double dotSV6(const double* n, const double* v) { return n[0] * v[0] + n[1] * v[1] + n[2] * v[2] + n[3] * v[3] + n[4] * v[4] + n[5] * v[5]; }
+
+// Impulse dynamics: body-frame constraint impulses in cw.imp -> dqd (per dof) and body velocity changes (cw.delV).
+// (Skeleton::updateBiasImpulse + updateVelocityChange; GenericJoint.hpp:2135-2152,2266-2272,2365-2377)
+DDB_LCP_DI void impulsePass(const Snap& sn, const ContactWork& cw, int nb) {
+  for (int i = 0; i < nb; i++) {
+    const double* im = cw.imp(i);
+    double* bi = cw.bias(i);
+    for (int k = 0; k < 6; k++) bi[k] = -im[k];
+  }
+  for (int i = nb - 1; i >= 0; i--) {
+    const DevBody& b = c_topo.b[i];
+    SV bi = ldSV6(cw.bias(i));
+    double ui = 0.0;
+    const bool hasDof = b.type != DDB_JOINT_WELD;
+    if (hasDof) ui = -dot(b.S, bi);
+    cw.u()[i] = ui;
+    if (b.parent >= 0) {
+      SV beta = bi;
+      if (hasDof) {
+        SV ais = sn.ldSV(i, 12);
+        double ps = sn.ld(i, 15).x;
+        beta = bi + (ps * ui) * ais;
+      }
+      SV add = dAdInvT(sn.ldT(i), beta);
+      SV pb = ldSV6(cw.bias(b.parent));
+      stSV6(cw.bias(b.parent), pb + add);
+    }
+  }
+  for (int i = 0; i < nb; i++) {
+    const DevBody& b = c_topo.b[i];
+    SV Vp = svzero();
+    if (b.parent >= 0) Vp = AdInvT(sn.ldT(i), ldSV6(cw.delV(b.parent)));
+    double dq = 0.0;
+    if (b.type != DDB_JOINT_WELD) {
+      SV ais = sn.ldSV(i, 12);
+      double ps = sn.ld(i, 15).x;
+      dq = ps * (cw.u()[i] - dot(ais, Vp));
+      cw.dqd()[b.dof] = dq;
+    }
+    stSV6(cw.delV(i), Vp + dq * b.S);
+  }
+}
+
+// ContactConstraint::getTangentBasisMatrixODE with mFirstFrictionalDirection = z (ContactConstraint.cpp:716-746)
+DDB_LCP_DI void tangentBasis(const double* n, double* t1, double* t2) {
+  auto crossInto = [](const double* a, const double* b, double* c) { c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0]; };
+  const double ez[3] = {0, 0, 1}, ex[3] = {1, 0, 0}, ey[3] = {0, 1, 0};
+  double t[3];
+  crossInto(ez, n, t);
+  if (dot3(t, t) < 1e-12) {
+    crossInto(ex, n, t);
+    if (dot3(t, t) < 1e-12) {
+      crossInto(ey, n, t);
+      if (dot3(t, t) < 1e-12) crossInto(ez, n, t);
+    }
+  }
+  normalize3(t);
+  t1[0] = t[0]; t1[1] = t[1]; t1[2] = t[2];
+  crossInto(n, t, t2);
+}
+
+struct ContactStepOut {
+  int n_contacts, n_rows, n_groups, tier_mask;
+};
+
+// The whole contact stage for one world. qd_pre: velocities after the unconstrained update (in/out: becomes qd').
+// lcp_cache/n_cache: the solver's cached solution mX (in/out). lv: this world's LCP scratch view storage.
+DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, double* lcpD, int* lcpI, const double* qd_pre_in, double* qd_out,
+                                       int layout, int N, int w, double* lcp_cache, int* n_cache, const PgsOptions& pgs) {
+  const int nb = c_topo.nb, nd = c_topo.nd;
+  const ContactTopo& ct = c_ctopo;
+  ContactStepOut out = {0, 0, 0, 0};
+  // ---- world transforms and body velocities under the unconstrained velocity update ----
+  for (int i = 0; i < nb; i++) {
+    const DevBody& b = c_topo.b[i];
+    Xf t = sn.ldT(i);
+    double* Wi = cw.W(i);
+    if (b.parent >= 0) {
+      const double* Wp = cw.W(b.parent);
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) Wi[3 * r + c] = Wp[3 * r] * t.R.m[c] + Wp[3 * r + 1] * t.R.m[3 + c] + Wp[3 * r + 2] * t.R.m[6 + c];
+        Wi[9 + r] = Wp[3 * r] * t.p.x + Wp[3 * r + 1] * t.p.y + Wp[3 * r + 2] * t.p.z + Wp[9 + r];
+      }
+    } else {
+      for (int k = 0; k < 9; k++) Wi[k] = t.R.m[k];
+      Wi[9] = t.p.x; Wi[10] = t.p.y; Wi[11] = t.p.z;
+    }
+    SV Vp = svzero();
+    if (b.parent >= 0) Vp = AdInvT(t, ldSV6(cw.V(b.parent)));
+    double qdi = (b.type != DDB_JOINT_WELD) ? qd_pre_in[vidx(layout, N, nd, w, b.dof)] : 0.0;
+    stSV6(cw.V(i), Vp + qdi * b.S);
+  }
+  // ---- collision pass ----
+  int nc = 0;
+  for (int pi = 0; pi < ct.n_pairs; pi++) {
+    const int a = ct.pairA[pi], bb = ct.pairB[pi];
+    const ShapeDesc& sa = ct.shape[a];
+    const ShapeDesc& sb = ct.shape[bb];
+    Pose Ta, Tb;
+    auto shapePose = [&](const double* Wb, const ShapeDesc& s, Pose& T) {
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) T.R[3 * r + c] = Wb[3 * r] * s.offR[c] + Wb[3 * r + 1] * s.offR[3 + c] + Wb[3 * r + 2] * s.offR[6 + c];
+        T.p[r] = Wb[3 * r] * s.offP[0] + Wb[3 * r + 1] * s.offP[1] + Wb[3 * r + 2] * s.offP[2] + Wb[9 + r];
+      }
+    };
+    shapePose(cw.W(a), sa, Ta);
+    shapePose(cw.W(bb), sb, Tb);
+    ContactPoint pts[8];
+    const int np = collidePair(sa.shape, sa.size, Ta, sb.shape, sb.size, Tb, pts);
+    for (int k = 0; k < np; k++) {
+      const ContactPoint& c = pts[k];
+      bool close = false;
+      for (int t = 0; t < nc && !close; t++) {
+        const double* o = cw.contact(t);
+        double dx = c.point[0] - o[0], dy = c.point[1] - o[1], dz = c.point[2] - o[2];
+        if (sqrt(dx * dx + dy * dy + dz * dz) < 3.0e-12) close = true;
+      }
+      if (close) continue;
+      if (nc >= ct.cmax) continue;  // capacity reached (reported through n_contacts == cmax)
+      double* o = cw.contact(nc);
+      const double* vs[8] = {c.point, c.normal, c.edgeAClosest, c.edgeAFixed, c.edgeADir, c.edgeBClosest, c.edgeBFixed, c.edgeBDir};
+      for (int v = 0; v < 8; v++) for (int x = 0; x < 3; x++) o[3 * v + x] = vs[v][x];
+      o[24] = c.depth; o[25] = (double)c.type;
+      cw.bodyA()[nc] = a; cw.bodyB()[nc] = bb;
+      nc++;
+    }
+  }
+  out.n_contacts = nc;
+  // ---- constraints: contacts with a non-zero normal, depth in [0, clip], at least one reactive body ----
+  int* offs = cw.i + 3 * cw.L.cmax;  // first LCP row of each constraint inside its group
+  for (int c = 0; c < nc; c++) {
+    const double* o = cw.contact(c);
+    const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
+    const bool ra = ct.shape[a].reactive != 0, rb = ct.shape[bb].reactive != 0;
+    const double depth = o[24];
+    cw.dim()[c] = 0;
+    if (dot3(o + 3, o + 3) < 1e-12 || depth < 0.0 || depth > ct.clip_depth || (!ra && !rb)) continue;
+    const double mu = fmin(ct.shape[a].friction, ct.shape[bb].friction);
+    const int dim = mu > 1e-3 ? 3 : 1;
+    cw.dim()[c] = dim;
+    double dirs[3][3];
+    for (int x = 0; x < 3; x++) dirs[0][x] = o[3 + x];
+    if (dim == 3) tangentBasis(dirs[0], dirs[1], dirs[2]);
+    const double* WA = cw.W(a);
+    const double* WB = cw.W(bb);
+    double pA[3], pB[3];
+    {
+      double dA[3] = {o[0] - WA[9], o[1] - WA[10], o[2] - WA[11]}, dB[3] = {o[0] - WB[9], o[1] - WB[10], o[2] - WB[11]};
+      for (int x = 0; x < 3; x++) { pA[x] = colDot(WA, x, dA); pB[x] = colDot(WB, x, dB); }
+    }
+    for (int k = 0; k < dim; k++) {
+      double dA[3], dB[3], nd3[3] = {-dirs[k][0], -dirs[k][1], -dirs[k][2]};
+      for (int x = 0; x < 3; x++) { dA[x] = colDot(WA, x, dirs[k]); dB[x] = colDot(WB, x, nd3); }
+      double* na = cw.NA(c, k);
+      double* nbp = cw.NB(c, k);
+      na[0] = pA[1] * dA[2] - pA[2] * dA[1]; na[1] = pA[2] * dA[0] - pA[0] * dA[2]; na[2] = pA[0] * dA[1] - pA[1] * dA[0];
+      na[3] = dA[0]; na[4] = dA[1]; na[5] = dA[2];
+      nbp[0] = pB[1] * dB[2] - pB[2] * dB[1]; nbp[1] = pB[2] * dB[0] - pB[0] * dB[2]; nbp[2] = pB[0] * dB[1] - pB[1] * dB[0];
+      nbp[3] = dB[0]; nbp[4] = dB[1]; nbp[5] = dB[2];
+    }
+  }
+  // ---- constrained groups: union-find over skeletons, groups numbered by first appearance ----
+  int root[DDB_MAX_BODIES], usize[DDB_MAX_BODIES], groupRoot[DDB_MAX_BODIES];
+  for (int s = 0; s < ct.nskel; s++) { root[s] = s; usize[s] = 1; }
+  for (int c = 0; c < nc; c++) {
+    if (!cw.dim()[c]) continue;
+    const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
+    if (!ct.shape[a].reactive || !ct.shape[bb].reactive) continue;
+    int sa = ct.shape[a].skel, sb = ct.shape[bb].skel;
+    if (sa == sb) continue;
+    while (root[sa] != sa) { root[sa] = root[root[sa]]; sa = root[sa]; }
+    while (root[sb] != sb) { root[sb] = root[root[sb]]; sb = root[sb]; }
+    if (sa == sb) continue;
+    if (usize[sa] < usize[sb]) { root[sa] = sb; usize[sb] += usize[sa]; }
+    else { root[sb] = sa; usize[sa] += usize[sb]; }
+  }
+  int ng = 0;
+  for (int c = 0; c < nc; c++) {
+    cw.groupOf()[c] = -1;
+    if (!cw.dim()[c]) continue;
+    int s = ct.shape[cw.bodyA()[c]].reactive ? ct.shape[cw.bodyA()[c]].skel : ct.shape[cw.bodyB()[c]].skel;
+    while (root[s] != s) s = root[s];
+    int g = -1;
+    for (int x = 0; x < ng; x++) if (groupRoot[x] == s) g = x;
+    if (g < 0) { g = ng; groupRoot[ng++] = s; }
+    cw.groupOf()[c] = g;
+  }
+  out.n_groups = ng;
+  for (int i = 0; i < nb; i++) for (int k = 0; k < 6; k++) cw.imp(i)[k] = 0.0;
+  int groupBase[DDB_MAX_BODIES];
+  int mxSize = *n_cache;  // the solver's mX persists across groups and steps while its size is unchanged
+  int rowsTotal = 0;
+  double* A = cw.A();
+  for (int g = 0; g < ng; g++) {
+    // rows of this group
+    int n = 0;
+    for (int c = 0; c < nc; c++) if (cw.groupOf()[c] == g) { offs[c] = n; n += cw.dim()[c]; }
+    if (rowsTotal + n > ct.kmax) {  // capacity: leave the remaining groups unsolved (reported through n_rows = -1)
+      for (int c = 0; c < nc; c++) if (cw.groupOf()[c] >= g) cw.groupOf()[c] = -1;
+      rowsTotal = -1;
+      break;
+    }
+    double* b = cw.b(); double* lo = cw.lo(); double* hi = cw.hi(); double* x0 = cw.x0(); double* x = cw.x();
+    int* findex = cw.findex();
+    // ---- assembly by impulse tests ----
+    for (int c = 0; c < nc; c++) {
+      if (cw.groupOf()[c] != g) continue;
+      const int o = offs[c], dim = cw.dim()[c];
+      const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
+      const bool ra = ct.shape[a].reactive != 0, rb = ct.shape[bb].reactive != 0;
+      const double mu = fmin(ct.shape[a].friction, ct.shape[bb].friction);
+      const double rest = ct.shape[a].restitution * ct.shape[bb].restitution;
+      for (int k = 0; k < dim; k++) {
+        double rv = 0.0;
+        rv -= dotSV6(cw.NA(c, k), cw.V(a));
+        rv -= dotSV6(cw.NB(c, k), cw.V(bb));
+        b[o + k] = rv;
+        findex[o + k] = -1;
+      }
+      lo[o] = 0.0; hi[o] = INFINITY;
+      if (dim == 3) { for (int t = 1; t < 3; t++) { lo[o + t] = -mu; hi[o + t] = mu; findex[o + t] = o; } }
+      // penetration correction is off by default (World.cpp:85); restitution bounce (ContactConstraint.cpp:395-418)
+      double bouncing = 0.0;
+      if (rest > 1e-3) {
+        double restitutionVel = b[o] * rest;
+        if (restitutionVel > 1e-1) { if (restitutionVel > bouncing) { bouncing = restitutionVel; if (bouncing > 1e+2) bouncing = 1e+2; } }
+      }
+      b[o] += bouncing;
+      for (int k = 0; k < dim; k++) {
+        for (int i = 0; i < nb; i++) for (int z = 0; z < 6; z++) cw.imp(i)[z] = 0.0;
+        if (ra) for (int z = 0; z < 6; z++) cw.imp(a)[z] += cw.NA(c, k)[z];
+        if (rb) for (int z = 0; z < 6; z++) cw.imp(bb)[z] += cw.NB(c, k)[z];
+        for (int z = 0; z < nd; z++) cw.dqd()[z] = 0.0;
+        impulsePass(sn, cw, nb);
+        double* mcol = cw.massed(rowsTotal + o + k);
+        for (int z = 0; z < nd; z++) mcol[z] = cw.dqd()[z];
+        for (int m = c; m < nc; m++) {
+          if (cw.groupOf()[m] != g) continue;
+          const int am = cw.bodyA()[m], bm = cw.bodyB()[m];
+          for (int l = 0; l < cw.dim()[m]; l++) {
+            double v = 0.0;
+            if (ct.shape[am].reactive) v += dotSV6(cw.NA(m, l), cw.delV(am));
+            if (ct.shape[bm].reactive) v += dotSV6(cw.NB(m, l), cw.delV(bm));
+            A[(size_t)(o + k) * n + offs[m] + l] = v;
+          }
+        }
+        for (int m = 0; m < c; m++) {
+          if (cw.groupOf()[m] != g) continue;
+          for (int l = 0; l < cw.dim()[m]; l++) A[(size_t)(o + k) * n + offs[m] + l] = A[(size_t)(offs[m] + l) * n + o + k];
+        }
+      }
+    }
+    // ---- the solver's cached solution ----
+    if (mxSize == n) { for (int k = 0; k < n; k++) x0[k] = lcp_cache[k]; }
+    else { for (int k = 0; k < n; k++) x0[k] = 0.0; }
+    for (int k = 0; k < n; k++) x[k] = x0[k];
+    // ---- LCPUtils::reduce: merge duplicate columns (index map + column scale instead of explicit matrices) ----
+    int* keep = cw.keep();
+    int* mapTo = cw.mapTo();
+    LcpView v;
+    auto isValid = [&]() {
+      return lcpValid(n, [&](int i, int j) { return A[(size_t)i * n + j]; }, [&](int i) { return x[i]; }, [&](int i) { return b[i]; },
+                      [&](int i) { return hi[i]; }, [&](int i) { return lo[i]; }, [&](int i) { return findex[i]; }, false);
+    };
+    auto hasNaN = [&]() { for (int k = 0; k < n; k++) if (isnan(x[k])) return true; return false; };
+    // column scales live in the (unused until the solve) L area of the LCP scratch
+    auto buildReduced = [&](bool frictionless) -> int {
+      int nr = 0;
+      if (frictionless) {
+        for (int k = 0; k < n; k++) { if (findex[k] == -1) { mapTo[k] = nr; keep[nr++] = k; } else mapTo[k] = -1; }
+        v.init(lcpD, lcpI, nr, ct.kmax);
+        for (int a = 0; a < nr; a++) {
+          for (int c2 = 0; c2 < nr; c2++) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]];
+          v.b(a) = b[keep[a]]; v.lo(a) = lo[keep[a]]; v.hi(a) = hi[keep[a]]; v.findex(a) = -1; v.x(a) = x0[keep[a]];
+        }
+        return nr;
+      }
+      nr = n;
+      // scale[] and fidx[] of the reduced problem are kept in the view's d / C arrays until the copy below
+      v.init(lcpD, lcpI, n, ct.kmax);
+      for (int k = 0; k < n; k++) { keep[k] = k; mapTo[k] = k; v.d(k) = 1.0; v.C(k) = findex[k]; }
+      for (;;) {
+        bool found = false;
+        for (int a = 0; a < nr - 1 && !found; a++) {
+          for (int c2 = a + 1; c2 < nr; c2++) {
+            if (v.C(a) != v.C(c2) || hi[keep[a]] != hi[keep[c2]] || lo[keep[a]] != lo[keep[c2]]) continue;
+            if (!(fabs(b[keep[a]] - b[keep[c2]]) < 1e-4)) continue;
+            double sq = 0.0;
+            for (int k = 0; k < nr; k++) {
+              double dl = A[(size_t)keep[k] * n + keep[a]] * v.d(a) - A[(size_t)keep[k] * n + keep[c2]] * v.d(c2);
+              sq += dl * dl;
+            }
+            if (!(sq < 1e-4)) continue;
+            // mergeLCPColumns(a, c2)
+            v.d(a) = v.d(a) * 2.0;
+            for (int k = 0; k < nr; k++) {
+              int f = v.C(k);
+              if (f == c2) v.C(k) = a; else if (f > c2) v.C(k) = f - 1;
+            }
+            for (int k = c2; k < nr - 1; k++) { keep[k] = keep[k + 1]; v.d(k) = v.d(k + 1); v.C(k) = v.C(k + 1); }
+            for (int k = 0; k < n; k++) { if (mapTo[k] == c2) mapTo[k] = a; else if (mapTo[k] > c2) mapTo[k]--; }
+            nr--;
+            found = true;
+            break;
+          }
+        }
+        if (!found) break;
+      }
+      // materialise the reduced problem in the view (scale/fidx are read before their slots are overwritten)
+      v.n = nr; v.nskip = dpad(nr);
+      for (int a = 0; a < nr; a++) { v.tmp(a) = v.d(a); v.findex(a) = v.C(a); }
+      for (int a = 0; a < nr; a++) {
+        for (int c2 = 0; c2 < nr; c2++) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]] * v.tmp(c2);
+        v.b(a) = b[keep[a]]; v.lo(a) = lo[keep[a]]; v.hi(a) = hi[keep[a]]; v.x(a) = x0[keep[a]];
+      }
+      return nr;
+    };
+    auto mapOut = [&]() { for (int k = 0; k < n; k++) x[k] = mapTo[k] >= 0 ? v.x(mapTo[k]) : 0.0; };
+    bool success = false;
+    int tier = 1;
+    {
+      buildReduced(false);
+      success = dantzigSolve(v, 0, true);
+      if (success) { mapOut(); if (!isValid()) success = false; }
+    }
+    if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
+    if (!success) {
+      tier = 2;
+      buildReduced(false);
+      success = pgsSolve(v, pgs);
+      if (success) { mapOut(); if (!isValid()) success = false; }
+    }
+    if (!success) {
+      tier = 3;
+      buildReduced(true);
+      pgsSolve(v, pgs);
+      mapOut();
+    }
+    if (hasNaN()) { for (int k = 0; k < n; k++) x[k] = 0.0; }
+    out.tier_mask |= 1 << tier;
+    // the solution becomes the solver's mX
+    mxSize = n;
+    for (int k = 0; k < n; k++) lcp_cache[k] = x[k];
+    // remember the multipliers of this group's rows for the final impulse accumulation
+    groupBase[g] = rowsTotal;
+    for (int k = 0; k < n; k++) cw.xall()[rowsTotal + k] = x[k];
+    rowsTotal += n;
+  }
+  out.n_rows = rowsTotal;
+  if (rowsTotal < 0) out.tier_mask |= 1 << 8;
+  *n_cache = mxSize;
+  // ---- apply the impulses (ContactConstraint::applyImpulse order: normal, t1, t2 per constraint) ----
+  for (int i = 0; i < nb; i++) for (int z = 0; z < 6; z++) cw.imp(i)[z] = 0.0;
+  bool any = false;
+  for (int c = 0; c < nc; c++) {
+    const int dim = cw.dim()[c];
+    if (!dim || cw.groupOf()[c] < 0) continue;
+    any = true;
+    const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
+    const double* xr = cw.xall() + groupBase[cw.groupOf()[c]] + offs[c];
+    for (int k = 0; k < dim; k++) {
+      const double lam = xr[k];
+      if (ct.shape[a].reactive) for (int z = 0; z < 6; z++) cw.imp(a)[z] += cw.NA(c, k)[z] * lam;
+      if (ct.shape[bb].reactive) for (int z = 0; z < 6; z++) cw.imp(bb)[z] += cw.NB(c, k)[z] * lam;
+    }
+  }
+  for (int z = 0; z < nd; z++) cw.dqd()[z] = 0.0;
+  if (any) impulsePass(sn, cw, nb);
+  for (int z = 0; z < nd; z++) {
+    const size_t ix = vidx(layout, N, nd, w, z);
+    qd_out[ix] = qd_pre_in[ix] + cw.dqd()[z];
+  }
+  return out;
+}
+
+}  // namespace ddb

@@ -1,0 +1,18 @@
+// contact_api.h — host-side interface between the two translation units: ddb_api.cu (dynamics kernels, FMA allowed)
+// and lcp_api.cu (LCP / narrow phase / contact stage, compiled with -fmad=false to keep the reference's operation order).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+namespace ddb {
+struct DevTopo;
+struct ContactTopo;
+// upload the topology of the launching handle into the contact TU's constant memory (stream-ordered)
+cudaError_t contactBindTopology(const DevTopo* topo, const void* ctopo_host, cudaStream_t s);
+size_t contactTopoBytes();
+// scratch sizes per handle
+void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* work_doubles, size_t* work_ints, size_t* lcp_doubles, size_t* lcp_ints);
+// the contact stage after k_forward: qd (in: unconstrained update, out: post-contact) ; lcp_cache [N][kmax], n_cache [N],
+// counts_out [N][4] = n_contacts, n_rows, n_groups, tier mask
+cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd_inout, double* lcp_cache,
+                          int* n_cache, int* counts_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i);
+}  // namespace ddb

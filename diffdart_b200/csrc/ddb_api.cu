@@ -4,11 +4,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
 
 #include "kernels.cuh"
+#include "contact.cuh"
+#include "contact_api.h"
+#include "fold.h"
 
 using namespace ddb;
 
@@ -89,6 +93,12 @@ struct ddb_handle {
   Limits lim{};
   std::string err;
   int64_t launches = 0;
+  // contact stage
+  bool hasContacts = false;
+  ContactTopo ctopo;
+  int cmax = 0, kmax = 0;
+  double *cwork_d = nullptr, *clcp_d = nullptr, *lcp_cache = nullptr;
+  int *cwork_i = nullptr, *clcp_i = nullptr, *n_cache = nullptr, *ccounts = nullptr;
   // host-buffer path
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
@@ -110,129 +120,12 @@ int cudaFail(ddb_handle* h, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cudaFail(h, e__, #call); \
   } while (0)
 
-struct HM3 { double m[9]; };
-HM3 mmul(const HM3& A, const HM3& B) {
-  HM3 r;
-  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
-  return r;
-}
-void mvec(const HM3& A, const double* x, double* y) {
-  for (int i = 0; i < 3; i++) y[i] = A.m[3 * i] * x[0] + A.m[3 * i + 1] * x[1] + A.m[3 * i + 2] * x[2];
-}
-void hcross(const double* a, const double* b, double* c) {
-  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
-}
-
-// Fold T_parentToJoint * J(q) * T_childToJoint^-1 into N0 + c N1 + s N2, P0 + c P1 + s P2.
-int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out, bool& chain, std::string& err) {
-  if (!t || !p || !t->bodies) { err = "null topology/params"; return DDB_ERR_INVALID; }
-  if (t->n_bodies < 1 || t->n_bodies > DDB_MAX_BODIES || t->n_dofs < 0 || t->n_dofs > DDB_MAX_DOFS) {
-    err = "n_bodies/n_dofs out of range"; return DDB_ERR_INVALID;
-  }
-  std::memset(&out, 0, sizeof(out));
-  out.nb = t->n_bodies; out.nd = t->n_dofs; out.layout = p->layout;
-  out.dt = p->time_step;
-  for (int k = 0; k < 3; k++) out.g[k] = p->gravity[k];
-  chain = true;
-  int dofCount = 0;
-  for (int i = 0; i < t->n_bodies; i++) {
-    const ddb_body& s = t->bodies[i];
-    DevBody& b = out.b[i];
-    if (s.parent >= i || s.parent < -1) { err = "bodies must be listed parent-before-child"; return DDB_ERR_INVALID; }
-    if (s.joint_type != DDB_JOINT_WELD && s.joint_type != DDB_JOINT_REVOLUTE && s.joint_type != DDB_JOINT_PRISMATIC) {
-      err = "joint type not supported by the contact-free kernels (weld/revolute/prismatic only)"; return DDB_ERR_INVALID;
-    }
-    int nd = s.joint_type == DDB_JOINT_WELD ? 0 : 1;
-    if (nd && (s.dof_offset < 0 || s.dof_offset >= t->n_dofs)) { err = "dof_offset out of range"; return DDB_ERR_INVALID; }
-    dofCount += nd;
-    b.parent = s.parent; b.type = s.joint_type; b.dof = nd ? s.dof_offset : -1; b.gravity = s.gravity_mode != 0;
-    if (!(nd == 1 && s.dof_offset == i && s.parent == i - 1)) chain = false;
-    HM3 Ra, Rc, Rb;
-    std::memcpy(Ra.m, s.parent_to_joint.r, sizeof(Ra.m));
-    std::memcpy(Rc.m, s.child_to_joint.r, sizeof(Rc.m));
-    const double* pa = s.parent_to_joint.p;
-    const double* pc = s.child_to_joint.p;
-    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Rb.m[3 * r + c] = Rc.m[3 * c + r];  // Rc^T
-    double pb[3];
-    mvec(Rb, pc, pb);
-    for (int k = 0; k < 3; k++) pb[k] = -pb[k];
-    double a[3] = {s.axis[0], s.axis[1], s.axis[2]};
-    double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    if (nd) {
-      if (!(an > 0)) { err = "zero joint axis"; return DDB_ERR_INVALID; }
-      for (int k = 0; k < 3; k++) a[k] /= an;  // Joint::setAxis normalizes
-    }
-    HM3 M0 = mmul(Ra, Rb);
-    double Rapb[3];
-    mvec(Ra, pb, Rapb);
-    if (s.joint_type == DDB_JOINT_REVOLUTE) {
-      double Raa[3], Rbta[3];
-      mvec(Ra, a, Raa);
-      for (int c = 0; c < 3; c++) Rbta[c] = Rb.m[c] * a[0] + Rb.m[3 + c] * a[1] + Rb.m[6 + c] * a[2];  // (a^T Rb)_c
-      HM3 K = {{0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}};
-      HM3 M2 = mmul(mmul(Ra, K), Rb);
-      double adotpb = a[0] * pb[0] + a[1] * pb[1] + a[2] * pb[2];
-      double axpb[3], RaAxpb[3];
-      hcross(a, pb, axpb);
-      mvec(Ra, axpb, RaAxpb);
-      for (int r = 0; r < 3; r++)
-        for (int c = 0; c < 3; c++) {
-          double m1 = Raa[r] * Rbta[c];
-          b.N0[3 * r + c] = m1;
-          b.N1[3 * r + c] = M0.m[3 * r + c] - m1;
-          b.N2[3 * r + c] = M2.m[3 * r + c];
-        }
-      for (int k = 0; k < 3; k++) {
-        b.P0[k] = pa[k] + Raa[k] * adotpb;
-        b.P1[k] = Rapb[k] - Raa[k] * adotpb;
-        b.P2[k] = RaAxpb[k];
-      }
-      // S = AdTAngular(T_c2j, axis) (RevoluteJoint.cpp:140-150)
-      double w[3], v[3];
-      mvec(Rc, a, w);
-      hcross(pc, w, v);
-      b.S.w = V3{w[0], w[1], w[2]};
-      b.S.v = V3{v[0], v[1], v[2]};
-    } else {
-      std::memcpy(b.N0, M0.m, sizeof(M0.m));
-      for (int k = 0; k < 3; k++) b.P0[k] = pa[k] + Rapb[k];
-      if (s.joint_type == DDB_JOINT_PRISMATIC) {
-        double Raa[3], v[3];
-        mvec(Ra, a, Raa);
-        for (int k = 0; k < 3; k++) b.P1[k] = Raa[k];
-        // S = AdTLinear(T_c2j, axis) (PrismaticJoint.cpp:139-150)
-        mvec(Rc, a, v);
-        b.S.w = V3{0, 0, 0};
-        b.S.v = V3{v[0], v[1], v[2]};
-      }
-    }
-    // Inertia::computeSpatialTensor (Inertia.cpp:394-409)
-    const double m = s.mass, cx = s.com[0], cy = s.com[1], cz = s.com[2];
-    b.I.m = m;
-    b.I.h = V3{m * cx, m * cy, m * cz};
-    b.I.J[0] = s.moment[0] + m * (cy * cy + cz * cz);
-    b.I.J[1] = s.moment[1] + m * (cx * cx + cz * cz);
-    b.I.J[2] = s.moment[2] + m * (cx * cx + cy * cy);
-    b.I.J[3] = s.moment[3] - m * cx * cy;
-    b.I.J[4] = s.moment[4] - m * cx * cz;
-    b.I.J[5] = s.moment[5] - m * cy * cz;
-  }
-  if (dofCount != t->n_dofs) { err = "n_dofs does not match the joints"; return DDB_ERR_INVALID; }
-  auto finite = [&](const double* a, double def) {
-    if (!a) return false;
-    for (int i = 0; i < t->n_dofs; i++) if (a[i] != def) return true;
-    return false;
-  };
-  out.has_limits = finite(t->position_lower, -INFINITY) || finite(t->position_upper, INFINITY) || finite(t->velocity_lower, -INFINITY) ||
-                   finite(t->velocity_upper, INFINITY) || finite(t->force_lower, -INFINITY) || finite(t->force_upper, INFINITY);
-  return DDB_OK;
-}
-
 // make this handle's topology the one in constant memory (stream-ordered)
 int bindTopology(ddb_handle* h, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (g_owner[h->device] == h) return DDB_OK;
   DDB_CUDA(h, cudaMemcpyToSymbolAsync(c_topo, &h->topo, sizeof(DevTopo), 0, cudaMemcpyHostToDevice, s));
+  if (h->hasContacts) DDB_CUDA(h, contactBindTopology(&h->topo, &h->ctopo, s));
   // the host copy lives in the handle (pageable): make sure the copy has been staged before anyone frees it
   g_owner[h->device] = h;
   return DDB_OK;
@@ -322,6 +215,12 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
   if (rc != DDB_OK) return rc;
   h->n = h->topo.nd; h->nb = h->topo.nb;
   if (h->n == 0) return fail(h, DDB_ERR_INVALID, "world has no degrees of freedom");
+  {
+    int rc2 = foldContactTopology(topo, params, h->ctopo, h->err);
+    if (rc2 != DDB_OK) return rc2;
+    h->hasContacts = h->ctopo.n_pairs > 0;
+    h->cmax = h->ctopo.cmax; h->kmax = h->ctopo.kmax;
+  }
   // DDB_FORCE_GENERIC=1 routes chains through the generic tree kernels (used by the tests to cover both)
   const char* fg = getenv("DDB_FORCE_GENERIC");
   if (fg && fg[0] == '1') h->chain = false;
@@ -341,6 +240,22 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
     h->lim = Limits{h->lim_dev, h->lim_dev + h->n, h->lim_dev + 2 * h->n, h->lim_dev + 3 * h->n, h->lim_dev + 4 * h->n, h->lim_dev + 5 * h->n};
   }
   DDB_CUDA(h, cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
+  if (h->hasContacts) {
+    size_t wd, wi, ld, li;
+    contactScratchSizes(h->N, h->nb, h->n, h->cmax, h->kmax, &wd, &wi, &ld, &li);
+    DDB_CUDA(h, cudaMalloc(&h->cwork_d, wd * sizeof(double)));
+    DDB_CUDA(h, cudaMalloc(&h->cwork_i, wi * sizeof(int)));
+    DDB_CUDA(h, cudaMalloc(&h->clcp_d, ld * sizeof(double)));
+    DDB_CUDA(h, cudaMalloc(&h->clcp_i, li * sizeof(int)));
+    DDB_CUDA(h, cudaMalloc(&h->lcp_cache, (size_t)h->N * h->kmax * sizeof(double)));
+    DDB_CUDA(h, cudaMalloc(&h->n_cache, (size_t)h->N * sizeof(int)));
+    DDB_CUDA(h, cudaMalloc(&h->ccounts, (size_t)h->N * 4 * sizeof(int)));
+    DDB_CUDA(h, cudaMemset(h->lcp_cache, 0, (size_t)h->N * h->kmax * sizeof(double)));
+    DDB_CUDA(h, cudaMemset(h->n_cache, 0, (size_t)h->N * sizeof(int)));
+    DDB_CUDA(h, cudaMemset(h->ccounts, 0, (size_t)h->N * 4 * sizeof(int)));
+    DDB_CUDA(h, cudaMemset(h->cwork_d, 0, wd * sizeof(double)));
+    DDB_CUDA(h, cudaMemset(h->cwork_i, 0, wi * sizeof(int)));
+  }
   return DDB_OK;
 }
 
@@ -355,6 +270,8 @@ int ddb_destroy(ddb_handle* h) {
   for (double* s : h->slots) if (s) cudaFree(s);
   if (h->lim_dev) cudaFree(h->lim_dev);
   if (h->stage) cudaFree(h->stage);
+  for (void* p : {(void*)h->cwork_d, (void*)h->cwork_i, (void*)h->clcp_d, (void*)h->clcp_i, (void*)h->lcp_cache, (void*)h->n_cache, (void*)h->ccounts})
+    if (p) cudaFree(p);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   delete h;
   return DDB_OK;
@@ -386,7 +303,7 @@ int ddb_snapshot_reserve(ddb_handle* h, int32_t n_slots, int32_t* n_out) {
 }
 
 int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, const double* tau, double* qn, double* qdn,
-                double* /*lcp_cache_inout*/, int32_t* /*n_rows_inout*/, int32_t* /*active_set_out*/, int32_t* /*status_out*/) {
+                double* lcp_cache_inout, int32_t* n_rows_inout, int32_t* /*active_set_out*/, int32_t* status_out) {
   if (!h || !q || !qd || !tau || !qn || !qdn) return fail(h, DDB_ERR_INVALID, "ddb_forward: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
@@ -394,13 +311,60 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
   h->k.fwd(s, h->N, q, qd, tau, qn, qdn, h->slots[h->cur]);
   DDB_CUDA(h, cudaGetLastError());
   h->launches++;
+  if (h->hasContacts) {
+    // collision, contact rows, LCP assembly and solve, impulses: qdn holds the unconstrained update on entry
+    double* cache = lcp_cache_inout ? lcp_cache_inout : h->lcp_cache;
+    int* ncache = n_rows_inout ? n_rows_inout : h->n_cache;
+    DDB_CUDA(h, contactLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], qdn, cache, ncache, h->ccounts,
+                              h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i));
+    h->launches++;
+    if (status_out)
+      DDB_CUDA(h, cudaMemcpy2DAsync(status_out, sizeof(int), h->ccounts + 3, 4 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToDevice, s));
+  }
   h->slotValid[h->cur] = 1;
+  return DDB_OK;
+}
+
+int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t* max_rows) {
+  if (!h) return DDB_ERR_INVALID;
+  if (max_contacts) *max_contacts = h->cmax;
+  if (max_rows) *max_rows = h->kmax;
+  return DDB_OK;
+}
+// Copies the contact-stage results of the last ddb_forward to the host (synchronises the device):
+// counts [N][4] = n_contacts, n_rows, n_groups, solver tier mask (bit 1 Dantzig, 2 PGS, 3 friction dropped, 8 capacity);
+// for one world: contacts [cmax][26] (layout of ddb_collide_pairs), bodies [cmax][2], dims [cmax] (0 = filtered out),
+// the last group's boxed LCP A [n*n] packed, b/lo/hi/x [n] and findex [n]; any pointer may be NULL.
+int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims, double* A,
+                           double* b, double* lo, double* hi, double* x, int32_t* findex) {
+  if (!h || !h->hasContacts) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  DDB_CUDA(h, cudaDeviceSynchronize());
+  if (counts) DDB_CUDA(h, cudaMemcpy(counts, h->ccounts, (size_t)h->N * 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (world < 0 || world >= h->N) return DDB_OK;
+  ContactLayout L{h->nb, h->n, h->cmax, h->kmax};
+  const double* wd = h->cwork_d + (size_t)world * L.doubles();
+  const int* wi = h->cwork_i + (size_t)world * L.ints();
+  const size_t K = h->kmax, Cm = h->cmax;
+  if (contacts) DDB_CUDA(h, cudaMemcpy(contacts, wd + L.oContacts(), Cm * 26 * sizeof(double), cudaMemcpyDeviceToHost));
+  if (bodies) {
+    DDB_CUDA(h, cudaMemcpy2D(bodies, 2 * sizeof(int), wi, sizeof(int), sizeof(int), Cm, cudaMemcpyDeviceToHost));
+    DDB_CUDA(h, cudaMemcpy2D(bodies + 1, 2 * sizeof(int), wi + Cm, sizeof(int), sizeof(int), Cm, cudaMemcpyDeviceToHost));
+  }
+  if (dims) DDB_CUDA(h, cudaMemcpy(dims, wi + 2 * Cm, Cm * sizeof(int), cudaMemcpyDeviceToHost));
+  if (A) DDB_CUDA(h, cudaMemcpy(A, wd + L.oA(), K * K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (b) DDB_CUDA(h, cudaMemcpy(b, wd + L.oB(), K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (lo) DDB_CUDA(h, cudaMemcpy(lo, wd + L.oB() + K, K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (hi) DDB_CUDA(h, cudaMemcpy(hi, wd + L.oB() + 2 * K, K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (x) DDB_CUDA(h, cudaMemcpy(x, wd + L.oB() + 5 * K, K * sizeof(double), cudaMemcpyDeviceToHost));
+  if (findex) DDB_CUDA(h, cudaMemcpy(findex, wi + 5 * Cm, K * sizeof(int), cudaMemcpyDeviceToHost));
   return DDB_OK;
 }
 
 int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau) {
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");
+  if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_backward: the backward pass through contacts is not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
@@ -413,6 +377,7 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
 int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* vp, double* vv, double* fv) {
   if (!h) return DDB_ERR_INVALID;
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_jacobians: no forward pass retained in the current snapshot slot");
+  if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_jacobians: Jacobians through contacts are not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;

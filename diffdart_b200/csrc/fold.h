@@ -1,0 +1,166 @@
+// fold.h — host-side folding of a ddb_topology into the device descriptors (DevTopo for the tree recursions,
+// ContactTopo for the contact stage). Pure C++: shared by ddb_api.cu and the host-emulation tests.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace ddb {
+
+struct HM3 { double m[9]; };
+inline HM3 mmul(const HM3& A, const HM3& B) {
+  HM3 r;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.m[3 * i + j] = A.m[3 * i] * B.m[j] + A.m[3 * i + 1] * B.m[3 + j] + A.m[3 * i + 2] * B.m[6 + j];
+  return r;
+}
+inline void mvec(const HM3& A, const double* x, double* y) {
+  for (int i = 0; i < 3; i++) y[i] = A.m[3 * i] * x[0] + A.m[3 * i + 1] * x[1] + A.m[3 * i + 2] * x[2];
+}
+inline void hcross(const double* a, const double* b, double* c) {
+  c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// Fold T_parentToJoint * J(q) * T_childToJoint^-1 into N0 + c N1 + s N2, P0 + c P1 + s P2.
+inline int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out, bool& chain, std::string& err) {
+  if (!t || !p || !t->bodies) { err = "null topology/params"; return DDB_ERR_INVALID; }
+  if (t->n_bodies < 1 || t->n_bodies > DDB_MAX_BODIES || t->n_dofs < 0 || t->n_dofs > DDB_MAX_DOFS) {
+    err = "n_bodies/n_dofs out of range"; return DDB_ERR_INVALID;
+  }
+  std::memset(&out, 0, sizeof(out));
+  out.nb = t->n_bodies; out.nd = t->n_dofs; out.layout = p->layout;
+  out.dt = p->time_step;
+  for (int k = 0; k < 3; k++) out.g[k] = p->gravity[k];
+  chain = true;
+  int dofCount = 0;
+  for (int i = 0; i < t->n_bodies; i++) {
+    const ddb_body& s = t->bodies[i];
+    DevBody& b = out.b[i];
+    if (s.parent >= i || s.parent < -1) { err = "bodies must be listed parent-before-child"; return DDB_ERR_INVALID; }
+    if (s.joint_type != DDB_JOINT_WELD && s.joint_type != DDB_JOINT_REVOLUTE && s.joint_type != DDB_JOINT_PRISMATIC) {
+      err = "joint type not supported by the contact-free kernels (weld/revolute/prismatic only)"; return DDB_ERR_INVALID;
+    }
+    int nd = s.joint_type == DDB_JOINT_WELD ? 0 : 1;
+    if (nd && (s.dof_offset < 0 || s.dof_offset >= t->n_dofs)) { err = "dof_offset out of range"; return DDB_ERR_INVALID; }
+    dofCount += nd;
+    b.parent = s.parent; b.type = s.joint_type; b.dof = nd ? s.dof_offset : -1; b.gravity = s.gravity_mode != 0;
+    if (!(nd == 1 && s.dof_offset == i && s.parent == i - 1)) chain = false;
+    HM3 Ra, Rc, Rb;
+    std::memcpy(Ra.m, s.parent_to_joint.r, sizeof(Ra.m));
+    std::memcpy(Rc.m, s.child_to_joint.r, sizeof(Rc.m));
+    const double* pa = s.parent_to_joint.p;
+    const double* pc = s.child_to_joint.p;
+    for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) Rb.m[3 * r + c] = Rc.m[3 * c + r];  // Rc^T
+    double pb[3];
+    mvec(Rb, pc, pb);
+    for (int k = 0; k < 3; k++) pb[k] = -pb[k];
+    double a[3] = {s.axis[0], s.axis[1], s.axis[2]};
+    double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    if (nd) {
+      if (!(an > 0)) { err = "zero joint axis"; return DDB_ERR_INVALID; }
+      for (int k = 0; k < 3; k++) a[k] /= an;  // Joint::setAxis normalizes
+    }
+    HM3 M0 = mmul(Ra, Rb);
+    double Rapb[3];
+    mvec(Ra, pb, Rapb);
+    if (s.joint_type == DDB_JOINT_REVOLUTE) {
+      double Raa[3], Rbta[3];
+      mvec(Ra, a, Raa);
+      for (int c = 0; c < 3; c++) Rbta[c] = Rb.m[c] * a[0] + Rb.m[3 + c] * a[1] + Rb.m[6 + c] * a[2];  // (a^T Rb)_c
+      HM3 K = {{0, -a[2], a[1], a[2], 0, -a[0], -a[1], a[0], 0}};
+      HM3 M2 = mmul(mmul(Ra, K), Rb);
+      double adotpb = a[0] * pb[0] + a[1] * pb[1] + a[2] * pb[2];
+      double axpb[3], RaAxpb[3];
+      hcross(a, pb, axpb);
+      mvec(Ra, axpb, RaAxpb);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+          double m1 = Raa[r] * Rbta[c];
+          b.N0[3 * r + c] = m1;
+          b.N1[3 * r + c] = M0.m[3 * r + c] - m1;
+          b.N2[3 * r + c] = M2.m[3 * r + c];
+        }
+      for (int k = 0; k < 3; k++) {
+        b.P0[k] = pa[k] + Raa[k] * adotpb;
+        b.P1[k] = Rapb[k] - Raa[k] * adotpb;
+        b.P2[k] = RaAxpb[k];
+      }
+      // S = AdTAngular(T_c2j, axis) (RevoluteJoint.cpp:140-150)
+      double w[3], v[3];
+      mvec(Rc, a, w);
+      hcross(pc, w, v);
+      b.S.w = V3{w[0], w[1], w[2]};
+      b.S.v = V3{v[0], v[1], v[2]};
+    } else {
+      std::memcpy(b.N0, M0.m, sizeof(M0.m));
+      for (int k = 0; k < 3; k++) b.P0[k] = pa[k] + Rapb[k];
+      if (s.joint_type == DDB_JOINT_PRISMATIC) {
+        double Raa[3], v[3];
+        mvec(Ra, a, Raa);
+        for (int k = 0; k < 3; k++) b.P1[k] = Raa[k];
+        // S = AdTLinear(T_c2j, axis) (PrismaticJoint.cpp:139-150)
+        mvec(Rc, a, v);
+        b.S.w = V3{0, 0, 0};
+        b.S.v = V3{v[0], v[1], v[2]};
+      }
+    }
+    // Inertia::computeSpatialTensor (Inertia.cpp:394-409)
+    const double m = s.mass, cx = s.com[0], cy = s.com[1], cz = s.com[2];
+    b.I.m = m;
+    b.I.h = V3{m * cx, m * cy, m * cz};
+    b.I.J[0] = s.moment[0] + m * (cy * cy + cz * cz);
+    b.I.J[1] = s.moment[1] + m * (cx * cx + cz * cz);
+    b.I.J[2] = s.moment[2] + m * (cx * cx + cy * cy);
+    b.I.J[3] = s.moment[3] - m * cx * cy;
+    b.I.J[4] = s.moment[4] - m * cx * cz;
+    b.I.J[5] = s.moment[5] - m * cy * cz;
+  }
+  if (dofCount != t->n_dofs) { err = "n_dofs does not match the joints"; return DDB_ERR_INVALID; }
+  auto finite = [&](const double* a, double def) {
+    if (!a) return false;
+    for (int i = 0; i < t->n_dofs; i++) if (a[i] != def) return true;
+    return false;
+  };
+  out.has_limits = finite(t->position_lower, -INFINITY) || finite(t->position_upper, INFINITY) || finite(t->velocity_lower, -INFINITY) ||
+                   finite(t->velocity_upper, INFINITY) || finite(t->force_lower, -INFINITY) || finite(t->force_upper, INFINITY);
+  return DDB_OK;
+}
+
+
+// shapes, reactive flags (skeleton has DOFs), collidable pairs in collision-object order, capacities
+inline int foldContactTopology(const ddb_topology* topo, const ddb_params* params, ContactTopo& ct, std::string& err) {
+  const int nb = topo->n_bodies;
+    std::memset(&ct, 0, sizeof(ct));
+    ct.clip_depth = params->contact_clipping_depth;
+    int nskel = 0;
+    for (int i = 0; i < nb; i++) nskel = std::max(nskel, topo->bodies[i].skeleton + 1);
+    if (nskel > DDB_MAX_BODIES) { err = "too many skeletons"; return DDB_ERR_INVALID; }
+    ct.nskel = nskel;
+    std::vector<char> skelHasDof(nskel, 0);
+    for (int i = 0; i < nb; i++) if (topo->bodies[i].joint_type != DDB_JOINT_WELD) skelHasDof[topo->bodies[i].skeleton] = 1;
+    for (int i = 0; i < nb; i++) {
+      const ddb_body& sb = topo->bodies[i];
+      ShapeDesc& sd = ct.shape[i];
+      sd.shape = sb.shape_type; sd.skel = sb.skeleton; sd.reactive = skelHasDof[sb.skeleton];
+      sd.friction = sb.friction; sd.restitution = sb.restitution;
+      for (int k = 0; k < 3; k++) { sd.size[k] = sb.shape_size[k]; sd.offP[k] = sb.shape_offset.p[k]; }
+      for (int k = 0; k < 9; k++) sd.offR[k] = sb.shape_offset.r[k];
+    }
+    int np = 0;
+    for (int i = 0; i < nb; i++)
+      for (int j = i + 1; j < nb; j++) {
+        if (ct.shape[i].shape == DDB_SHAPE_NONE || ct.shape[j].shape == DDB_SHAPE_NONE) continue;
+        if (ct.shape[i].skel == ct.shape[j].skel) continue;              // self-collision checking is off by default
+        if (!ct.shape[i].reactive && !ct.shape[j].reactive) continue;    // such contacts never become active constraints
+        if (np >= DDB_MAX_BODIES * 4) { err = "too many collidable pairs"; return DDB_ERR_INVALID; }
+        ct.pairA[np] = i; ct.pairB[np] = j; np++;
+      }
+    ct.n_pairs = np;
+    int cap = params->reserved[0] > 0 ? params->reserved[0] : 64;  // reserved[0]: max contacts per world
+    ct.cmax = std::min(8 * np, cap);
+    ct.kmax = 3 * ct.cmax;
+  return DDB_OK;
+}
+
+}  // namespace ddb

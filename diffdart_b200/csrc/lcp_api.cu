@@ -1,8 +1,8 @@
 // lcp_api.cu — batched boxed-LCP entry points of the C ABI (compiled with -fmad=false, see lcp.cuh).
 #include <cstdio>
 #include "../../include/ddb.h"
-#include "lcp.cuh"
-#include "collide.cuh"
+#include "contact.cuh"
+#include "contact_api.h"
 
 using namespace ddb;
 
@@ -68,7 +68,49 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
   }
 }
 
+// the contact stage of World::step, one world per thread
+__global__ void __launch_bounds__(64)
+k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
+          int* __restrict__ n_cache, int* __restrict__ counts, double* __restrict__ work_d, int* __restrict__ work_i,
+          double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L};
+  const size_t warp = w >> 5, lane = w & 31;
+  double* ld = lcp_d + warp * lcpScratchDoubles(L.kmax) * 32 + lane;
+  int* li = lcp_i + warp * lcpScratchInts(L.kmax) * 32 + lane;
+  int nc = n_cache[w];
+  ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs);
+  n_cache[w] = nc;
+  counts[4 * w] = o.n_contacts; counts[4 * w + 1] = o.n_rows; counts[4 * w + 2] = o.n_groups; counts[4 * w + 3] = o.tier_mask;
+}
+
 }  // namespace
+
+namespace ddb {
+cudaError_t contactBindTopology(const DevTopo* topo, const void* ctopo_host, cudaStream_t s) {
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_topo, topo, sizeof(DevTopo), 0, cudaMemcpyHostToDevice, s);
+  if (e != cudaSuccess) return e;
+  return cudaMemcpyToSymbolAsync(c_ctopo, ctopo_host, sizeof(ContactTopo), 0, cudaMemcpyHostToDevice, s);
+}
+size_t contactTopoBytes() { return sizeof(ContactTopo); }
+void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, size_t* wi, size_t* ld, size_t* li) {
+  ContactLayout L{nb, nd, cmax, kmax};
+  const size_t warps = ((size_t)N + 31) / 32;
+  *wd = (size_t)N * L.doubles();
+  *wi = (size_t)N * L.ints();
+  *ld = warps * lcpScratchDoubles(kmax) * 32;
+  *li = warps * lcpScratchInts(kmax) * 32;
+}
+cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd, double* lcp_cache,
+                          int* n_cache, int* counts, double* work_d, int* work_i, double* lcp_d, int* lcp_i) {
+  ContactLayout L{nb, nd, cmax, kmax};
+  PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
+  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, work_d, work_i, lcp_d, lcp_i, pgs);
+  return cudaGetLastError();
+}
+}  // namespace ddb
 
 extern "C" {
 

@@ -160,6 +160,17 @@ int ddb_jacobians(ddb_handle* h, void* cuda_stream,
                   double* pos_pos_dev, double* pos_vel_dev, double* vel_pos_dev,
                   double* vel_vel_dev, double* force_vel_dev);
 
+/*
+ * Contact stage (run inside ddb_forward when the topology has collidable pairs): collision detection, contact
+ * constraints, boxed-LCP assembly by impulse tests, reduce -> Dantzig -> validity -> PGS -> friction-free PGS, impulses
+ * (ConstraintSolver::solve, constraint/ConstraintSolver.cpp:386-404; BoxedLcpConstraintSolver.cpp:188-684 without the
+ * gradient-matrix branches). ddb_params.reserved[0] caps the contacts per world (default 64); rows = 3 * contacts.
+ * status_out of ddb_forward = solver tier mask per world (bit 1 Dantzig, 2 PGS, 3 friction dropped, 8 capacity hit).
+ */
+int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t* max_rows);
+int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims,
+                           double* A, double* b, double* lo, double* hi, double* x, int32_t* findex);
+
 /* Replaces BackpropSnapshot::getInvMassMatrix / getMassMatrix helpers
    (python/_diffdart/neural/BackpropSnapshot.cpp:42-146): [N][n][n] col-major. */
 int ddb_inv_mass_matrix(ddb_handle* h, void* cuda_stream, double* minv_dev);

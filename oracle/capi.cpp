@@ -6,6 +6,8 @@
 #include <functional>
 #include "dd_step.hpp"
 #include "dd_lcp.hpp"
+#include "dd_contact.hpp"
+#include <dlfcn.h>
 
 using namespace ddo;
 
@@ -160,6 +162,51 @@ int ddo_pgs_solve(int n, const double* A, double* x, const double* b, const doub
 }
 int ddo_lcp_valid(int n, const double* A, const double* x, const double* b, const double* hi, const double* lo, const int* findex, int ignoreFriction) {
   return lcpValid(n, A, x, b, hi, lo, findex, ignoreFriction != 0) ? 1 : 0;
+}
+
+// ---- contact path ----
+// load the reference's own solvers (oracle/_ref/*.so); returns a bit mask of what was found
+int ddo_load_ref_libs(const char* dantzig_so, const char* boxbox_so) {
+  int mask = 0;
+  if (dantzig_so) { void* h = dlopen(dantzig_so, RTLD_NOW | RTLD_LOCAL); if (h) { refLibs().dantzig = (RefDantzigFn)dlsym(h, "ddref_dantzig_solve"); if (refLibs().dantzig) mask |= 1; } }
+  if (boxbox_so) { void* h = dlopen(boxbox_so, RTLD_NOW | RTLD_LOCAL); if (h) { refLibs().boxbox = (RefBoxBoxFn)dlsym(h, "ddref_collide_box_box"); if (refLibs().boxbox) mask |= 2; } }
+  return mask;
+}
+// One world, World::step with contacts (gradients disabled). kmax: capacity of the per-row outputs.
+// contacts_out [cmax][10]: bodyA bodyB point(3) normal(3) depth type; returns through counts[0..3]: n contacts, n rows, n groups, tier mask
+void ddo_step_contacts(void* h, const double* q, const double* qd, const double* tau, double* lcp_cache, int* n_cache, int kmax, double* qn,
+                       double* qdn, double* pre_vel, int cmax, double* contacts_out, double* A_out, double* b_out, double* lo_out, double* hi_out,
+                       int* findex_out, double* x_out, int* counts) {
+  const Model& M = ((OracleWorld*)h)->M;
+  std::vector<double> cache(lcp_cache, lcp_cache + *n_cache);
+  ContactStepResult R;
+  stepWithContacts(M, q, qd, tau, cache, R);
+  for (int i = 0; i < M.nd; i++) { qn[i] = R.qNext[i]; qdn[i] = R.qdNext[i]; if (pre_vel) pre_vel[i] = R.preConstraintVel[i]; }
+  *n_cache = (int)std::min<size_t>(cache.size(), kmax);
+  for (int i = 0; i < *n_cache; i++) lcp_cache[i] = cache[i];
+  counts[0] = (int)R.contacts.size();
+  for (int k = 0; k < (int)R.contacts.size() && k < cmax && contacts_out; k++) {
+    double* o = contacts_out + 10 * k;
+    const Contact& c = R.contacts[k];
+    o[0] = c.bodyA; o[1] = c.bodyB;
+    for (int x = 0; x < 3; x++) { o[2 + x] = c.point[x]; o[5 + x] = c.normal[x]; }
+    o[8] = c.depth; o[9] = c.type;
+  }
+  int rows = 0, tiers = 0;
+  // groups are concatenated in order; A_out is block diagonal in a kmax x kmax row-major matrix
+  for (const GroupLCP& g : R.groups) {
+    for (int i = 0; i < g.n && rows + i < kmax; i++) {
+      if (A_out) for (int j = 0; j < g.n && rows + j < kmax; j++) A_out[(size_t)(rows + i) * kmax + rows + j] = g.A[(size_t)i * g.n + j];
+      if (b_out) b_out[rows + i] = g.b[i];
+      if (lo_out) lo_out[rows + i] = g.lo[i];
+      if (hi_out) hi_out[rows + i] = g.hi[i];
+      if (findex_out) findex_out[rows + i] = g.findex[i] >= 0 ? g.findex[i] + rows : -1;
+      if (x_out) x_out[rows + i] = g.x[i];
+    }
+    rows += g.n;
+    tiers |= 1 << g.tier;
+  }
+  counts[1] = rows; counts[2] = (int)R.groups.size(); counts[3] = tiers;
 }
 
 }  // extern "C"

@@ -113,6 +113,32 @@ class OracleWorld:
         lib().ddo_body_transforms(self.h, q.shape[0], _ptr(q), _ptr(out))
         return out
 
+    def step_contacts(self, q, qd, tau, lcp_cache=None, kmax=256, cmax=64):
+        """World::step with contacts (gradients disabled) for ONE world. Returns a dict with the next state and the
+        intermediate quantities (contacts, boxed LCP, solution, solver tier mask)."""
+        mask = lib().ddo_load_ref_libs(REF_SO.encode(), BOXBOX_SO.encode())
+        if mask != 3:
+            raise RuntimeError("oracle/_ref libraries missing (mask %d)" % mask)
+        n = self.n
+        q, qd, tau = (np.ascontiguousarray(a, dtype=np.float64).reshape(n) for a in (q, qd, tau))
+        cache = np.zeros(kmax)
+        ncache = C.c_int(0)
+        if lcp_cache is not None:
+            cache[:len(lcp_cache)] = lcp_cache
+            ncache.value = len(lcp_cache)
+        qn, qdn, pre = np.zeros(n), np.zeros(n), np.zeros(n)
+        contacts = np.zeros((cmax, 10))
+        A, b, lo, hi, x = np.zeros((kmax, kmax)), np.zeros(kmax), np.zeros(kmax), np.zeros(kmax), np.zeros(kmax)
+        fi = -np.ones(kmax, dtype=np.int32)
+        counts = np.zeros(4, dtype=np.int32)
+        ipt = C.POINTER(C.c_int)
+        lib().ddo_step_contacts(self.h, _ptr(q), _ptr(qd), _ptr(tau), _ptr(cache), C.byref(ncache), kmax, _ptr(qn), _ptr(qdn), _ptr(pre), cmax,
+                                _ptr(contacts), _ptr(A), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(ipt), _ptr(x), counts.ctypes.data_as(ipt))
+        nc, k = int(counts[0]), int(counts[1])
+        return {"q_next": qn, "qd_next": qdn, "pre_constraint_vel": pre, "contacts": contacts[:nc], "A": A[:k, :k], "b": b[:k], "lo": lo[:k],
+                "hi": hi[:k], "findex": fi[:k], "x": x[:k], "n_groups": int(counts[2]), "tier_mask": int(counts[3]),
+                "lcp_cache": cache[:ncache.value].copy()}
+
     def spatial_inertias(self):
         out = np.empty((self.nb, 6, 6))
         lib().ddo_spatial_inertias(self.h, _ptr(out))
@@ -197,6 +223,7 @@ def ref_dantzig(A, b, lo, hi, findex, early_termination=False):
     return bool(ok), x
 
 
+BOXBOX_SO = os.path.join(HERE, "_ref", "libboxbox_ref.so")
 # ---------------------------------------------------------------------------
 # the reference's own box-box narrow phase (DARTCollide.cpp:49-1427 compiled through a small shim)
 # ---------------------------------------------------------------------------

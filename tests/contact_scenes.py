@@ -1,0 +1,112 @@
+"""Contact scenes built from Revolute / Prismatic / Weld joints (FreeJoint bodies come later): seeded states in which
+contacts exist with depth in (0, 0.03)."""
+import numpy as np
+
+from diffdart_b200 import skeletons
+
+
+def _floor(world, thickness=1.0, mu=1.0, name="floor"):
+    floor = skeletons.Skeleton(name)
+    fb = floor.createWeldJointAndBodyNodePair(None).setTransformFromParentBodyNode(p=[0, 0, -0.5 * thickness])
+    fb.setBoxShape([10, 10, thickness]).setFrictionCoeff(mu)
+    world.addSkeleton(floor)
+
+
+def _xyz_body(world, name, mass=2.0, mu=1.0, box=None, sphere=None, restitution=0.0):
+    """A body that translates along x, y, z (three prismatic joints with light carrier links)."""
+    s = skeletons.Skeleton(name)
+    bx = s.createPrismaticJointAndBodyNodePair(None).setAxis([1, 0, 0]).setMass(1e-3).setMomentOfInertia(1e-3, 1e-3, 1e-3)
+    by = s.createPrismaticJointAndBodyNodePair(bx).setAxis([0, 1, 0]).setMass(1e-3).setMomentOfInertia(1e-3, 1e-3, 1e-3)
+    bz = s.createPrismaticJointAndBodyNodePair(by).setAxis([0, 0, 1]).setMass(mass).setFrictionCoeff(mu).setRestitutionCoeff(restitution)
+    if box is not None:
+        bz.setBoxShape(box)
+    if sphere is not None:
+        bz.setSphereShape(sphere)
+    world.addSkeleton(s)
+
+
+def sliding_box(mu=1.0):
+    """Box sliding on the floor: 4 contacts, 12 rows, sliding friction."""
+    w = skeletons.WorldDescription()
+    _floor(w, mu=mu)
+    _xyz_body(w, "box", box=[1, 1, 1], mu=mu)
+    return w
+
+
+def sliding_box_states(N, seed):
+    rng = np.random.default_rng(seed)
+    q = np.stack([rng.uniform(-1, 1, N), rng.uniform(-1, 1, N), 0.5 - rng.uniform(1e-4, 5e-3, N)], axis=1)
+    qd = np.stack([rng.uniform(-1, 1, N), rng.uniform(-1, 1, N), rng.uniform(-0.5, 0.2, N)], axis=1)
+    tau = rng.uniform(-3, 3, (N, 3))
+    return q, qd, tau
+
+
+def two_box_stack():
+    """Two translating boxes stacked on the floor: one constrained group, 4 + 4 contacts."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    _xyz_body(w, "lower", box=[1, 1, 0.5])
+    _xyz_body(w, "upper", mass=1.0, box=[0.6, 0.8, 0.5])
+    return w
+
+
+def two_box_stack_states(N, seed):
+    rng = np.random.default_rng(seed)
+    pen = lambda: rng.uniform(1e-4, 3e-3, N)
+    z0 = 0.25 - pen()
+    q = np.stack([rng.uniform(-.2, .2, N), rng.uniform(-.2, .2, N), z0,
+                  rng.uniform(-.1, .1, N), rng.uniform(-.05, .05, N), z0 + 0.5 - pen()], axis=1)
+    qd = rng.uniform(-0.3, 0.3, (N, 6))
+    tau = rng.uniform(-1, 1, (N, 6))
+    return q, qd, tau
+
+
+def separate_groups():
+    """Two boxes far apart on the floor (two constrained groups) + a sphere resting on the floor (frictionless)."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    _xyz_body(w, "a", box=[1, 1, 1])
+    _xyz_body(w, "b", box=[0.5, 0.5, 0.5], mass=0.7)
+    _xyz_body(w, "ball", sphere=0.3, mass=0.5, mu=0.0)
+    return w
+
+
+def separate_groups_states(N, seed):
+    rng = np.random.default_rng(seed)
+    pen = lambda: rng.uniform(1e-4, 3e-3, N)
+    q = np.stack([rng.uniform(-3, -2, N), rng.uniform(-1, 1, N), 0.5 - pen(),
+                  rng.uniform(2, 3, N), rng.uniform(-1, 1, N), 0.25 - pen(),
+                  rng.uniform(-.5, .5, N), rng.uniform(3, 4, N), 0.3 - pen()], axis=1)
+    qd = rng.uniform(-0.5, 0.5, (N, 9))
+    tau = rng.uniform(-1, 1, (N, 9))
+    return q, qd, tau
+
+
+def pendulum_on_floor():
+    """Two-link revolute pendulum (y axis) whose tip box touches the floor."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    s = skeletons.Skeleton("pendulum")
+    a = s.createRevoluteJointAndBodyNodePair(None).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, 1.5])
+    a.setLocalCOM([0, 0, -0.4])
+    b = s.createRevoluteJointAndBodyNodePair(a).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, -0.8])
+    b.setLocalCOM([0, 0, -0.3]).setBoxShape([0.2, 0.2, 0.2], p=[0, 0, -0.6])
+    w.addSkeleton(s)
+    return w
+
+
+def pendulum_on_floor_states(N, seed):
+    rng = np.random.default_rng(seed)
+    # both joints near zero: tip box bottom at z = 1.5 - 0.8 - 0.6 - 0.1 = 0.0 -> lower the angles slightly for contact
+    q = rng.uniform(-0.02, 0.02, (N, 2))
+    qd = rng.uniform(-0.5, 0.5, (N, 2))
+    tau = rng.uniform(-1, 1, (N, 2))
+    return q, qd, tau
+
+
+SCENES = {
+    "sliding_box": (sliding_box, sliding_box_states),
+    "two_box_stack": (two_box_stack, two_box_stack_states),
+    "separate_groups": (separate_groups, separate_groups_states),
+    "pendulum_on_floor": (pendulum_on_floor, pendulum_on_floor_states),
+}

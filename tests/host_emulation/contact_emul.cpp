@@ -1,0 +1,42 @@
+// TEST INFRASTRUCTURE ONLY — see cuda_shim.h. Host build of the forward kernel + contact stage (generic tree
+// instantiation) so that the whole contact step can be checked against the oracle on the CPU.
+#include "cuda_shim.h"
+#include <string>
+#include <vector>
+struct dim3_ { int x; };
+static dim3_ blockIdx, threadIdx, blockDim;
+inline void sincos(double x, double* s, double* c);
+#include "kernels_nocuda.cuh"
+#include "contact_nocuda.cuh"
+#include "fold.h"
+using namespace ddb;
+
+extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
+                                 double* lcp_cache, int* n_cache, double* qn, double* qdn, int* counts, double* contacts_out, int* bodies_out,
+                                 int* dims_out, double* A_out, double* b_out, double* x_out, int* caps) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
+  const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
+  caps[0] = cmax; caps[1] = kmax;
+  std::vector<double> snap(snapDoublesPerWorld(nb, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  if (c_ctopo.n_pairs == 0) { counts[0] = counts[1] = counts[2] = counts[3] = 0; return 0; }
+  ContactLayout L{nb, nd, cmax, kmax};
+  std::vector<double> wd(L.doubles(), 0.0), ld(lcpScratchDoubles(kmax) * 32, 0.0);
+  std::vector<int> wi(L.ints(), 0), li(lcpScratchInts(kmax) * 32, 0);
+  Snap sn{reinterpret_cast<double2*>(snap.data()), N, 0};
+  ContactWork cw{wd.data(), wi.data(), L};
+  PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
+  ContactStepOut o = contactStage(sn, cw, ld.data() + 3, li.data() + 3, qdn, qdn, c_topo.layout, N, 0, lcp_cache, n_cache, pgs);
+  counts[0] = o.n_contacts; counts[1] = o.n_rows; counts[2] = o.n_groups; counts[3] = o.tier_mask;
+  for (int c = 0; c < cmax; c++) {
+    for (int k = 0; k < 26; k++) contacts_out[c * 26 + k] = cw.contact(c)[k];
+    bodies_out[2 * c] = cw.bodyA()[c]; bodies_out[2 * c + 1] = cw.bodyB()[c]; dims_out[c] = cw.dim()[c];
+  }
+  for (int k = 0; k < kmax * kmax; k++) A_out[k] = cw.A()[k];
+  for (int k = 0; k < kmax; k++) { b_out[k] = cw.b()[k]; x_out[k] = cw.xall()[k]; }
+  return 0;
+}
