@@ -98,6 +98,25 @@ DDB_LCP_DI void impulsePass(const Snap& sn, const ContactWork& cw, int nb) {
   for (int i = nb - 1; i >= 0; i--) {
     const DevBody& b = c_topo.b[i];
     SV bi = ldSV6(cw.bias(i));
+    if (b.type == DDB_JOINT_FREE) {
+      // u = -S^T bias (6); beta = bias + AIS psi u goes to the parent
+      double u6[6];
+      mulS6T(b, bi, u6);
+      for (int k = 0; k < 6; k++) u6[k] = -u6[k];
+      // keep u in delV (it is rewritten by the downward sweep before anyone reads it)
+      for (int k = 0; k < 6; k++) cw.delV(i)[k] = u6[k];
+      cw.u()[i] = 0.0;
+      if (b.parent >= 0) {
+        double AISm[36], psi6[36], pu[6], av[6];
+        ld36(sn, i, 12, AISm); ld36(sn, i, 30, psi6);
+        for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * u6[l]; pu[k] = acc; }
+        for (int a = 0; a < 6; a++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += AISm[a * 6 + k] * pu[k]; av[a] = acc; }
+        SV add = dAdInvT(sn.ldT(i), bi + sv6(av));
+        SV pb = ldSV6(cw.bias(b.parent));
+        stSV6(cw.bias(b.parent), pb + add);
+      }
+      continue;
+    }
     double ui = 0.0;
     const bool hasDof = b.type != DDB_JOINT_WELD;
     if (hasDof) ui = -dot(b.S, bi);
@@ -118,6 +137,15 @@ DDB_LCP_DI void impulsePass(const Snap& sn, const ContactWork& cw, int nb) {
     const DevBody& b = c_topo.b[i];
     SV Vp = svzero();
     if (b.parent >= 0) Vp = AdInvT(sn.ldT(i), ldSV6(cw.delV(b.parent)));
+    if (b.type == DDB_JOINT_FREE) {
+      double AISm[36], psi6[36], r6[6], dq6[6];
+      ld36(sn, i, 12, AISm); ld36(sn, i, 30, psi6);
+      const double vp[6] = {Vp.w.x, Vp.w.y, Vp.w.z, Vp.v.x, Vp.v.y, Vp.v.z};
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int a = 0; a < 6; a++) acc += AISm[a * 6 + k] * vp[a]; r6[k] = cw.delV(i)[k] - acc; }
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * r6[l]; dq6[k] = acc; cw.dqd()[b.dof + k] = acc; }
+      stSV6(cw.delV(i), Vp + mulS6(b, dq6));
+      continue;
+    }
     double dq = 0.0;
     if (b.type != DDB_JOINT_WELD) {
       SV ais = sn.ldSV(i, 12);
@@ -175,8 +203,14 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     }
     SV Vp = svzero();
     if (b.parent >= 0) Vp = AdInvT(t, ldSV6(cw.V(b.parent)));
-    double qdi = (b.type != DDB_JOINT_WELD) ? qd_pre_in[vidx(layout, N, nd, w, b.dof)] : 0.0;
-    stSV6(cw.V(i), Vp + qdi * b.S);
+    if (b.type == DDB_JOINT_FREE) {
+      double qd6[6];
+      for (int k = 0; k < 6; k++) qd6[k] = qd_pre_in[vidx(layout, N, nd, w, b.dof + k)];
+      stSV6(cw.V(i), Vp + mulS6(b, qd6));
+    } else {
+      double qdi = (b.type != DDB_JOINT_WELD) ? qd_pre_in[vidx(layout, N, nd, w, b.dof)] : 0.0;
+      stSV6(cw.V(i), Vp + qdi * b.S);
+    }
   }
   // ---- collision pass ----
   int nc = 0;

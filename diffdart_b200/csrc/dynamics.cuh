@@ -33,10 +33,15 @@ struct DevBody {
   double P0[3], P1[3], P2[3];
   SV S;   // Joint::getRelativeJacobian() column (body frame, constant)
   RBI I;  // spatial inertia
+  int snapOff, ndof;  // first snapshot pair of this body; joint DOFs (0, 1 or 6)
+  // FreeJoint only (FreeJoint.cpp:673-693): N0/P0 hold T_parentToJoint, N1/P1 hold T_childToJoint^-1 and
+  // S6 = getAdTMatrix(T_childToJoint), row-major 6x6
+  double S6[36];
 };
 
 struct DevTopo {
   int nb, nd, layout, has_limits;
+  int snapPairs, has_free;  // total snapshot pairs per world; any FreeJoint in the tree
   double g[3];
   double dt;
   DevBody b[DDB_MAX_BODIES];
@@ -60,13 +65,18 @@ DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {
 // Keeping these instead of recomputing them moves work from the FP64 pipe (the binding unit)
 // to L2/HBM, which the path barely uses otherwise.
 // ---------------------------------------------------------------------------------------------
+// A FreeJoint body needs 6x6 blocks and uses 56 pairs instead: 0-5 T, 6-8 V, 9-11 A, 12-29 AIS (row-major 6x6),
+// 30-47 psi (6x6), 48-50 qd, 51-53 qdd (u between the sweeps), 54-55 (G, pad).
 constexpr int kSnapPairs = 18;
+constexpr int kSnapPairsFree = 56;
 
 struct Snap {
   double2* base;  // [nb*18][N]
   int N, w;
-  DDB_DI void st(int body, int k, double a, double b) const { base[(size_t)(body * kSnapPairs + k) * N + w] = make_double2(a, b); }
-  DDB_DI double2 ld(int body, int k) const { return __ldg(base + (size_t)(body * kSnapPairs + k) * N + w); }
+  DDB_DI void st(int body, int k, double a, double b) const { base[(size_t)(c_topo.b[body].snapOff + k) * N + w] = make_double2(a, b); }
+  DDB_DI double2 ld(int body, int k) const { return __ldg(base + (size_t)(c_topo.b[body].snapOff + k) * N + w); }
+  // plain (coherent) load: for values written earlier by the same thread in the same kernel
+  DDB_DI double2 ldc(int body, int k) const { return base[(size_t)(c_topo.b[body].snapOff + k) * N + w]; }
   DDB_DI void stSV(int body, int k, SV x) const {
     st(body, k, x.w.x, x.w.y); st(body, k + 1, x.w.z, x.v.x); st(body, k + 2, x.v.y, x.v.z);
   }
@@ -107,6 +117,117 @@ DDB_DI Xf jointTransform(const DevBody& b, double qi) {
   return t;
 }
 
+// ---- FreeJoint pieces (generic instantiation only) ----
+// math::expMapRot (Geometry.cpp:471-487): second-order Taylor below |q| = 1e-3
+DDB_DI M3 expMapRot(V3 q) {
+  const double theta = sqrt(dot(q, q));
+  M3 K; K.m[0] = 0; K.m[1] = -q.z; K.m[2] = q.y; K.m[3] = q.z; K.m[4] = 0; K.m[5] = -q.x; K.m[6] = -q.y; K.m[7] = q.x; K.m[8] = 0;
+  M3 K2 = mul(K, K);
+  double a, b;
+  if (theta < 1.0e-3) { a = 1.0; b = 0.5; }
+  else { a = sin(theta) / theta; b = (1.0 - cos(theta)) / (theta * theta); }
+  M3 R;
+#pragma unroll
+  for (int i = 0; i < 9; i++) R.m[i] = ((i % 4 == 0) ? 1.0 : 0.0) + a * K.m[i] + b * K2.m[i];
+  return R;
+}
+// math::logMap(R) = AngleAxis(R).angle * axis, through Eigen's Quaternion(Matrix3) (Geometry.cpp:610-650)
+DDB_DI V3 logMapRot(const M3& M) {
+  double q[4];
+  double t = M.m[0] + M.m[4] + M.m[8];
+  if (t > 0.0) {
+    t = sqrt(t + 1.0);
+    q[3] = 0.5 * t;
+    t = 0.5 / t;
+    q[0] = (M.m[7] - M.m[5]) * t; q[1] = (M.m[2] - M.m[6]) * t; q[2] = (M.m[3] - M.m[1]) * t;
+  } else {
+    int i = 0;
+    if (M.m[4] > M.m[0]) i = 1;
+    if (M.m[8] > M.m[4 * i]) i = 2;
+    const int j = (i + 1) % 3, k = (j + 1) % 3;
+    t = sqrt(M.m[4 * i] - M.m[4 * j] - M.m[4 * k] + 1.0);
+    q[i] = 0.5 * t;
+    t = 0.5 / t;
+    q[3] = (M.m[3 * k + j] - M.m[3 * j + k]) * t;
+    q[j] = (M.m[3 * j + i] + M.m[3 * i + j]) * t;
+    q[k] = (M.m[3 * k + i] + M.m[3 * i + k]) * t;
+  }
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+  if (n != 0.0) {
+    const double angle = 2.0 * atan2(n, fabs(q[3]));
+    if (q[3] < 0.0) n = -n;
+    return mk(angle * (q[0] / n), angle * (q[1] / n), angle * (q[2] / n));
+  }
+  return mk(0, 0, 0);
+}
+DDB_DI Xf mulXf(const Xf& A, const Xf& B) { Xf r; r.R = mul(A.R, B.R); r.p = mul(A.R, B.p) + A.p; return r; }
+DDB_DI Xf freeJointTransform(const DevBody& b, const double* q6) {
+  Xf A, J, Bt;
+#pragma unroll
+  for (int k = 0; k < 9; k++) { A.R.m[k] = b.N0[k]; Bt.R.m[k] = b.N1[k]; }
+  A.p = mk(b.P0[0], b.P0[1], b.P0[2]);
+  Bt.p = mk(b.P1[0], b.P1[1], b.P1[2]);
+  J.R = expMapRot(mk(q6[0], q6[1], q6[2]));
+  J.p = mk(q6[3], q6[4], q6[5]);
+  return mulXf(mulXf(A, J), Bt);
+}
+DDB_DI SV mulS6(const DevBody& b, const double* x6) {  // S6 * x
+  double r[6];
+#pragma unroll
+  for (int a = 0; a < 6; a++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) acc += b.S6[a * 6 + k] * x6[k];
+    r[a] = acc;
+  }
+  return sv(mk(r[0], r[1], r[2]), mk(r[3], r[4], r[5]));
+}
+DDB_DI void mulS6T(const DevBody& b, SV f, double* out6) {  // S6^T * f
+  const double fv[6] = {f.w.x, f.w.y, f.w.z, f.v.x, f.v.y, f.v.z};
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    double acc = 0.0;
+#pragma unroll
+    for (int a = 0; a < 6; a++) acc += b.S6[a * 6 + k] * fv[a];
+    out6[k] = acc;
+  }
+}
+// inverse of a symmetric positive definite 6x6 (stands in for math::inverse<SE3Space>: ldlt().solve(I))
+DDB_DI void spdInverse6(const double* Am, double* out) {
+  double L[36], D[6];
+  for (int j = 0; j < 6; j++) {
+    double d = Am[j * 6 + j];
+    for (int k = 0; k < j; k++) d -= L[j * 6 + k] * L[j * 6 + k] * D[k];
+    D[j] = d;
+    for (int i = j + 1; i < 6; i++) {
+      double sacc = Am[i * 6 + j];
+      for (int k = 0; k < j; k++) sacc -= L[i * 6 + k] * L[j * 6 + k] * D[k];
+      L[i * 6 + j] = sacc / d;
+    }
+  }
+  for (int c = 0; c < 6; c++) {
+    double y[6];
+    for (int i = 0; i < 6; i++) { double sacc = (i == c) ? 1.0 : 0.0; for (int k = 0; k < i; k++) sacc -= L[i * 6 + k] * y[k]; y[i] = sacc; }
+    for (int i = 0; i < 6; i++) y[i] /= D[i];
+    for (int i = 5; i >= 0; i--) { double sacc = y[i]; for (int k = i + 1; k < 6; k++) sacc -= L[k * 6 + i] * y[k]; y[i] = sacc; }
+    for (int i = 0; i < 6; i++) out[i * 6 + c] = y[i];
+  }
+}
+// 6-vectors in the snapshot: three pairs starting at pair k
+DDB_DI void st6(const Snap& sn, int body, int k, const double* x) { sn.st(body, k, x[0], x[1]); sn.st(body, k + 1, x[2], x[3]); sn.st(body, k + 2, x[4], x[5]); }
+DDB_DI void ld6c(const Snap& sn, int body, int k, double* x) {
+  double2 a = sn.ldc(body, k), b = sn.ldc(body, k + 1), c = sn.ldc(body, k + 2);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
+}
+DDB_DI void ld6(const Snap& sn, int body, int k, double* x) {
+  double2 a = sn.ld(body, k), b = sn.ld(body, k + 1), c = sn.ld(body, k + 2);
+  x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
+}
+DDB_DI void st36(const Snap& sn, int body, int k, const double* m) { for (int i = 0; i < 18; i++) sn.st(body, k + i, m[2 * i], m[2 * i + 1]); }
+DDB_DI void ld36c(const Snap& sn, int body, int k, double* m) { for (int i = 0; i < 18; i++) { double2 a = sn.ldc(body, k + i); m[2 * i] = a.x; m[2 * i + 1] = a.y; } }
+DDB_DI void ld36(const Snap& sn, int body, int k, double* m) { for (int i = 0; i < 18; i++) { double2 a = sn.ld(body, k + i); m[2 * i] = a.x; m[2 * i + 1] = a.y; } }
+DDB_DI SV sv6(const double* x) { return sv(mk(x[0], x[1], x[2]), mk(x[3], x[4], x[5])); }
+
 // ---------------------------------------------------------------------------------------------
 // Forward dynamics (Featherstone ABA in body frames, d = k = 0) + snapshot.
 //   sweep 1 root->leaves: T_i, V_i, G_i
@@ -133,11 +254,23 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
     const bool d = TS::hasDof(i);
-    const double qi = d ? qOf(TS::dofOf(i)) : 0.0, qdi = d ? qdOf(TS::dofOf(i)) : 0.0;
-    Xf t = jointTransform(b, qi);
+    const bool isFree = !CHAIN && b.type == DDB_JOINT_FREE;
+    Xf t;
+    SV Sq;
+    if (isFree) {
+      double q6[6], qd6[6];
+      for (int k = 0; k < 6; k++) { q6[k] = qOf(b.dof + k); qd6[k] = qdOf(b.dof + k); }
+      t = freeJointTransform(b, q6);
+      Sq = mulS6(b, qd6);
+      qdv[i] = 0.0;
+      st6(sn, i, 48, qd6);
+    } else {
+      const double qi = d ? qOf(TS::dofOf(i)) : 0.0, qdi = d ? qdOf(TS::dofOf(i)) : 0.0;
+      t = jointTransform(b, qi);
+      qdv[i] = qdi;
+      Sq = qdi * b.S;
+    }
     T[i] = t;
-    qdv[i] = qdi;
-    SV Sq = qdi * b.S;
     V[i] = (p >= 0) ? AdInvT(t, V[p]) + Sq : Sq;
     V3 gp = (p >= 0) ? G[p] : mk(c_topo.g[0], c_topo.g[1], c_topo.g[2]);
     G[i] = mulT(t.R, gp);
@@ -152,6 +285,39 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
+    if (!CHAIN && b.type == DDB_JOINT_FREE) {
+      // 6-DOF joint: AIS = IA S (6x6), psi = (S^T IA S)^-1, u = tau - S^T (IA eta + bias); a free joint transmits
+      // only beta = bias + IA (eta + S psi u) to its parent and no articulated inertia (IA - AIS psi AIS^T = 0)
+      double qd6[6], AISm[36], M6[36], psi6[36], u6[6], pu[6];
+      ld6c(sn, i, 48, qd6);
+      SV Sq = mulS6(b, qd6);
+      SV eta = ad(V[i], Sq);
+      for (int k = 0; k < 6; k++) {
+        double col[6];
+        for (int a = 0; a < 6; a++) col[a] = b.S6[a * 6 + k];
+        SV c = mul(IA[i], sv6(col));
+        AISm[0 * 6 + k] = c.w.x; AISm[1 * 6 + k] = c.w.y; AISm[2 * 6 + k] = c.w.z; AISm[3 * 6 + k] = c.v.x; AISm[4 * 6 + k] = c.v.y; AISm[5 * 6 + k] = c.v.z;
+      }
+      for (int k = 0; k < 6; k++)
+        for (int l = 0; l < 6; l++) { double acc = 0.0; for (int a = 0; a < 6; a++) acc += b.S6[a * 6 + k] * AISm[a * 6 + l]; M6[k * 6 + l] = acc; }
+      spdInverse6(M6, psi6);
+      SV bf = mul(IA[i], eta) + bias[i];
+      double sb[6];
+      mulS6T(b, bf, sb);
+      for (int k = 0; k < 6; k++) u6[k] = tauOf(b.dof + k) - sb[k];
+      st36(sn, i, 12, AISm);
+      st36(sn, i, 30, psi6);
+      st6(sn, i, 51, u6);
+      AIS[i] = svzero(); psi[i] = 0.0; u[i] = 0.0;
+      if (p >= 0) {
+        for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * u6[l]; pu[k] = acc; }
+        double av[6];
+        for (int a = 0; a < 6; a++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += AISm[a * 6 + k] * pu[k]; av[a] = acc; }
+        SV beta = bias[i] + mul(IA[i], eta) + sv6(av);
+        bias[p] = bias[p] + dAdInvT(T[i], beta);
+      }
+      return;
+    }
     SV eta = ad(V[i], qdv[i] * b.S);  // partial acceleration (GenericJoint.hpp:1740-1750, dS = 0)
     SV ais = svzero();
     double ps = 0.0, ui = 0.0;
@@ -179,6 +345,19 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
     SV Ap = (p >= 0) ? AdInvT(T[i], A[p]) : svzero();
+    if (!CHAIN && b.type == DDB_JOINT_FREE) {
+      double AISm[36], psi6[36], u6[6], qd6[6], r6[6], acc6[6];
+      ld36c(sn, i, 12, AISm); ld36c(sn, i, 30, psi6); ld6c(sn, i, 51, u6); ld6c(sn, i, 48, qd6);
+      const double ap[6] = {Ap.w.x, Ap.w.y, Ap.w.z, Ap.v.x, Ap.v.y, Ap.v.z};
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int a = 0; a < 6; a++) acc += AISm[a * 6 + k] * ap[a]; r6[k] = u6[k] - acc; }
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * r6[l]; acc6[k] = acc; store(b.dof + k, acc); }
+      A[i] = Ap + mulS6(b, acc6) + ad(V[i], mulS6(b, qd6));
+      sn.stSV(i, 9, A[i]);
+      st6(sn, i, 51, acc6);
+      sn.st(i, 54, G[i].x, G[i].y);
+      sn.st(i, 55, G[i].z, 0.0);
+      return;
+    }
     double acc = 0.0;
     if (TS::hasDof(i)) {
       // qdd = psi (u - (IA S)^T AdInvT(T, A_parent))   (GenericJoint.hpp:2316-2327)

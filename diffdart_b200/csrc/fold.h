@@ -38,11 +38,15 @@ inline int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out
     const ddb_body& s = t->bodies[i];
     DevBody& b = out.b[i];
     if (s.parent >= i || s.parent < -1) { err = "bodies must be listed parent-before-child"; return DDB_ERR_INVALID; }
-    if (s.joint_type != DDB_JOINT_WELD && s.joint_type != DDB_JOINT_REVOLUTE && s.joint_type != DDB_JOINT_PRISMATIC) {
-      err = "joint type not supported by the contact-free kernels (weld/revolute/prismatic only)"; return DDB_ERR_INVALID;
+    if (s.joint_type != DDB_JOINT_WELD && s.joint_type != DDB_JOINT_REVOLUTE && s.joint_type != DDB_JOINT_PRISMATIC && s.joint_type != DDB_JOINT_FREE) {
+      err = "unknown joint type"; return DDB_ERR_INVALID;
     }
-    int nd = s.joint_type == DDB_JOINT_WELD ? 0 : 1;
-    if (nd && (s.dof_offset < 0 || s.dof_offset >= t->n_dofs)) { err = "dof_offset out of range"; return DDB_ERR_INVALID; }
+    int nd = s.joint_type == DDB_JOINT_WELD ? 0 : (s.joint_type == DDB_JOINT_FREE ? 6 : 1);
+    b.ndof = nd;
+    b.snapOff = out.snapPairs;
+    out.snapPairs += s.joint_type == DDB_JOINT_FREE ? kSnapPairsFree : kSnapPairs;
+    if (s.joint_type == DDB_JOINT_FREE) out.has_free = 1;
+    if (nd && (s.dof_offset < 0 || s.dof_offset + nd > t->n_dofs)) { err = "dof_offset out of range"; return DDB_ERR_INVALID; }
     dofCount += nd;
     b.parent = s.parent; b.type = s.joint_type; b.dof = nd ? s.dof_offset : -1; b.gravity = s.gravity_mode != 0;
     if (!(nd == 1 && s.dof_offset == i && s.parent == i - 1)) chain = false;
@@ -57,14 +61,30 @@ inline int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out
     for (int k = 0; k < 3; k++) pb[k] = -pb[k];
     double a[3] = {s.axis[0], s.axis[1], s.axis[2]};
     double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
-    if (nd) {
+    if (nd == 1) {
       if (!(an > 0)) { err = "zero joint axis"; return DDB_ERR_INVALID; }
       for (int k = 0; k < 3; k++) a[k] /= an;  // Joint::setAxis normalizes
+    }
+    if (s.joint_type == DDB_JOINT_FREE) {
+      // T = T_p2j * [expMapRot(q0..2) | q3..5] * T_c2j^-1 (FreeJoint.cpp:673-683); S = getAdTMatrix(T_c2j) (:686-693)
+      std::memcpy(b.N0, Ra.m, sizeof(Ra.m));
+      std::memcpy(b.N1, Rb.m, sizeof(Rb.m));
+      for (int k = 0; k < 3; k++) { b.P0[k] = pa[k]; b.P1[k] = pb[k]; }
+      HM3 P = {{0, -pc[2], pc[1], pc[2], 0, -pc[0], -pc[1], pc[0], 0}};
+      HM3 PR = mmul(P, Rc);
+      for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 3; c++) {
+          b.S6[r * 6 + c] = Rc.m[3 * r + c];
+          b.S6[r * 6 + 3 + c] = 0.0;
+          b.S6[(3 + r) * 6 + c] = PR.m[3 * r + c];
+          b.S6[(3 + r) * 6 + 3 + c] = Rc.m[3 * r + c];
+        }
     }
     HM3 M0 = mmul(Ra, Rb);
     double Rapb[3];
     mvec(Ra, pb, Rapb);
-    if (s.joint_type == DDB_JOINT_REVOLUTE) {
+    if (s.joint_type == DDB_JOINT_FREE) {
+    } else if (s.joint_type == DDB_JOINT_REVOLUTE) {
       double Raa[3], Rbta[3];
       mvec(Ra, a, Raa);
       for (int c = 0; c < 3; c++) Rbta[c] = Rb.m[c] * a[0] + Rb.m[3 + c] * a[1] + Rb.m[6 + c] * a[2];  // (a^T Rb)_c

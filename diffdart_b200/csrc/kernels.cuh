@@ -15,9 +15,9 @@ struct Limits {  // device arrays of length n (valid only when c_topo.has_limits
 };
 
 // doubles per world in one snapshot slot
-__host__ __device__ inline size_t snapDoublesPerWorld(int nb, int n, bool limits) { return (size_t)2 * kSnapPairs * nb + (limits ? 3 * n : 0); }
+__host__ __device__ inline size_t snapDoublesPerWorld(int snapPairs, int n, bool limits) { return (size_t)2 * snapPairs + (limits ? 3 * n : 0); }
 // the clip section (q, qd, tau as [3n][N]) sits behind the per-body pairs
-DDB_DI double* clipSection(double* snap, int nb, int N) { return snap + (size_t)2 * kSnapPairs * nb * N; }
+DDB_DI double* clipSection(double* snap, int /*nb*/, int N) { return snap + (size_t)2 * c_topo.snapPairs * N; }
 
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
@@ -68,6 +68,23 @@ k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, co
         clip[(size_t)d * N + w] = qv;
         clip[(size_t)(n + d) * N + w] = qdv;
         clip[(size_t)(2 * n + d) * N + w] = tau[ix];
+      }
+    }
+    if (c_topo.has_free) {
+      // FreeJoint::integratePositionsExplicit (FreeJoint.cpp:596-601): Q+ = Q * [expMapRot(w dt) | v dt], q+ = [logMap(R+); p+]
+#pragma unroll 1
+      for (int i = 0; i < nb; i++) {
+        const DevBody& b = c_topo.b[i];
+        if (b.type != DDB_JOINT_FREE) continue;
+        double p6[6], v6[6];
+        for (int k = 0; k < 6; k++) { size_t ix = vidx(layout, N, n, w, b.dof + k); p6[k] = q[ix]; v6[k] = qd[ix]; }
+        Xf Q, D;
+        Q.R = expMapRot(mk(p6[0], p6[1], p6[2])); Q.p = mk(p6[3], p6[4], p6[5]);
+        D.R = expMapRot(mk(v6[0] * dt, v6[1] * dt, v6[2] * dt)); D.p = mk(v6[3] * dt, v6[4] * dt, v6[5] * dt);
+        Xf Qn = mulXf(Q, D);
+        V3 lw = logMapRot(Qn.R);
+        const double o6[6] = {lw.x, lw.y, lw.z, Qn.p.x, Qn.p.y, Qn.p.z};
+        for (int k = 0; k < 6; k++) qn[vidx(layout, N, n, w, b.dof + k)] = o6[k];
       }
     }
   }

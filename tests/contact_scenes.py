@@ -104,7 +104,45 @@ def pendulum_on_floor_states(N, seed):
     return q, qd, tau
 
 
+def box_stack(n=5):
+    """BASELINE config 3: examples/box_stacking — welded floor + n FreeJoint boxes 1x1x0.5, mu = 1."""
+    return skeletons.create_box_stack(n)
+
+
+def box_stack_states(N, seed, n=5):
+    """resting stack with 1 mm overlap per interface, x,y ~ U(-0.05,0.05), yaw ~ U(-0.1,0.1),
+    qd ~ U(-0.1,0.1), tau = 0. FreeJoint coordinates are [logMap(R); p]."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 6 * n))
+    for i in range(n):
+        q[:, 6 * i + 2] = rng.uniform(-0.1, 0.1, N)
+        q[:, 6 * i + 3] = rng.uniform(-0.05, 0.05, N)
+        q[:, 6 * i + 4] = rng.uniform(-0.05, 0.05, N)
+        q[:, 6 * i + 5] = 0.25 + 0.5 * i - 1e-3 * (i + 1)
+    qd = rng.uniform(-0.1, 0.1, (N, 6 * n))
+    tau = np.zeros((N, 6 * n))
+    return q, qd, tau
+
+
+def free_box_on_floor():
+    """One FreeJoint box dropped on the floor at an arbitrary small tilt (vertex / edge / face contacts)."""
+    return skeletons.create_box_stack(1)
+
+
+def free_box_on_floor_states(N, seed):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 6))
+    q[:, 0:3] = rng.uniform(-0.05, 0.05, (N, 3))
+    q[:, 3:5] = rng.uniform(-1, 1, (N, 2))
+    q[:, 5] = 0.25 + rng.uniform(-2e-3, 2e-2, N)
+    qd = rng.uniform(-0.5, 0.5, (N, 6))
+    tau = rng.uniform(-1, 1, (N, 6))
+    return q, qd, tau
+
+
 SCENES = {
+    "box_stack": (box_stack, box_stack_states),
+    "free_box_on_floor": (free_box_on_floor, free_box_on_floor_states),
     "sliding_box": (sliding_box, sliding_box_states),
     "two_box_stack": (two_box_stack, two_box_stack_states),
     "separate_groups": (separate_groups, separate_groups_states),

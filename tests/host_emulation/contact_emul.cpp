@@ -20,7 +20,7 @@ extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* par
   if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
   const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
   caps[0] = cmax; caps[1] = kmax;
-  std::vector<double> snap(snapDoublesPerWorld(nb, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
   k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
   if (c_ctopo.n_pairs == 0) { counts[0] = counts[1] = counts[2] = counts[3] = 0; return 0; }

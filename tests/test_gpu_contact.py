@@ -41,7 +41,7 @@ def contact_debug(world, w):
 def test_contact_step_matches_oracle(scene):
     make, states = SCENES[scene]
     desc = make()
-    N = 200
+    N = 64 if scene == "box_stack" else 200
     q, qd, tau = states(N, 5)
     world = BatchedWorld(desc, N)
     world.setPositions(cuda(q)); world.setVelocities(cuda(qd)); world.setForces(cuda(tau))

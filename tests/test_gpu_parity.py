@@ -204,10 +204,14 @@ def test_error_paths():
     assert lib.ddb_snapshot_select(h, 3) == 1
     assert lib.ddb_forward(h, None, None, g.data_ptr(), g.data_ptr(), g.data_ptr(), g.data_ptr(), None, None, None, None) == 1
     lib.ddb_destroy(h)
-    # FreeJoint topologies are not handled by the contact-free kernels yet: refuse, do not guess
+    # the backward pass through FreeJoint / contacts is not built yet: refused with a message, never approximated
     topo, params, keep = skeletons.create_box_stack(2).to_ctypes()
     h = _abi._vp()
-    assert lib.ddb_create(C.byref(topo), C.byref(params), 8, 0, C.byref(h)) == 1
+    assert lib.ddb_create(C.byref(topo), C.byref(params), 8, 0, C.byref(h)) == 0
+    g6 = torch.zeros(8, 12, dtype=torch.float64, device="cuda")
+    assert lib.ddb_forward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.clone().data_ptr(), g6.clone().data_ptr(), None, None, None, None) == 0
+    assert lib.ddb_backward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr()) == 4
+    assert b"not implemented" in lib.ddb_last_error(h)
     lib.ddb_destroy(h)
 
 
@@ -266,3 +270,21 @@ def test_full_size_properties():
     assert np.all(np.linalg.eigvalsh(fv) > 0)
     assert np.allclose(fv, o.dt * Minv, rtol=1e-15, atol=1e-18)
     assert np.all(np.isfinite(qn)) and np.all(np.isfinite(J["posVel"]))
+
+
+@pytest.mark.parametrize("seed,nb", [(21, 1), (22, 4), (23, 9)])
+def test_free_joint_forward(seed, nb):
+    """FreeJoint root (FreeJoint.cpp:64-81,587-601,673-693) + revolute/prismatic children, no contact: next state vs the
+    oracle, incl. the exp/log-map position integration at small and large rotation vectors."""
+    desc = skeletons.create_random_tree(nb, seed, free_root=True)
+    n = desc.getNumDofs()
+    q, qd, tau = random_inputs(n, 48, seed)
+    q[:8, 0:3] *= 1e-4   # below expMapRot's 1e-3 Taylor switch
+    q[8:16, 0:3] *= 2.5  # large rotation vectors
+    world = BatchedWorld(desc, 48)
+    world.setPositions(cuda(q)); world.setVelocities(cuda(qd)); world.setForces(cuda(tau))
+    forwardPass(world)
+    o = orc.OracleWorld(desc)
+    oqn, oqdn = o.step(q, qd, tau)
+    assert ref_equals(world.getVelocities().cpu().numpy(), oqdn, 1e-11), max_ref_err(world.getVelocities().cpu().numpy(), oqdn)
+    assert ref_equals(world.getPositions().cpu().numpy(), oqn, 1e-11), max_ref_err(world.getPositions().cpu().numpy(), oqn)
