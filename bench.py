@@ -28,10 +28,15 @@ UNIT = "world-steps/s"
 N_WORLDS = 65536
 N_DOFS = 5
 WORKLOAD = "pendulum5: 65536 five-link revolute pendulums per GPU, no contact (BASELINE configs[1]); step = forward + analytic backward VJP"
-# Algorithmic HBM bytes per world: forward reads q,qd,tau (3n) writes q',qd' (2n) + snapshot
-# q,qd,qdd (3n); backward reads the snapshot (3n) + dL/dq',dL/dqd' (2n), writes dL/dq,dL/dqd,dL/dtau (3n).
-FWD_BYTES = 8 * N_DOFS * 8
-BWD_BYTES = 8 * N_DOFS * 8
+# Algorithmic HBM bytes per world, SURVEY.md §8(d): forward reads q,qd,tau (3n) and writes q',qd' (2n) = 40n B;
+# backward reads dL/dq',dL/dqd' (2n) + the pre-step state (3n) and writes dL/dq,dL/dqd,dL/dtau (3n) = 64n B.
+# (The design additionally moves a 288 B/body snapshot each way on purpose — DESIGN.md §4 — which shows up in
+# roofline.traffic, not in the algorithmic bytes.)
+FWD_BYTES = 40 * N_DOFS
+BWD_BYTES = 64 * N_DOFS
+# DRAM traffic per launch from the round-1 `ncu --set full` capture (profiles/r01_ncu_full_summary.csv), bytes
+FWD_TRAFFIC = 7.96e6 + 72.4e6
+BWD_TRAFFIC = 93.4e6 + 3.63e6
 # FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
 FWD_FLOPS = 4639
 BWD_FLOPS = 4242
@@ -150,7 +155,7 @@ def run_ours(args):
     lib = _abi.load_library()
     desc = skeletons.create_multiarm_robot(N_DOFS)
     N, n = N_WORLDS, N_DOFS
-    SETS = 8  # rotating buffer sets: 8 x ~34 MB of inputs/outputs/snapshot = 272 MB > 126 MB L2, so every step is cold
+    SETS = 8  # rotating buffer sets: 8 x (26 MB of inputs/outputs + 94 MB snapshot slot) = 960 MB >> 126 MB L2: every step is cold
     topo, params, keep = desc.to_ctypes(n_snapshot_slots=SETS)
     h = _abi._vp()
     rc = lib.ddb_create(C.byref(topo), C.byref(params), N, local_rank, C.byref(h))
@@ -254,14 +259,14 @@ def run_ours(args):
         else:
             hbm_peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         value = world_size * N * args.steps / (elapsed_ms * 1e-3)
-        dom = ("k_backward", bwd_ms, BWD_BYTES, BWD_FLOPS) if bwd_ms >= fwd_ms else ("k_forward", fwd_ms, FWD_BYTES, FWD_FLOPS)
+        dom = ("k_backward", bwd_ms, BWD_BYTES, BWD_FLOPS, BWD_TRAFFIC) if bwd_ms >= fwd_ms else ("k_forward", fwd_ms, FWD_BYTES, FWD_FLOPS, FWD_TRAFFIC)
         achieved = dom[2] * N / (dom[1] * 1e-3) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "worlds_per_gpu": N, "n_dofs": n, "dt": 1e-3,
-                       "cache": "8 rotating input/output/snapshot sets (272 MB > 126 MB L2): every step reads cold inputs"},
+                       "cache": "8 rotating input/output/snapshot sets (960 MB >> 126 MB L2): every step reads cold inputs"},
             "clocks": sampler.result(),
             "e2e": {"value": world_size * N * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 5 * N * n * 8,
                     "d2h_bytes_per_step": 5 * N * n * 8, "steps": e2e_steps,
@@ -269,7 +274,7 @@ def run_ours(args):
             "gpu_launches": launches,
             "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": None, "peak_source": peak_src,
+                         "traffic": dom[4], "peak_source": peak_src,
                          "note": "FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md §4"},
             "roofline_fp64": {"peak": peak.value, "unit": "TFLOP/s", "peak_source": "ddb_measure_fp64_peak (DFMA micro-benchmark, this run)",
                               "achieved": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12,

@@ -365,7 +365,6 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");
   if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_backward: the backward pass through contacts is not implemented yet (forward only)");
-  if (h->topo.has_free) return fail(h, DDB_ERR_STATE, "ddb_backward: the backward pass through FreeJoint is not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
@@ -379,7 +378,6 @@ int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* v
   if (!h) return DDB_ERR_INVALID;
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_jacobians: no forward pass retained in the current snapshot slot");
   if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_jacobians: Jacobians through contacts are not implemented yet (forward only)");
-  if (h->topo.has_free) return fail(h, DDB_ERR_STATE, "ddb_jacobians: Jacobians through FreeJoint are not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
@@ -392,7 +390,6 @@ int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* v
 int ddb_inv_mass_matrix(ddb_handle* h, void* stream, double* minv) {
   if (!h || !minv) return fail(h, DDB_ERR_INVALID, "ddb_inv_mass_matrix: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_inv_mass_matrix: no forward pass retained in the current snapshot slot");
-  if (h->topo.has_free) return fail(h, DDB_ERR_STATE, "ddb_inv_mass_matrix: FreeJoint is not implemented yet in the M^-1 kernel");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;

@@ -66,9 +66,9 @@ DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {
 // to L2/HBM, which the path barely uses otherwise.
 // ---------------------------------------------------------------------------------------------
 // A FreeJoint body needs 6x6 blocks and uses 56 pairs instead: 0-5 T, 6-8 V, 9-11 A, 12-29 AIS (row-major 6x6),
-// 30-47 psi (6x6), 48-50 qd, 51-53 qdd (u between the sweeps), 54-55 (G, pad).
+// 30-47 psi (6x6), 48-50 qd, 51-53 qdd (u between the sweeps), 54-55 (G, pad), 56-58 q.
 constexpr int kSnapPairs = 18;
-constexpr int kSnapPairsFree = 56;
+constexpr int kSnapPairsFree = 59;  // + pairs 56-58: the joint coordinates q (6)
 
 struct Snap {
   double2* base;  // [nb*18][N]
@@ -264,6 +264,7 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
       Sq = mulS6(b, qd6);
       qdv[i] = 0.0;
       st6(sn, i, 48, qd6);
+      st6(sn, i, 56, q6);
     } else {
       const double qi = d ? qOf(TS::dofOf(i)) : 0.0, qdi = d ? qdOf(TS::dofOf(i)) : 0.0;
       t = jointTransform(b, qi);
@@ -404,8 +405,8 @@ struct BwdScratch {
   V3 pG[NB];
 };
 
-template <int NB, bool CHAIN, class LamF>
-DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws) {
+template <int NB, bool CHAIN, class LamF, class MuF>
+DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws, MuF muFree) {
   typedef Tree<NB, CHAIN> TS;
   SV* c = ws.c;
   double* a = ws.a;
@@ -415,6 +416,22 @@ DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws)
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
+    if (!CHAIN && b.type == DDB_JOINT_FREE) {
+      // a (6) = lambda - S^T c; the parent receives X^T (c + AIS psi a); a is kept in c[i] (no longer needed as bias)
+      double a6[6], sc[6];
+      mulS6T(b, c[i], sc);
+      for (int k = 0; k < 6; k++) a6[k] = lamOf(b.dof + k) - sc[k];
+      if (p >= 0) {
+        double AISm[36], psi6[36], pa[6], av[6];
+        ld36(sn, i, 12, AISm); ld36(sn, i, 30, psi6);
+        for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * a6[l]; pa[k] = acc; }
+        for (int r = 0; r < 6; r++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += AISm[r * 6 + k] * pa[k]; av[r] = acc; }
+        c[p] = c[p] + dAdInvT(sn.ldT(i), c[i] + sv6(av));
+      }
+      c[i] = sv6(a6);
+      a[i] = 0.0;
+      return;
+    }
     double ai = 0.0;
     if (TS::hasDof(i)) ai = lamOf(TS::dofOf(i)) - dot(b.S, c[i]);
     a[i] = ai;
@@ -430,6 +447,17 @@ DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws)
     double m = 0.0;
     SV Up = svzero();
     if (p >= 0) Up = AdInvT(sn.ldT(i), U[p]);
+    if (!CHAIN && b.type == DDB_JOINT_FREE) {
+      double AISm[36], psi6[36], r6[6], mu6[6];
+      ld36(sn, i, 12, AISm); ld36(sn, i, 30, psi6);
+      const double up6[6] = {Up.w.x, Up.w.y, Up.w.z, Up.v.x, Up.v.y, Up.v.z};
+      const double a6[6] = {c[i].w.x, c[i].w.y, c[i].w.z, c[i].v.x, c[i].v.y, c[i].v.z};
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int r = 0; r < 6; r++) acc += AISm[r * 6 + k] * up6[r]; r6[k] = a6[k] - acc; }
+      for (int k = 0; k < 6; k++) { double acc = 0.0; for (int l = 0; l < 6; l++) acc += psi6[k * 6 + l] * r6[l]; mu6[k] = acc; muFree(b.dof + k, acc); }
+      mu[i] = 0.0;
+      U[i] = Up + mulS6(b, mu6);
+      return;
+    }
     if (TS::hasDof(i)) {
       SV ais = sn.ldSV(i, 12);
       double ps = sn.ld(i, 15).x;
@@ -469,8 +497,55 @@ DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws)
 //                - Gbar_i . (w_S x G_i)
 // with X_i U_p = U_i - mu_i S_i, X_i V_p = V_i - qd_i S_i, X_i A_p = A_i - qdd_i S_i - ad(V_i, S_i qd_i).
 // ---------------------------------------------------------------------------------------------
-template <int NB, bool CHAIN, class Out>
-DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out) {
+// expMapJac(q)^T: the right Jacobian of the exponential map (math::expMapJac, Geometry.cpp:489-505, is the left one),
+// with the series used below |q| = 1e-3 so that it stays smooth
+DDB_DI M3 expRightJac(V3 q) {
+  const double t2 = dot(q, q), theta = sqrt(t2);
+  double a, b;
+  if (theta < 1.0e-3) { a = 0.5 - t2 / 24.0; b = 1.0 / 6.0 - t2 / 120.0; }
+  else { a = (1.0 - cos(theta)) / t2; b = (theta - sin(theta)) / (t2 * theta); }
+  M3 K; K.m[0] = 0; K.m[1] = -q.z; K.m[2] = q.y; K.m[3] = q.z; K.m[4] = 0; K.m[5] = -q.x; K.m[6] = -q.y; K.m[7] = q.x; K.m[8] = 0;
+  M3 K2 = mul(K, K);
+  M3 J;
+#pragma unroll
+  for (int i = 0; i < 9; i++) J.m[i] = ((i % 4 == 0) ? 1.0 : 0.0) - a * K.m[i] + b * K2.m[i];  // transpose flips the sign of K
+  return J;
+}
+DDB_DI M3 inv3(const M3& A) {
+  const double c00 = A.m[4] * A.m[8] - A.m[5] * A.m[7], c01 = A.m[5] * A.m[6] - A.m[3] * A.m[8], c02 = A.m[3] * A.m[7] - A.m[4] * A.m[6];
+  const double det = A.m[0] * c00 + A.m[1] * c01 + A.m[2] * c02, id = 1.0 / det;
+  M3 r;
+  r.m[0] = c00 * id; r.m[1] = (A.m[2] * A.m[7] - A.m[1] * A.m[8]) * id; r.m[2] = (A.m[1] * A.m[5] - A.m[2] * A.m[4]) * id;
+  r.m[3] = c01 * id; r.m[4] = (A.m[0] * A.m[8] - A.m[2] * A.m[6]) * id; r.m[5] = (A.m[2] * A.m[3] - A.m[0] * A.m[5]) * id;
+  r.m[6] = c02 * id; r.m[7] = (A.m[1] * A.m[6] - A.m[0] * A.m[7]) * id; r.m[8] = (A.m[0] * A.m[4] - A.m[1] * A.m[3]) * id;
+  return r;
+}
+// 6x6 blocks of d q+ / d q (pp) and d q+ / d qd (vp) for one FreeJoint (row-major), closed form of
+// FreeJoint::integratePositionsExplicit (FreeJoint.cpp:596-601): R+ = R(q_r) exp(dt w), p+ = p + dt R(q_r) v.
+// The reference differentiates it numerically (FreeJoint.cpp:604-653, eps 1e-6 / 1e-7).
+DDB_DI void freeJointPosJacobians(const double* q6, const double* qd6, double dt, double* pp, double* vp) {
+  const V3 qr = mk(q6[0], q6[1], q6[2]), w = mk(qd6[0] * dt, qd6[1] * dt, qd6[2] * dt), v = mk(qd6[3], qd6[4], qd6[5]);
+  const M3 R = expMapRot(qr), E = expMapRot(w);
+  const V3 qn = logMapRot(mul(R, E));
+  const M3 JrQ = expRightJac(qr), JrW = expRightJac(w), JrNinv = inv3(expRightJac(qn));
+  M3 Et; for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) Et.m[3 * i + j] = E.m[3 * j + i];
+  const M3 Prr = mul(JrNinv, mul(Et, JrQ));   // d q+_r / d q_r
+  const M3 Vrr = mul(JrNinv, JrW);            // d q+_r / d (dt w)
+  M3 Vx; Vx.m[0] = 0; Vx.m[1] = -v.z; Vx.m[2] = v.y; Vx.m[3] = v.z; Vx.m[4] = 0; Vx.m[5] = -v.x; Vx.m[6] = -v.y; Vx.m[7] = v.x; Vx.m[8] = 0;
+  const M3 Ppr = mul(mul(R, Vx), JrQ);        // d (R v) / d q_r = -R [v]x Jr(q_r)
+  for (int i = 0; i < 36; i++) { pp[i] = 0.0; vp[i] = 0.0; }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      pp[i * 6 + j] = Prr.m[3 * i + j];
+      pp[(3 + i) * 6 + j] = -dt * Ppr.m[3 * i + j];
+      pp[(3 + i) * 6 + 3 + j] = (i == j) ? 1.0 : 0.0;
+      vp[i * 6 + j] = dt * Vrr.m[3 * i + j];
+      vp[(3 + i) * 6 + 3 + j] = dt * R.m[3 * i + j];
+    }
+}
+
+template <int NB, bool CHAIN, class Out, class OutFree>
+DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFree outFree) {
   typedef Tree<NB, CHAIN> TS;
   const double* mu = ws.mu;
   const SV* U = ws.U;
@@ -481,6 +556,49 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
     const SV Vi = sn.ldSV(i, 6), Ai = sn.ldSV(i, 9);
+    if (!CHAIN && b.type == DDB_JOINT_FREE) {
+      double qd6[6], qdd6[6];
+      ld6(sn, i, 48, qd6); ld6(sn, i, 51, qdd6);
+      const double2 g0 = sn.ld(i, 54), g1 = sn.ld(i, 55);
+      const V3 Gi = mk(g0.x, g0.y, g1.x);
+      const SV Ui = U[i];
+      SV IV = mul(b.I, Vi);
+      SV Aeff = Ai;
+      if (b.gravity) Aeff.v = Aeff.v - Gi;
+      SV P = mul(b.I, Ui);
+      SV Sq = mulS6(b, qd6);
+      SV Ub = mul(b.I, Aeff) - dad(Vi, IV) + pU[i];
+      SV Ab = P + pA[i];
+      SV Vb = dad(Ui, IV) + mul(b.I, ad(Ui, Vi)) - dad(Sq, Ab) + pV[i];
+      V3 Gb = b.gravity ? pG[i] - P.v : pG[i];
+      Xf t = sn.ldT(i);
+      // what the parent contributes, expressed in this body's frame
+      SV XU = svzero(), XV = svzero(), XA = svzero();
+      if (p >= 0) { XU = AdInvT(t, U[p]); XV = AdInvT(t, sn.ldSV(p, 6)); XA = AdInvT(t, sn.ldSV(p, 9)); }
+      // joint coordinates of the FreeJoint: the child frame moves with twist S6 * jhat_k(q) per unit q_k,
+      // jhat_k = [Jr(q_r) e_k; 0] (k < 3), [0; R(q_r)^T e_k] (k >= 3)
+      double q6[6], dq6[6], dqd6[6];
+      ld6(sn, i, 56, q6);
+      const V3 qr = mk(q6[0], q6[1], q6[2]);
+      const M3 Jr = expRightJac(qr), Rq = expMapRot(qr);
+      for (int k = 0; k < 6; k++) {
+        double jh[6] = {0, 0, 0, 0, 0, 0};
+        if (k < 3) { jh[0] = Jr.m[k]; jh[1] = Jr.m[3 + k]; jh[2] = Jr.m[6 + k]; }
+        else { jh[3] = Rq.m[3 * (k - 3)]; jh[4] = Rq.m[3 * (k - 3) + 1]; jh[5] = Rq.m[3 * (k - 3) + 2]; }
+        const SV Sk = mulS6(b, jh);
+        dq6[k] = -(dot(dad(Sk, Ub), XU) + dot(dad(Sk, Ab), XA) + dot(dad(Sk, Vb), XV)) - dot(Gb, cross(Sk.w, Gi));
+      }
+      SV w2 = Vb + dad(Vi, Ab);
+      mulS6T(b, w2, dqd6);
+      outFree(i, dq6, dqd6);
+      if (p >= 0) {
+        pU[p] = pU[p] + dAdInvT(t, Ub);
+        pA[p] = pA[p] + dAdInvT(t, Ab);
+        pV[p] = pV[p] + dAdInvT(t, Vb);
+        pG[p] = pG[p] + mul(t.R, Gb);
+      }
+      return;
+    }
     const double qdi = sn.ld(i, 15).y;
     const double2 g0 = sn.ld(i, 16), g1 = sn.ld(i, 17);
     const V3 Gi = mk(g0.x, g0.y, g1.x);

@@ -109,14 +109,15 @@ k_backward(int N, double* __restrict__ snap, const double* __restrict__ gqn, con
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   // lambda = dL/dqd'
-  solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return gqdn[vidx(layout, N, n, w, d)]; }, ws);
+  solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return gqdn[vidx(layout, N, n, w, d)]; }, ws,
+                          [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; });
   if (CHAIN) {
 #pragma unroll
     for (int i = 0; i < NB; i++) gtau[vidx(layout, N, n, w, i)] = dt * mu[i];
   } else {
 #pragma unroll 1
     for (int i = 0; i < nb; i++)
-      if (c_topo.b[i].type != DDB_JOINT_WELD) gtau[vidx(layout, N, n, w, c_topo.b[i].dof)] = dt * mu[i];
+      if (c_topo.b[i].ndof == 1) gtau[vidx(layout, N, n, w, c_topo.b[i].dof)] = dt * mu[i];
   }
   idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
     size_t ix = vidx(layout, N, n, w, d);
@@ -124,6 +125,20 @@ k_backward(int N, double* __restrict__ snap, const double* __restrict__ gqn, con
     // pos-pos = I, vel-pos = dt I for R^1 joints; pos-vel^T l = -dt dPhi/dq; vel-vel^T l = l - dt dPhi/dqd
     gq[ix] = fma(-dt, dq, a);
     gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
+  }, [&](int body, const double* dq6, const double* dqd6) {
+    // FreeJoint block: dL/dq = posPos^T g_q' - dt dPhi/dq, dL/dqd = velPos^T g_q' + l - dt dPhi/dqd
+    const DevBody& b = c_topo.b[body];
+    double q6[6], qd6[6], pp[36], vp[36], a6[6];
+    ld6(sn, body, 56, q6); ld6(sn, body, 48, qd6);
+    freeJointPosJacobians(q6, qd6, dt, pp, vp);
+    for (int k = 0; k < 6; k++) a6[k] = gqn[vidx(layout, N, n, w, b.dof + k)];
+    for (int k = 0; k < 6; k++) {
+      double sp = 0.0, sv2 = 0.0;
+      for (int r = 0; r < 6; r++) { sp += pp[r * 6 + k] * a6[r]; sv2 += vp[r * 6 + k] * a6[r]; }
+      const size_t ix = vidx(layout, N, n, w, b.dof + k);
+      gq[ix] = sp - dt * dq6[k];
+      gqd[ix] = sv2 + gqdn[ix] - dt * dqd6[k];
+    }
   });
   if (c_topo.has_limits) {
     const double* clip = clipSection(snap, nb, N);
@@ -153,7 +168,8 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+                            [&](int d, double m) { if (forceVel) forceVel[base + (size_t)d * n + j] = dt * m; });
     if (forceVel) {
       if (CHAIN) {
 #pragma unroll
@@ -161,13 +177,19 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
       } else {
 #pragma unroll 1
         for (int i = 0; i < nb; i++)
-          if (c_topo.b[i].type != DDB_JOINT_WELD) forceVel[base + (size_t)c_topo.b[i].dof * n + j] = dt * mu[i];
+          if (c_topo.b[i].ndof == 1) forceVel[base + (size_t)c_topo.b[i].dof * n + j] = dt * mu[i];
       }
     }
     if (posVel || velVel) {
       idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
         if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
         if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
+      }, [&](int body, const double* dq6, const double* dqd6) {
+        const int d0 = c_topo.b[body].dof;
+        for (int k = 0; k < 6; k++) {
+          if (posVel) posVel[base + (size_t)(d0 + k) * n + j] = -dt * dq6[k];
+          if (velVel) velVel[base + (size_t)(d0 + k) * n + j] = (d0 + k == j ? 1.0 : 0.0) - dt * dqd6[k];
+        }
       });
     }
     if (posPos || velPos) {
@@ -176,6 +198,22 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
         if (posPos) posPos[base + (size_t)d * n + j] = d == j ? 1.0 : 0.0;
         if (velPos) velPos[base + (size_t)d * n + j] = d == j ? dt : 0.0;
       }
+    }
+  }
+  if (c_topo.has_free && (posPos || velPos)) {
+    // FreeJoint blocks of pos-pos / vel-pos (the identity / dt entries written above are overwritten)
+#pragma unroll 1
+    for (int i = 0; i < nb; i++) {
+      const DevBody& b = c_topo.b[i];
+      if (b.type != DDB_JOINT_FREE) continue;
+      double q6[6], qd6[6], pp[36], vp[36];
+      ld6(sn, i, 56, q6); ld6(sn, i, 48, qd6);
+      freeJointPosJacobians(q6, qd6, dt, pp, vp);
+      for (int r = 0; r < 6; r++)
+        for (int c = 0; c < 6; c++) {
+          if (posPos) posPos[base + (size_t)(b.dof + c) * n + b.dof + r] = pp[r * 6 + c];
+          if (velPos) velPos[base + (size_t)(b.dof + c) * n + b.dof + r] = vp[r * 6 + c];
+        }
     }
   }
 }
@@ -192,14 +230,15 @@ k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+                            [&](int d, double m) { minv[base + (size_t)j * n + d] = m; });
     if (CHAIN) {
 #pragma unroll
       for (int i = 0; i < NB; i++) minv[base + (size_t)j * n + i] = mu[i];
     } else {
 #pragma unroll 1
       for (int i = 0; i < nb; i++)
-        if (c_topo.b[i].type != DDB_JOINT_WELD) minv[base + (size_t)j * n + c_topo.b[i].dof] = mu[i];
+        if (c_topo.b[i].ndof == 1) minv[base + (size_t)j * n + c_topo.b[i].dof] = mu[i];
     }
   }
 }

@@ -124,6 +124,7 @@ DDB_LCP_DI void lcpSolveL1Generic(int n, LF Lf, BF Bf) {
   int i = 0;
   for (; i <= n - 4; i += 4) {
     double Z1 = 0, Z2 = 0, Z3 = 0, Z4 = 0;
+#pragma unroll 4
     for (int j = 0; j < i; ++j) {
       const double q = Bf(j);
       Z1 += Lf(i, j) * q;
@@ -142,6 +143,7 @@ DDB_LCP_DI void lcpSolveL1Generic(int n, LF Lf, BF Bf) {
   }
   for (; i < n; ++i) {
     double Z = 0;
+#pragma unroll 8
     for (int j = 0; j < i; ++j) Z += Lf(i, j) * Bf(j);
     Bf(i) = Bf(i) - Z;
   }
@@ -157,6 +159,7 @@ DDB_LCP_DI void lcpSolveL1T(const LcpView& v, int boff, int n) {
 // fastdot.cpp: sum of products, left to right
 DDB_LCP_DI double lcpDot(const LcpView& v, int aoff, int boff, int n) {
   double s = 0;
+#pragma unroll 8
   for (int k = 0; k < n; ++k) s += v.D(aoff, k) * v.D(boff, k);
   return s;
 }
@@ -419,7 +422,9 @@ DDB_LCP_DI bool dantzigSolve(const LcpView& v, int nub_in, bool earlyTermination
     // w[i] = A(i,C) x(C) + A(i,N) x(N) - b[i]
     {
       double s1 = 0, s2 = 0;
+#pragma unroll 8
       for (int k = 0; k < st.nC; ++k) s1 += v.A(i, k) * v.x(k);
+#pragma unroll 8
       for (int k = 0; k < st.nN; ++k) s2 += v.A(i, st.nC + k) * v.x(st.nC + k);
       v.w(i) = s1 + s2 - v.b(i);
     }
@@ -441,6 +446,7 @@ DDB_LCP_DI bool dantzigSolve(const LcpView& v, int nub_in, bool earlyTermination
         // delta_w(N) = A(N,C) delta_x(C) + dir * A(N,i)
         for (int k = 0; k < st.nN; ++k) {
           double s = 0;
+#pragma unroll 8
           for (int c = 0; c < st.nC; ++c) s += v.A(st.nC + k, c) * v.dx(c);
           v.dw(st.nC + k) = s;
         }
@@ -538,7 +544,9 @@ DDB_LCP_DI bool pgsSolve(const LcpView& v, const PgsOptions& opt) {
     v.C(norder++) = i;
     const double old_x = v.x(i);
     double new_x = v.b(i);
+#pragma unroll 8
     for (int j = 0; j < i; ++j) new_x -= v.Araw(i, j) * v.x(j);
+#pragma unroll 8
     for (int j = i + 1; j < n; ++j) new_x -= v.Araw(i, j) * v.x(j);
     new_x /= v.Araw(i, i);
     const int fi = v.findex(i);
@@ -563,7 +571,9 @@ DDB_LCP_DI bool pgsSolve(const LcpView& v, const PgsOptions& opt) {
       const int index = v.C(o);
       double new_x = v.b(index);
       const double old_x = v.x(index);
+#pragma unroll 8
       for (int j = 0; j < index; ++j) new_x -= v.Araw(index, j) * v.x(j);
+#pragma unroll 8
       for (int j = index + 1; j < n; ++j) new_x -= v.Araw(index, j) * v.x(j);
       const int fi = v.findex(index);
       double xi;

@@ -1,0 +1,29 @@
+"""Forward-only throughput of the contact path on BASELINE config 3 (box stacking, 5 FreeJoint boxes on a floor)."""
+import ctypes as C, json, os, sys, time
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import numpy as np, torch
+from contact_scenes import box_stack, box_stack_states
+from diffdart_b200.world import BatchedWorld, forwardPass
+
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+desc = box_stack()
+q, qd, tau = box_stack_states(N, 7)
+world = BatchedWorld(desc, N)
+cu = lambda a: torch.tensor(a, dtype=torch.float64, device="cuda")
+world.setPositions(cu(q)); world.setVelocities(cu(qd)); world.setForces(cu(tau))
+for _ in range(3):  # warm-up steps also populate the LCP cache
+    world.setForces(cu(tau)); forwardPass(world)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(steps):
+    world.setForces(cu(tau)); forwardPass(world)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / steps
+counts = np.zeros((N, 4), dtype=np.int32)
+world._lib.ddb_contact_debug_host(world._h, counts.ctypes.data_as(C.c_void_p), -1, None, None, None, None, None, None, None, None, None)
+tiers = {int(k): int(v) for k, v in zip(*np.unique(counts[:, 3], return_counts=True))}
+print(json.dumps({"workload": "box_stack forward only", "N": N, "ms_per_step": ms, "world_steps_per_s": N / (ms * 1e-3),
+                  "contacts_mean": float(counts[:, 0].mean()), "rows_mean": float(counts[:, 1].mean()), "tier_mask_hist": tiers}))

@@ -40,3 +40,21 @@ extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* par
   for (int k = 0; k < kmax; k++) { b_out[k] = cw.b()[k]; x_out[k] = cw.xall()[k]; }
   return 0;
 }
+
+// forward + backward + Jacobians of one world through the generic tree kernels (no contact stage)
+extern "C" int emul_step_backward(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
+                                  const double* gqn, const double* gqdn, double* qn, double* qdn, double* gq, double* gqd, double* gtau,
+                                  double* posPos, double* posVel, double* velPos, double* velVel, double* forceVel, double* minv) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  const int N = 1, nd = c_topo.nd;
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  Limits lim{};
+  k_backward<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), gqn, gqdn, gq, gqd, gtau, lim);
+  k_jacobians<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), posPos, posVel, velPos, velVel, forceVel);
+  k_inv_mass<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), minv);
+  return 0;
+}

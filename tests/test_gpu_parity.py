@@ -204,7 +204,7 @@ def test_error_paths():
     assert lib.ddb_snapshot_select(h, 3) == 1
     assert lib.ddb_forward(h, None, None, g.data_ptr(), g.data_ptr(), g.data_ptr(), g.data_ptr(), None, None, None, None) == 1
     lib.ddb_destroy(h)
-    # the backward pass through FreeJoint / contacts is not built yet: refused with a message, never approximated
+    # the backward pass through contacts is not built yet: refused with a message, never approximated
     topo, params, keep = skeletons.create_box_stack(2).to_ctypes()
     h = _abi._vp()
     assert lib.ddb_create(C.byref(topo), C.byref(params), 8, 0, C.byref(h)) == 0
@@ -288,3 +288,32 @@ def test_free_joint_forward(seed, nb):
     oqn, oqdn = o.step(q, qd, tau)
     assert ref_equals(world.getVelocities().cpu().numpy(), oqdn, 1e-11), max_ref_err(world.getVelocities().cpu().numpy(), oqdn)
     assert ref_equals(world.getPositions().cpu().numpy(), oqn, 1e-11), max_ref_err(world.getPositions().cpu().numpy(), oqn)
+
+
+@pytest.mark.parametrize("seed,nb", [(21, 1), (22, 4), (23, 9)])
+def test_free_joint_backward(seed, nb):
+    """Closed-form backward through a FreeJoint root: pos-pos / vel-pos blocks of the exp/log-map integration (the
+    reference finite-differences them, FreeJoint.cpp:604-653), 6-DOF blocks in the M^-1 solve and the ID adjoint.
+    Bar: 1e-8 (north star) against both oracle modes; the residual ~1e-9 comes from the reference's second-order
+    Taylor branch of expMapRot below 1e-3 (Geometry.cpp:479-483), which dt*omega always falls into."""
+    desc = skeletons.create_random_tree(nb, seed, free_root=True)
+    n = desc.getNumDofs()
+    q, qd, tau = random_inputs(n, 40, seed)
+    q[:8, 0:3] *= 1e-4
+    q[8:16, 0:3] *= 2.5
+    rng = np.random.default_rng(seed)
+    gq, gqd = rng.normal(size=q.shape), rng.normal(size=q.shape)
+    qn, qdn, dq, dqd, dtau, J, Minv = run_gpu(desc, q, qd, tau, gq, gqd)
+    o = orc.OracleWorld(desc)
+    assert ref_equals(Minv, o.inv_mass_matrix(q), 1e-11)
+    Je = o.jacobians(q, qd, tau, "exact", threads=4)
+    Jr = o.jacobians(q, qd, tau, "reference", threads=4)
+    for k in Je:
+        assert ref_equals(J[k], Je[k], 1e-8), (k, max_ref_err(J[k], Je[k]))
+        assert ref_equals(J[k], Jr[k], 1e-8), (k, max_ref_err(J[k], Jr[k]))
+    for k in ("posVel", "velVel", "forceVel"):  # no exp/log map involved: tight
+        assert ref_equals(J[k], Je[k], 1e-10), (k, max_ref_err(J[k], Je[k]))
+    _, _, ogq, ogqd, ogtau = o.step_backprop(q, qd, tau, gq, gqd, mode="exact", threads=4, with_step=False)
+    assert ref_equals(dq, ogq, 1e-8) and ref_equals(dqd, ogqd, 1e-8) and ref_equals(dtau, ogtau, 1e-11)
+    assert np.allclose(dq, np.einsum("wrc,wr->wc", J["posPos"], gq) + np.einsum("wrc,wr->wc", J["posVel"], gqd), rtol=1e-12, atol=1e-13)
+    assert np.allclose(dqd, np.einsum("wrc,wr->wc", J["velPos"], gq) + np.einsum("wrc,wr->wc", J["velVel"], gqd), rtol=1e-12, atol=1e-13)
