@@ -26,6 +26,7 @@ struct ShapeDesc {  // per body collision shape (one ShapeNode per body)
 };
 struct ContactTopo {
   int n_pairs, cmax, kmax, nskel;
+  int gradients, pad0;  // 1: the gradient-enabled solve of forwardPass (short-circuit, standardisation, classification)
   double clip_depth;
   int pairA[DDB_MAX_BODIES * 4], pairB[DDB_MAX_BODIES * 4];  // collidable pairs in collision-object order
   ShapeDesc shape[DDB_MAX_BODIES];
@@ -40,8 +41,8 @@ struct ContactLayout {
   __host__ __device__ size_t oNB() const { return oNA() + (size_t)cmax * 18; }
   __host__ __device__ size_t oMassed() const { return oNB() + (size_t)cmax * 18; }    // [kmax][nd]
   __host__ __device__ size_t oA() const { return oMassed() + (size_t)kmax * nd; }     // [kmax][kmax] (per group, n x n packed)
-  __host__ __device__ size_t oB() const { return oA() + (size_t)kmax * kmax; }        // b lo hi x0 x xall: 6 x [kmax]
-  __host__ __device__ size_t oW() const { return oB() + (size_t)6 * kmax; }           // [nb][12] world transforms
+  __host__ __device__ size_t oB() const { return oA() + (size_t)kmax * kmax; }        // b lo hi x0 x xall xs xnew colnorm: 9 x [kmax]
+  __host__ __device__ size_t oW() const { return oB() + (size_t)9 * kmax; }           // [nb][12] world transforms
   __host__ __device__ size_t oV() const { return oW() + (size_t)nb * 12; }            // [nb][6] body velocities (pre-constraint)
   __host__ __device__ size_t oImp() const { return oV() + (size_t)nb * 6; }           // [nb][6] constraint impulses
   __host__ __device__ size_t oBias() const { return oImp() + (size_t)nb * 6; }        // [nb][6]
@@ -49,7 +50,7 @@ struct ContactLayout {
   __host__ __device__ size_t oU() const { return oDelV() + (size_t)nb * 6; }          // [nb] + dqd [nd]
   __host__ __device__ size_t doubles() const { return oU() + (size_t)nb + nd; }
   // ints: bodyA bodyB dim type group [cmax each], findex keep mapTo [kmax each], misc
-  __host__ __device__ size_t ints() const { return (size_t)5 * cmax + (size_t)3 * kmax + 8; }
+  __host__ __device__ size_t ints() const { return (size_t)5 * cmax + (size_t)7 * kmax + 8; }
 };
 
 struct ContactWork {
@@ -67,6 +68,9 @@ struct ContactWork {
   DDB_LCP_DI double* x0() const { return d + L.oB() + 3 * (size_t)L.kmax; }
   DDB_LCP_DI double* x() const { return d + L.oB() + 4 * (size_t)L.kmax; }
   DDB_LCP_DI double* xall() const { return d + L.oB() + 5 * (size_t)L.kmax; }  // multipliers of every row of the world
+  DDB_LCP_DI double* xs() const { return d + L.oB() + 6 * (size_t)L.kmax; }
+  DDB_LCP_DI double* xnew() const { return d + L.oB() + 7 * (size_t)L.kmax; }
+  DDB_LCP_DI double* colnorm() const { return d + L.oB() + 8 * (size_t)L.kmax; }
   DDB_LCP_DI double* W(int body) const { return d + L.oW() + (size_t)body * 12; }
   DDB_LCP_DI double* V(int body) const { return d + L.oV() + (size_t)body * 6; }
   DDB_LCP_DI double* imp(int body) const { return d + L.oImp() + (size_t)body * 6; }
@@ -81,6 +85,10 @@ struct ContactWork {
   DDB_LCP_DI int* findex() const { return i + 5 * L.cmax; }
   DDB_LCP_DI int* keep() const { return i + 5 * L.cmax + L.kmax; }
   DDB_LCP_DI int* mapTo() const { return i + 5 * L.cmax + 2 * L.kmax; }
+  DDB_LCP_DI int* mapping() const { return i + 5 * L.cmax + 3 * L.kmax; }   // ConstraintMapping of the current group
+  DDB_LCP_DI int* clampIdx() const { return i + 5 * L.cmax + 4 * L.kmax; }
+  DDB_LCP_DI int* ubIdx() const { return i + 5 * L.cmax + 5 * L.kmax; }
+  DDB_LCP_DI int* activeAll() const { return i + 5 * L.cmax + 6 * L.kmax; }  // active set of every row of the world
 };
 
 DDB_LCP_DI SV ldSV6(const double* p) { return sv(mk(p[0], p[1], p[2]), mk(p[3], p[4], p[5])); }
@@ -372,6 +380,8 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         }
       }
     }
+    // ---- squared column norms of A (aColNormGradientBackup) ----
+    for (int j = 0; j < n; j++) { double sacc = 0.0; for (int r = 0; r < n; r++) sacc += A[(size_t)r * n + j] * A[(size_t)r * n + j]; cw.colnorm()[j] = sacc; }
     // ---- the solver's cached solution ----
     if (mxSize == n) { for (int k = 0; k < n; k++) x0[k] = lcp_cache[k]; }
     else { for (int k = 0; k < n; k++) x0[k] = 0.0; }
@@ -438,27 +448,149 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       return nr;
     };
     auto mapOut = [&]() { for (int k = 0; k < n; k++) x[k] = mapTo[k] >= 0 ? v.x(mapTo[k]) : 0.0; };
+    // ---- gradient-enabled pieces (ConstrainedGroupGradientMatrices.cpp:206-324,467-697; LCPUtils.cpp:87-141) ----
+    int* mapping = cw.mapping();
+    int* clampIdx = cw.clampIdx();
+    int* ubIdx = cw.ubIdx();
+    auto validWith = [&](const double* xv, bool ignoreFriction) {
+      return lcpValid(n, [&](int i, int j) { return A[(size_t)i * n + j]; }, [&](int i) { return xv[i]; }, [&](int i) { return b[i]; },
+                      [&](int i) { return hi[i]; }, [&](int i) { return lo[i]; }, [&](int i) { return findex[i]; }, ignoreFriction);
+    };
+    auto classify = [&](const double* xv, bool ignoreFriction, int& numClamping) {
+      numClamping = 0;
+      int numUB = 0;
+      for (int j = 0; j < n; j++) { mapping[j] = findex[j]; clampIdx[j] = -1; ubIdx[j] = -1; }
+      for (int j = 0; j < n; j++) {
+        if (cw.colnorm()[j] < 1e-9) { mapping[j] = -2; continue; }
+        const double force = xv[j];
+        double upper = hi[j], lower = lo[j];
+        const int fp = findex[j];
+        if (fp != -1) { upper *= xv[fp]; lower *= xv[fp]; }
+        if (fabs(force) < 1e-6) {
+          if (fp != -1) {
+            if (fabs(xv[fp]) < 1e-6) mapping[j] = -2;
+            else if (ignoreFriction) mapping[j] = -2;
+            else { mapping[j] = -1; clampIdx[j] = numClamping++; }
+          } else mapping[j] = -2;
+          continue;
+        }
+        const double tie = 1e-5;
+        if ((xv[j] > lower + tie && xv[j] < upper - tie) || (lower - xv[j] > 1e-2 || xv[j] - upper > 1e-2)) {
+          mapping[j] = -1; clampIdx[j] = numClamping++;
+        } else if (lower - xv[j] > 1e-2 || xv[j] - upper > 1e-2) {
+          mapping[j] = -3;
+        } else if (fp != -1 && fabs(xv[fp]) > 1e-9) {
+          if (cw.colnorm()[fp] > 1e-9 && (fp > j || mapping[fp] == -1)) { mapping[j] = fp; ubIdx[j] = numUB++; }
+          else mapping[j] = -2;
+        } else mapping[j] = -2;
+      }
+    };
+    // constructMatrices + opportunisticallyStandardizeResults: xv is replaced by the standardised solution when valid
+    auto constructAndStandardize = [&](double* xv, bool ignoreFriction) -> bool {
+      double* xn = cw.xnew();
+      for (int guard = 0; guard < 8; guard++) {
+        int nc2 = 0;
+        classify(xv, ignoreFriction, nc2);
+        if (nc2 == 0) {
+          for (int k = 0; k < n; k++) xn[k] = 0.0;
+          if (validWith(xn, ignoreFriction)) { for (int k = 0; k < n; k++) xv[k] = 0.0; return true; }
+          return false;
+        }
+        v.init(lcpD, lcpI, nc2, ct.kmax);
+        auto Qm = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * nc2 + j) * 32]; };
+        int* rowOfClamp = keep;
+        for (int j = 0; j < n; j++) if (clampIdx[j] >= 0) rowOfClamp[clampIdx[j]] = j;
+        for (int a = 0; a < nc2; a++) {
+          v.dw(a) = b[rowOfClamp[a]];
+          v.w(a) = xv[rowOfClamp[a]];  // original clamping impulses
+          for (int c2 = 0; c2 < nc2; c2++) Qm(a, c2) = A[(size_t)rowOfClamp[a] * n + rowOfClamp[c2]];
+        }
+        for (int j = 0; j < n; j++) {
+          if (mapping[j] < 0) continue;
+          const int fp = mapping[j];
+          const double upper = xv[fp] * hi[j], lower = xv[fp] * lo[j];
+          const double e = (fabs(xv[j] - upper) < fabs(xv[j] - lower)) ? hi[j] : lo[j];
+          const int col = clampIdx[fp];
+          for (int a = 0; a < nc2; a++) Qm(a, col) += A[(size_t)rowOfClamp[a] * n + j] * e;
+        }
+        codSolveDev(v, nc2);  // f_c in v.dx
+        bool anyNewlyNotClamping = false;
+        for (int i = 0; i < n; i++) {
+          xn[i] = 0.0;
+          if (clampIdx[i] != -1) {
+            const double f = v.dx(clampIdx[i]);
+            xn[i] = f;
+            if (fabs(f) < 1e-6 && fabs(xv[i]) > 1e-6 && findex[i] == -1) anyNewlyNotClamping = true;
+          }
+          if (ubIdx[i] != -1) {
+            const int fi = findex[i];
+            const double originalMultiple = v.w(clampIdx[fi]) / xv[i];
+            const double clean = (fabs(originalMultiple - hi[i]) < fabs(originalMultiple - lo[i])) ? hi[i] : lo[i];
+            xn[i] = v.dx(clampIdx[fi]) * clean;
+          }
+        }
+        if (!validWith(xn, ignoreFriction)) return false;
+        for (int k = 0; k < n; k++) xv[k] = xn[k];
+        if (!anyNewlyNotClamping) return true;
+      }
+      return true;
+    };
+    const bool gradients = ct.gradients != 0;
+    if (gradients && mxSize != n) {
+      // LCPUtils::guessSolution: least squares on {normal rows with b > 0} + {all friction rows}
+      int ncl = 0;
+      for (int i = 0; i < n; i++) { if (findex[i] == -1) { if (b[i] > 0) keep[ncl++] = i; } else keep[ncl++] = i; }
+      for (int k = 0; k < n; k++) x0[k] = 0.0;
+      if (ncl > 0) {
+        v.init(lcpD, lcpI, ncl, ct.kmax);
+        for (int a = 0; a < ncl; a++) {
+          v.dw(a) = b[keep[a]];
+          for (int c2 = 0; c2 < ncl; c2++) v.db[(size_t)(v.oL + a * ncl + c2) * 32] = A[(size_t)keep[a] * n + keep[c2]];
+        }
+        codSolveDev(v, ncl);
+        for (int a = 0; a < ncl; a++) x0[keep[a]] = v.dx(a);
+      }
+      for (int k = 0; k < n; k++) x[k] = x0[k];
+    }
     bool success = false;
     int tier = 1;
-    {
-      buildReduced(false);
-      success = dantzigSolve(v, 0, true);
-      if (success) { mapOut(); if (!isValid()) success = false; }
-    }
-    if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
-    if (!success) {
-      tier = 2;
-      buildReduced(false);
-      success = pgsSolve(v, pgs);
-      if (success) { mapOut(); if (!isValid()) success = false; }
+    bool ignoreFrictionFinal = false;
+    if (gradients) {
+      success = constructAndStandardize(x, false);
+      if (success) tier = 0;
+      else for (int k = 0; k < n; k++) x[k] = x0[k];
     }
     if (!success) {
-      tier = 3;
-      buildReduced(true);
-      pgsSolve(v, pgs);
-      mapOut();
+      tier = 1;
+      {
+        buildReduced(false);
+        success = dantzigSolve(v, 0, true);
+        if (success) { mapOut(); if (!isValid()) success = false; }
+      }
+      if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
+      if (!success) {
+        tier = 2;
+        buildReduced(false);
+        success = pgsSolve(v, pgs);
+        if (success) { mapOut(); if (!isValid()) success = false; }
+      }
+      if (!success) {
+        tier = 3;
+        ignoreFrictionFinal = true;
+        buildReduced(true);
+        pgsSolve(v, pgs);
+        mapOut();
+      }
+      if (hasNaN()) { for (int k = 0; k < n; k++) x[k] = 0.0; }
+      if (gradients) {
+        double* xs = cw.xs();
+        for (int k = 0; k < n; k++) xs[k] = x[k];
+        if (constructAndStandardize(xs, ignoreFrictionFinal)) { for (int k = 0; k < n; k++) x[k] = xs[k]; }
+      }
     }
-    if (hasNaN()) { for (int k = 0; k < n; k++) x[k] = 0.0; }
+    if (gradients) {
+      for (int k = 0; k < n; k++) cw.activeAll()[rowsTotal + k] = mapping[k] >= 0 ? mapping[k] + rowsTotal : mapping[k];
+    }
     out.tier_mask |= 1 << tier;
     // the solution becomes the solver's mX
     mxSize = n;

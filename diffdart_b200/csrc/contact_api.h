@@ -14,5 +14,5 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* work
 // the contact stage after k_forward: qd (in: unconstrained update, out: post-contact) ; lcp_cache [N][kmax], n_cache [N],
 // counts_out [N][4] = n_contacts, n_rows, n_groups, tier mask
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd_inout, double* lcp_cache,
-                          int* n_cache, int* counts_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i);
+                          int* n_cache, int* counts_out, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i);
 }  // namespace ddb

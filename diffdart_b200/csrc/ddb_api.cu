@@ -303,7 +303,7 @@ int ddb_snapshot_reserve(ddb_handle* h, int32_t n_slots, int32_t* n_out) {
 }
 
 int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, const double* tau, double* qn, double* qdn,
-                double* lcp_cache_inout, int32_t* n_rows_inout, int32_t* /*active_set_out*/, int32_t* status_out) {
+                double* lcp_cache_inout, int32_t* n_rows_inout, int32_t* active_set_out, int32_t* status_out) {
   if (!h || !q || !qd || !tau || !qn || !qdn) return fail(h, DDB_ERR_INVALID, "ddb_forward: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
@@ -316,7 +316,7 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
     double* cache = lcp_cache_inout ? lcp_cache_inout : h->lcp_cache;
     int* ncache = n_rows_inout ? n_rows_inout : h->n_cache;
     DDB_CUDA(h, contactLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], qdn, cache, ncache, h->ccounts,
-                              h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i));
+                              active_set_out, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i));
     h->launches++;
     if (status_out)
       DDB_CUDA(h, cudaMemcpy2DAsync(status_out, sizeof(int), h->ccounts + 3, 4 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToDevice, s));

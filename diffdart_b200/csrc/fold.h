@@ -153,6 +153,7 @@ inline int foldContactTopology(const ddb_topology* topo, const ddb_params* param
   const int nb = topo->n_bodies;
     std::memset(&ct, 0, sizeof(ct));
     ct.clip_depth = params->contact_clipping_depth;
+    ct.gradients = params->reserved[1] == 1 ? 0 : 1;  // reserved[1] = 1: plain World::step (constraint solver gradients disabled)
     int nskel = 0;
     for (int i = 0; i < nb; i++) nskel = std::max(nskel, topo->bodies[i].skeleton + 1);
     if (nskel > DDB_MAX_BODIES) { err = "too many skeletons"; return DDB_ERR_INVALID; }

@@ -71,8 +71,8 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
 // the contact stage of World::step, one world per thread
 __global__ void __launch_bounds__(64)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
-          int* __restrict__ n_cache, int* __restrict__ counts, double* __restrict__ work_d, int* __restrict__ work_i,
-          double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs) {
+          int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
+          int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
@@ -84,6 +84,10 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
   ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs);
   n_cache[w] = nc;
   counts[4 * w] = o.n_contacts; counts[4 * w + 1] = o.n_rows; counts[4 * w + 2] = o.n_groups; counts[4 * w + 3] = o.tier_mask;
+  if (active_out) {
+    // ConstraintMapping per LCP row (ConstrainedGroupGradientMatrices.hpp:32-38); rows beyond n_rows are IRRELEVANT (-4)
+    for (int k = 0; k < L.kmax; k++) active_out[(size_t)w * L.kmax + k] = (k < o.n_rows && c_ctopo.gradients) ? cw.activeAll()[k] : -4;
+  }
 }
 
 }  // namespace
@@ -104,10 +108,10 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, 
   *li = warps * lcpScratchInts(kmax) * 32;
 }
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd, double* lcp_cache,
-                          int* n_cache, int* counts, double* work_d, int* work_i, double* lcp_d, int* lcp_i) {
+                          int* n_cache, int* counts, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i) {
   ContactLayout L{nb, nd, cmax, kmax};
   PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
-  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, work_d, work_i, lcp_d, lcp_i, pgs);
+  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs);
   return cudaGetLastError();
 }
 }  // namespace ddb

@@ -96,6 +96,8 @@ class BatchedWorld:
     setForces = setExternalForces  # dart_layer.py:35 calls setForces; the binding exposes setExternalForces
 
     _squeeze = False
+    last_active_set = None
+    last_solver_status = None
 
     def getPositions(self):
         return self._out(self._q)
@@ -127,9 +129,19 @@ class BatchedWorld:
         qn, qdn = torch.empty_like(q), torch.empty_like(q)
         rc = self._lib.ddb_snapshot_select(self._h, slot)
         _check(self._lib, self._h, rc, "ddb_snapshot_select")
+        cm, km = C.c_int32(0), C.c_int32(0)
+        self._lib.ddb_contact_capacity(self._h, C.byref(cm), C.byref(km))
+        active = status = None
+        if km.value > 0:
+            # contact worlds: the solver's cached solution (World::getCachedLCPSolution) is carried by the handle;
+            # the active set (ConstraintMapping per LCP row) and the solver tier are returned per world
+            active = torch.empty(self.N, km.value, dtype=torch.int32, device=self.device)
+            status = torch.empty(self.N, dtype=torch.int32, device=self.device)
         rc = self._lib.ddb_forward(self._h, self._stream(), q.data_ptr(), qd.data_ptr(), tau.data_ptr(), qn.data_ptr(),
-                                   qdn.data_ptr(), None, None, None, None)
+                                   qdn.data_ptr(), None, None, None if active is None else active.data_ptr(),
+                                   None if status is None else status.data_ptr())
         _check(self._lib, self._h, rc, "ddb_forward")
+        self.last_active_set, self.last_solver_status = active, status
         return qn, qdn
 
     def launch_count(self):

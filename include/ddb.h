@@ -164,8 +164,14 @@ int ddb_jacobians(ddb_handle* h, void* cuda_stream,
  * Contact stage (run inside ddb_forward when the topology has collidable pairs): collision detection, contact
  * constraints, boxed-LCP assembly by impulse tests, reduce -> Dantzig -> validity -> PGS -> friction-free PGS, impulses
  * (ConstraintSolver::solve, constraint/ConstraintSolver.cpp:386-404; BoxedLcpConstraintSolver.cpp:188-684 without the
- * gradient-matrix branches). ddb_params.reserved[0] caps the contacts per world (default 64); rows = 3 * contacts.
- * status_out of ddb_forward = solver tier mask per world (bit 1 Dantzig, 2 PGS, 3 friction dropped, 8 capacity hit).
+ * gradient-matrix branches when ddb_params.reserved[1] == 1; by default the gradient-enabled solve of forwardPass:
+ * LCPUtils::guessSolution on a size change, short-circuit through the cached solution, classification into
+ * CLAMPING / UPPER_BOUND / NOT_CLAMPING / ILLEGAL and least-squares standardisation of the clamping impulses,
+ * ConstrainedGroupGradientMatrices.cpp:167-324,467-697). ddb_params.reserved[0] caps the contacts per world
+ * (default 64); rows = 3 * contacts.
+ * status_out of ddb_forward = solver tier mask per world (bit 0 short-circuit, 1 Dantzig, 2 PGS, 3 friction dropped,
+ * 8 capacity hit); active_set_out [N][max_rows] = ConstraintMapping per LCP row (-1 CLAMPING, -2 NOT_CLAMPING,
+ * -3 ILLEGAL, -4 IRRELEVANT = no such row, >= 0 UPPER_BOUND pointing at its normal row).
  */
 int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t* max_rows);
 int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims,

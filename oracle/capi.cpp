@@ -153,6 +153,14 @@ void ddo_log_map_rot(const double* R9, double* w) {
   for (int r = 0; r < 3; r++) w[r] = o[r];
 }
 
+// minimum-norm least squares (the oracle's stand-in for Eigen's completeOrthogonalDecomposition().solve)
+int ddo_cod_solve(int m, int n, const double* A, const double* b, double* x) {
+  std::vector<double> Av(A, A + (size_t)m * n), bv(b, b + m);
+  int rank = 0;
+  std::vector<double> xv = codSolve(m, n, Av, bv, &rank);
+  for (int i = 0; i < n; i++) x[i] = xv[i];
+  return rank;
+}
 // PGS on one problem: A n x n row-major (copied into the padded layout), x warm start in/out
 int ddo_pgs_solve(int n, const double* A, double* x, const double* b, const double* lo, const double* hi, const int* findex) {
   int ns = dPad(n);
@@ -176,11 +184,11 @@ int ddo_load_ref_libs(const char* dantzig_so, const char* boxbox_so) {
 // contacts_out [cmax][10]: bodyA bodyB point(3) normal(3) depth type; returns through counts[0..3]: n contacts, n rows, n groups, tier mask
 void ddo_step_contacts(void* h, const double* q, const double* qd, const double* tau, double* lcp_cache, int* n_cache, int kmax, double* qn,
                        double* qdn, double* pre_vel, int cmax, double* contacts_out, double* A_out, double* b_out, double* lo_out, double* hi_out,
-                       int* findex_out, double* x_out, int* counts) {
+                       int* findex_out, double* x_out, int* counts, int gradients, int* mapping_out) {
   const Model& M = ((OracleWorld*)h)->M;
   std::vector<double> cache(lcp_cache, lcp_cache + *n_cache);
   ContactStepResult R;
-  stepWithContacts(M, q, qd, tau, cache, R);
+  stepWithContacts(M, q, qd, tau, cache, R, gradients != 0);
   for (int i = 0; i < M.nd; i++) { qn[i] = R.qNext[i]; qdn[i] = R.qdNext[i]; if (pre_vel) pre_vel[i] = R.preConstraintVel[i]; }
   *n_cache = (int)std::min<size_t>(cache.size(), kmax);
   for (int i = 0; i < *n_cache; i++) lcp_cache[i] = cache[i];
@@ -202,6 +210,7 @@ void ddo_step_contacts(void* h, const double* q, const double* qd, const double*
       if (hi_out) hi_out[rows + i] = g.hi[i];
       if (findex_out) findex_out[rows + i] = g.findex[i] >= 0 ? g.findex[i] + rows : -1;
       if (x_out) x_out[rows + i] = g.x[i];
+      if (mapping_out && !g.mapping.empty()) mapping_out[rows + i] = g.mapping[i] >= 0 ? g.mapping[i] + rows : g.mapping[i];
     }
     rows += g.n;
     tiers |= 1 << g.tier;

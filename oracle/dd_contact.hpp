@@ -20,6 +20,7 @@
 #include <vector>
 #include "dd_dynamics.hpp"
 #include "dd_lcp.hpp"
+#include "dd_cod.hpp"
 
 namespace ddo {
 
@@ -240,7 +241,10 @@ struct GroupLCP {
   std::vector<double> A, b, lo, hi, x;  // A n x n row-major
   std::vector<int> findex;
   std::vector<double> massed;  // n columns of M^-1 J^T (nd each)
-  int tier = 0;                // 1 Dantzig, 2 PGS, 3 friction removed
+  std::vector<double> restitution;  // per row: the contact's coefficient on its normal row when it bounced, else 0
+  int tier = 0;                // 0 short-circuit, 1 Dantzig, 2 PGS, 3 friction removed
+  std::vector<int> mapping;    // ConstraintMapping per row: -1 CLAMPING, -2 NOT_CLAMPING, -3 ILLEGAL, >= 0 UPPER_BOUND -> normal row
+  bool standardized = false;
 };
 
 // impulse response of a unit impulse along column k of constraint c: dqd (nd) and body velocity changes (in d.b[i].delV)
@@ -282,6 +286,11 @@ inline void assembleGroup(const Model& M, Dyn<double>& d, const std::vector<Cons
       if (restitutionVel > 1e-1) { if (restitutionVel > bouncing) { bouncing = restitutionVel; if (bouncing > 1e+2) bouncing = 1e+2; } }
     }
     g.b[o] += bouncing;
+    {
+      bool didBounce = c.bounceOn && (g.b[o] - bouncing) * c.restitution > 1e-1;
+      g.restitution.resize(n, 0.0);
+      g.restitution[o] = didBounce ? c.restitution : 0.0;
+    }
     for (int k = 0; k < c.dim; k++) {
       impulseTest(M, d, c, k, dqd);
       for (int q = 0; q < M.nd; q++) g.massed[(size_t)(o + k) * M.nd + q] = dqd[q];
@@ -417,6 +426,157 @@ inline void solveGroupNoGrad(GroupLCP& g, const std::vector<double>& x0) {
   if (hasNaN(g.x)) std::fill(g.x.begin(), g.x.end(), 0.0);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Gradient-enabled path (BoxedLcpConstraintSolver.cpp:381-421,647-664; ConstrainedGroupGradientMatrices.cpp:167-324,467-855)
+// ---------------------------------------------------------------------------------------------------------
+// LCPUtils::guessSolution (LCPUtils.cpp:87-141)
+inline std::vector<double> guessSolution(const GroupLCP& g) {
+  const int n = g.n;
+  std::vector<int> cl;
+  for (int i = 0; i < n; i++) { if (g.findex[i] == -1) { if (g.b[i] > 0) cl.push_back(i); } else cl.push_back(i); }
+  const int nc = (int)cl.size();
+  if (nc == n) return codSolve(n, n, g.A, g.b);
+  std::vector<double> full(n, 0.0);
+  if (nc == 0) return full;
+  std::vector<double> rA((size_t)nc * nc), rb(nc);
+  for (int r = 0; r < nc; r++) { rb[r] = g.b[cl[r]]; for (int c = 0; c < nc; c++) rA[(size_t)r * nc + c] = g.A[(size_t)cl[r] * n + cl[c]]; }
+  std::vector<double> rx = codSolve(nc, nc, rA, rb);
+  for (int i = 0; i < nc; i++) full[cl[i]] = rx[i];
+  return full;
+}
+
+struct Classification {
+  std::vector<int> mapping, clampIdx, ubIdx;
+  int numClamping = 0, numUpperBound = 0;
+};
+// constructMatrices, the classification part (ConstrainedGroupGradientMatrices.cpp:467-697)
+inline Classification classify(const GroupLCP& g, const std::vector<double>& x, bool ignoreFriction) {
+  const int n = g.n;
+  Classification c;
+  c.mapping = g.findex; c.clampIdx.assign(n, -1); c.ubIdx.assign(n, -1);
+  const double CLAMPING_THRESHOLD = 1e-6;
+  for (int j = 0; j < n; j++) {
+    double colNorm = 0;  // aColNormGradientBackup: squared norm of column j of A
+    for (int r = 0; r < n; r++) colNorm += g.A[(size_t)r * n + j] * g.A[(size_t)r * n + j];
+    if (colNorm < 1e-9) { c.mapping[j] = -2; continue; }
+    const double force = x[j];
+    double upper = g.hi[j], lower = g.lo[j];
+    const int fp = g.findex[j];
+    if (fp != -1) { upper *= x[fp]; lower *= x[fp]; }
+    if (std::abs(force) < CLAMPING_THRESHOLD) {
+      if (fp != -1) {
+        if (std::abs(x[fp]) < CLAMPING_THRESHOLD) c.mapping[j] = -2;
+        else if (ignoreFriction) c.mapping[j] = -2;
+        else { c.mapping[j] = -1; c.clampIdx[j] = c.numClamping++; }
+      } else c.mapping[j] = -2;
+      continue;
+    }
+    const double tie = 1e-5;
+    if ((x[j] > lower + tie && x[j] < upper - tie) || (lower - x[j] > 1e-2 || x[j] - upper > 1e-2)) {
+      c.mapping[j] = -1; c.clampIdx[j] = c.numClamping++;
+    } else if (lower - x[j] > 1e-2 || x[j] - upper > 1e-2) {
+      c.mapping[j] = -3;
+    } else if (fp != -1 && std::abs(x[fp]) > 1e-9) {
+      double fpNorm = 0;
+      for (int r = 0; r < n; r++) fpNorm += g.A[(size_t)r * n + fp] * g.A[(size_t)r * n + fp];
+      if (fpNorm > 1e-9 && (fp > j || c.mapping[fp] == -1)) { c.mapping[j] = fp; c.ubIdx[j] = c.numUpperBound++; }
+      else c.mapping[j] = -2;
+    } else c.mapping[j] = -2;
+  }
+  return c;
+}
+// constructMatrices + opportunisticallyStandardizeResults (:206-324); x is updated when the standardised solution is valid
+inline bool constructAndStandardize(GroupLCP& g, std::vector<double>& x, bool ignoreFriction, Classification& cls) {
+  const int n = g.n;
+  for (int guard = 0; guard < 8; guard++) {
+    cls = classify(g, x, ignoreFriction);
+    if (n == 0) return true;
+    const int nc = cls.numClamping;
+    if (nc == 0) {
+      std::vector<double> zero(n, 0.0);
+      if (lcpValid(n, g.A.data(), zero.data(), g.b.data(), g.hi.data(), g.lo.data(), g.findex.data(), ignoreFriction)) { x = zero; return true; }
+      return false;
+    }
+    // Q = A_c^T M^-1 (A_c + A_ub E) = A[c,c] + A[c,ub] E ; E(u, clampIdx[findex]) = hi or lo, whichever bound x sits on
+    std::vector<int> rowOfClamp(nc);
+    for (int j = 0; j < n; j++) if (cls.clampIdx[j] >= 0) rowOfClamp[cls.clampIdx[j]] = j;
+    std::vector<double> Q((size_t)nc * nc, 0.0), bc(nc), fOrig(nc);
+    for (int a = 0; a < nc; a++) {
+      bc[a] = g.b[rowOfClamp[a]]; fOrig[a] = x[rowOfClamp[a]];
+      for (int b2 = 0; b2 < nc; b2++) Q[(size_t)a * nc + b2] = g.A[(size_t)rowOfClamp[a] * n + rowOfClamp[b2]];
+    }
+    for (int j = 0; j < n; j++) {
+      if (cls.mapping[j] < 0) continue;
+      const int fp = cls.mapping[j];
+      const double upper = x[fp] * g.hi[j], lower = x[fp] * g.lo[j];
+      const double e = (std::abs(x[j] - upper) < std::abs(x[j] - lower)) ? g.hi[j] : g.lo[j];
+      const int col = cls.clampIdx[fp];
+      for (int a = 0; a < nc; a++) Q[(size_t)a * nc + col] += g.A[(size_t)rowOfClamp[a] * n + j] * e;
+    }
+    std::vector<double> fc = codSolve(nc, nc, Q, bc);
+    std::vector<double> newX(n, 0.0);
+    bool anyNewlyNotClamping = false;
+    for (int i = 0; i < n; i++) {
+      if (cls.clampIdx[i] != -1) {
+        newX[i] = fc[cls.clampIdx[i]];
+        if (std::abs(fc[cls.clampIdx[i]]) < 1e-6 && std::abs(x[i]) > 1e-6 && g.findex[i] == -1) anyNewlyNotClamping = true;
+      }
+      if (cls.ubIdx[i] != -1) {
+        const int fi = g.findex[i];
+        const double originalMultiple = fOrig[cls.clampIdx[fi]] / x[i];
+        const double clean = (std::abs(originalMultiple - g.hi[i]) < std::abs(originalMultiple - g.lo[i])) ? g.hi[i] : g.lo[i];
+        newX[i] = fc[cls.clampIdx[fi]] * clean;
+      }
+    }
+    if (!lcpValid(n, g.A.data(), newX.data(), g.b.data(), g.hi.data(), g.lo.data(), g.findex.data(), ignoreFriction)) return false;
+    x = newX;
+    if (!anyNewlyNotClamping) return true;
+  }
+  return true;
+}
+
+// BoxedLcpConstraintSolver::solveConstrainedGroup with gradient matrices. mxResized: the solver's mX had another size.
+inline void solveGroupGrad(GroupLCP& g, const std::vector<double>& cache, bool mxResized) {
+  const int n = g.n;
+  std::vector<double> x0 = mxResized ? guessSolution(g) : cache;
+  Classification cls;
+  g.x = x0;
+  bool success = constructAndStandardize(g, g.x, false, cls);
+  g.tier = 0;
+  bool ignoreFriction = false;
+  if (!success) {
+    g.x = x0;
+    {
+      Reduced r = reduceLCP(g, g.x);
+      success = runDantzig(r, true);
+      if (success) { mapOut(r, g.x); if (!lcpValid(n, g.A.data(), g.x.data(), g.b.data(), g.hi.data(), g.lo.data(), g.findex.data(), false)) success = false; }
+      g.tier = 1;
+    }
+    if (hasNaN(g.x)) { success = false; std::fill(g.x.begin(), g.x.end(), 0.0); }
+    if (!success) {
+      Reduced r = reduceLCP(g, x0);
+      success = runPgs(r);
+      if (success) { mapOut(r, g.x); if (!lcpValid(n, g.A.data(), g.x.data(), g.b.data(), g.hi.data(), g.lo.data(), g.findex.data(), false)) success = false; }
+      g.tier = 2;
+    }
+    if (!success) {
+      ignoreFriction = true;
+      Reduced r = removeFrictionLCP(g, x0);
+      runPgs(r);
+      mapOut(r, g.x);
+      g.tier = 3;
+    }
+    if (hasNaN(g.x)) std::fill(g.x.begin(), g.x.end(), 0.0);
+    std::vector<double> xs = g.x;
+    bool st = constructAndStandardize(g, xs, ignoreFriction, cls);
+    if (st) g.x = xs;
+    g.standardized = st;
+  } else {
+    g.standardized = true;
+  }
+  g.mapping = cls.mapping;
+}
+
 struct ContactStepResult {
   std::vector<double> qNext, qdNext, preConstraintVel;
   std::vector<Contact> contacts;
@@ -426,7 +586,7 @@ struct ContactStepResult {
 
 // World::step with gradients disabled. lcpCache: the solver's mX (one group) in/out.
 inline void stepWithContacts(const Model& M, const double* q, const double* qd, const double* tau, std::vector<double>& lcpCache,
-                             ContactStepResult& R) {
+                             ContactStepResult& R, bool gradients = false) {
   const int n = M.nd;
   Dyn<double> d(M);
   d.setState(q, qd);
@@ -446,8 +606,10 @@ inline void stepWithContacts(const Model& M, const double* q, const double* qd, 
   for (GroupLCP& g : R.groups) {
     assembleGroup(M, d, R.constraints, g, M.dt, false);
     std::vector<double> x0(g.n, 0.0);
-    if ((int)lcpCache.size() == g.n) x0 = lcpCache;  // mX persists only while the size is unchanged (:205-210)
-    solveGroupNoGrad(g, x0);
+    const bool resized = (int)lcpCache.size() != g.n;
+    if (!resized) x0 = lcpCache;  // mX persists only while the size is unchanged (:205-210)
+    if (gradients) solveGroupGrad(g, x0, resized);
+    else solveGroupNoGrad(g, x0);
     lcpCache = g.x;
     for (size_t i = 0; i < g.cons.size(); i++) {
       const Constraint& c = R.constraints[g.cons[i]];

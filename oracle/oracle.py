@@ -113,7 +113,7 @@ class OracleWorld:
         lib().ddo_body_transforms(self.h, q.shape[0], _ptr(q), _ptr(out))
         return out
 
-    def step_contacts(self, q, qd, tau, lcp_cache=None, kmax=256, cmax=64):
+    def step_contacts(self, q, qd, tau, lcp_cache=None, kmax=256, cmax=64, gradients=False):
         """World::step with contacts (gradients disabled) for ONE world. Returns a dict with the next state and the
         intermediate quantities (contacts, boxed LCP, solution, solver tier mask)."""
         mask = lib().ddo_load_ref_libs(REF_SO.encode(), BOXBOX_SO.encode())
@@ -131,13 +131,14 @@ class OracleWorld:
         A, b, lo, hi, x = np.zeros((kmax, kmax)), np.zeros(kmax), np.zeros(kmax), np.zeros(kmax), np.zeros(kmax)
         fi = -np.ones(kmax, dtype=np.int32)
         counts = np.zeros(4, dtype=np.int32)
+        mapping = np.full(kmax, -9, dtype=np.int32)
         ipt = C.POINTER(C.c_int)
         lib().ddo_step_contacts(self.h, _ptr(q), _ptr(qd), _ptr(tau), _ptr(cache), C.byref(ncache), kmax, _ptr(qn), _ptr(qdn), _ptr(pre), cmax,
-                                _ptr(contacts), _ptr(A), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(ipt), _ptr(x), counts.ctypes.data_as(ipt))
+                                _ptr(contacts), _ptr(A), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(ipt), _ptr(x), counts.ctypes.data_as(ipt), 1 if gradients else 0, mapping.ctypes.data_as(ipt))
         nc, k = int(counts[0]), int(counts[1])
         return {"q_next": qn, "qd_next": qdn, "pre_constraint_vel": pre, "contacts": contacts[:nc], "A": A[:k, :k], "b": b[:k], "lo": lo[:k],
                 "hi": hi[:k], "findex": fi[:k], "x": x[:k], "n_groups": int(counts[2]), "tier_mask": int(counts[3]),
-                "lcp_cache": cache[:ncache.value].copy()}
+                "lcp_cache": cache[:ncache.value].copy(), "active_set": mapping[:k].copy()}
 
     def spatial_inertias(self):
         out = np.empty((self.nb, 6, 6))
@@ -178,6 +179,16 @@ def pgs_solve(A, b, lo, hi, findex, x0=None):
     fi = np.array(findex, dtype=np.int32)
     ok = lib().ddo_pgs_solve(n, _ptr(A), _ptr(x), _ptr(b), _ptr(lo), _ptr(hi), fi.ctypes.data_as(C.POINTER(C.c_int)))
     return bool(ok), x
+
+
+def cod_solve(A, b):
+    """The oracle's minimum-norm least-squares solve; returns (x, rank)."""
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    m, n = A.shape
+    x = np.zeros(n)
+    rank = lib().ddo_cod_solve(m, n, _ptr(A), _ptr(b), _ptr(x))
+    return x, rank
 
 
 def lcp_valid(A, x, b, lo, hi, findex, ignore_friction=False):

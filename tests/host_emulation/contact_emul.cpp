@@ -13,7 +13,7 @@ using namespace ddb;
 
 extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
                                  double* lcp_cache, int* n_cache, double* qn, double* qdn, int* counts, double* contacts_out, int* bodies_out,
-                                 int* dims_out, double* A_out, double* b_out, double* x_out, int* caps) {
+                                 int* dims_out, double* A_out, double* b_out, double* x_out, int* caps, int* active_out) {
   std::string err;
   bool chain;
   if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
@@ -37,7 +37,7 @@ extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* par
     bodies_out[2 * c] = cw.bodyA()[c]; bodies_out[2 * c + 1] = cw.bodyB()[c]; dims_out[c] = cw.dim()[c];
   }
   for (int k = 0; k < kmax * kmax; k++) A_out[k] = cw.A()[k];
-  for (int k = 0; k < kmax; k++) { b_out[k] = cw.b()[k]; x_out[k] = cw.xall()[k]; }
+  for (int k = 0; k < kmax; k++) { b_out[k] = cw.b()[k]; x_out[k] = cw.xall()[k]; if (active_out) active_out[k] = cw.activeAll()[k]; }
   return 0;
 }
 

@@ -26,6 +26,16 @@ int emul_lcp_solve(int n, const double* A, const double* b, const double* lo, co
   for (int i = 0; i < n; i++) x_out[i] = v.x(i);
   return ok ? 1 : 0;
 }
+int emul_cod_solve(int n, const double* Q, const double* c, double* x) {
+  std::vector<double> d(lcpScratchDoubles(n) * 32, 0.0);
+  std::vector<int> ib(lcpScratchInts(n) * 32, 0);
+  LcpView v;
+  v.init(d.data() + 7, ib.data() + 7, n, n);
+  for (int i = 0; i < n; i++) { for (int j = 0; j < n; j++) v.db[(size_t)(v.oL + i * n + j) * 32] = Q[i * n + j]; v.dw(i) = c[i]; }
+  int rank = codSolveDev(v, n);
+  for (int i = 0; i < n; i++) x[i] = v.dx(i);
+  return rank;
+}
 int emul_lcp_valid(int n, const double* A, const double* x, const double* b, const double* hi, const double* lo, const int* findex, int ignoreFriction) {
   return lcpValid(n, [&](int i, int j) { return A[i * n + j]; }, [&](int i) { return x[i]; }, [&](int i) { return b[i]; },
                   [&](int i) { return hi[i]; }, [&](int i) { return lo[i]; }, [&](int i) { return findex[i]; }, ignoreFriction != 0) ? 1 : 0;

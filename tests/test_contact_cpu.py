@@ -20,8 +20,9 @@ def emul():
     subprocess.run(["make", "-C", os.path.join(HERE, "host_emulation"), "-s"], check=True)
     lib = C.CDLL(os.path.join(HERE, "host_emulation", "_build", "libemul.so"))
 
-    def step(desc, q, qd, tau, cache=None):
+    def step(desc, q, qd, tau, cache=None, gradients=True):
         topo, params, keep = desc.to_ctypes()
+        params.reserved[1] = 0 if gradients else 1
         n = topo.n_dofs
         q, qd, tau = (np.ascontiguousarray(a, dtype=np.float64) for a in (q, qd, tau))
         cachebuf, nc = np.zeros(1024), C.c_int(0)
@@ -32,13 +33,14 @@ def emul():
         counts, caps = np.zeros(4, dtype=np.int32), np.zeros(2, dtype=np.int32)
         contacts, bodies, dims = np.zeros(64 * 26), np.zeros(128, dtype=np.int32), np.zeros(64, dtype=np.int32)
         A, b, x = np.zeros(192 * 192), np.zeros(192), np.zeros(192)
+        act = np.zeros(192, dtype=np.int32)
         rc = lib.emul_contact_step(C.byref(topo), C.byref(params), q.ctypes.data_as(dp), qd.ctypes.data_as(dp), tau.ctypes.data_as(dp),
                                    cachebuf.ctypes.data_as(dp), C.byref(nc), qn.ctypes.data_as(dp), qdn.ctypes.data_as(dp),
                                    counts.ctypes.data_as(ip), contacts.ctypes.data_as(dp), bodies.ctypes.data_as(ip), dims.ctypes.data_as(ip),
-                                   A.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp), caps.ctypes.data_as(ip))
+                                   A.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp), caps.ctypes.data_as(ip), act.ctypes.data_as(ip))
         assert rc == 0
         return {"q_next": qn, "qd_next": qdn, "counts": counts, "contacts": contacts.reshape(64, 26)[:counts[0]],
-                "x": x[:max(counts[1], 0)], "lcp_cache": cachebuf[:nc.value].copy()}
+                "x": x[:max(counts[1], 0)], "lcp_cache": cachebuf[:nc.value].copy(), "active_set": act[:max(counts[1], 0)].copy()}
 
     return step
 
@@ -51,14 +53,15 @@ def _quiet_ode(capfd):
 
 @pytest.mark.parametrize("scene", sorted(SCENES))
 def test_contact_step_matches_oracle(emul, scene):
+    """World::step with the constraint solver's gradients disabled (SURVEY §3.3): reduce -> Dantzig -> PGS chain."""
     make, states = SCENES[scene]
     desc = make()
     o = OracleWorld(desc)
-    q, qd, tau = states(16 if scene == "box_stack" else 60, 3)
+    q, qd, tau = states(6 if scene == "box_stack" else 40, 3)
     tiers = set()
     for w in range(len(q)):
         r = o.step_contacts(q[w], qd[w], tau[w])
-        e = emul(desc, q[w], qd[w], tau[w])
+        e = emul(desc, q[w], qd[w], tau[w], gradients=False)
         assert list(e["counts"]) == [len(r["contacts"]), len(r["x"]), r["n_groups"], r["tier_mask"]], w
         tiers.add(r["tier_mask"])
         if len(r["contacts"]):
@@ -70,19 +73,49 @@ def test_contact_step_matches_oracle(emul, scene):
         assert {2, 4, 8} <= tiers  # Dantzig, PGS and friction-dropped tiers all exercised
 
 
-def test_rollout_with_lcp_cache(emul):
-    """Several consecutive steps carrying the solver's cached solution (mX) from step to step."""
-    make, states = SCENES["two_box_stack"]
+@pytest.mark.parametrize("scene", sorted(SCENES))
+def test_forward_pass_with_gradients_matches_oracle(emul, scene):
+    """The gradient-enabled solve of neural::forwardPass over a 3-step rollout that carries the solver's cached solution:
+    guessSolution, short-circuit, classification, standardisation. The ACTIVE SET (ConstraintMapping per row) must be
+    identical; states agree to 1e-6 (north-star tolerance for contact-rich solves; PGS worlds) / 1e-10 otherwise."""
+    make, states = SCENES[scene]
     desc = make()
     o = OracleWorld(desc)
-    q, qd, tau = states(4, 9)
-    for w in range(4):
+    nw = 3 if scene == "box_stack" else 16
+    q, qd, tau = states(nw, 3)
+    tiers = set()
+    for w in range(nw):
         qo, qdo, co = q[w], qd[w], None
         qe, qde, ce = q[w], qd[w], None
-        for t in range(6):
-            r = o.step_contacts(qo, qdo, tau[w], lcp_cache=co)
+        for t in range(3):
+            r = o.step_contacts(qo, qdo, tau[w], lcp_cache=co, gradients=True)
             e = emul(desc, qe, qde, tau[w], cache=ce)
-            assert np.allclose(e["qd_next"], r["qd_next"], rtol=1e-9, atol=1e-11) and np.allclose(e["q_next"], r["q_next"], atol=1e-13)
-            assert np.allclose(e["lcp_cache"], r["lcp_cache"], rtol=1e-8, atol=1e-11)
+            tiers.add(r["tier_mask"])
+            assert list(e["counts"]) == [len(r["contacts"]), len(r["x"]), r["n_groups"], r["tier_mask"]], (w, t)
+            assert np.array_equal(e["active_set"], r["active_set"]), (w, t)
+            tol = 1e-6 if r["tier_mask"] & 12 else 1e-10
+            assert np.allclose(e["qd_next"], r["qd_next"], rtol=tol, atol=tol) and np.allclose(e["q_next"], r["q_next"], atol=1e-13)
             qo, qdo, co = r["q_next"], r["qd_next"], r["lcp_cache"]
             qe, qde, ce = e["q_next"], e["qd_next"], e["lcp_cache"]
+    if scene in ("sliding_box", "two_box_stack"):
+        assert 1 in tiers  # the short-circuit through the cached solution was taken
+
+
+def test_cod_min_norm_properties(emul):
+    """The oracle's stand-in for Eigen's completeOrthogonalDecomposition().solve: least-squares residual orthogonal to
+    the range, solution orthogonal to the null space, on full-rank and rank-deficient matrices (parity with Eigen itself
+    is unpinned: Eigen is not vendored)."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(0)
+    for t in range(200):
+        n = int(rng.integers(1, 40))
+        r = int(rng.integers(1, n + 1))
+        A = rng.normal(size=(n, r)) @ rng.normal(size=(r, n))
+        if t % 3 == 0:
+            A = A @ A.T
+        b = rng.normal(size=n)
+        x, rank = orc.cod_solve(A, b)
+        assert rank == r
+        assert np.allclose(A.T @ (A @ x - b), 0, atol=1e-8 * max(1.0, np.abs(A).max() ** 2))
+        xp = np.linalg.pinv(A, rcond=1e-12) @ b
+        assert np.allclose(x, xp, rtol=1e-8, atol=1e-9 * max(1.0, np.abs(xp).max()))

@@ -37,13 +37,26 @@ def contact_debug(world, w):
     return counts, contacts, x
 
 
+class PlainStepDescription:
+    """Wraps a WorldDescription so that the handle runs World::step with the solver's gradients disabled (reserved[1] = 1)."""
+
+    def __init__(self, desc):
+        self._d = desc
+
+    def to_ctypes(self, *a, **k):
+        topo, params, keep = self._d.to_ctypes(*a, **k)
+        params.reserved[1] = 1
+        return topo, params, keep
+
+
 @pytest.mark.parametrize("scene", sorted(SCENES))
 def test_contact_step_matches_oracle(scene):
+    """World::step with the constraint solver's gradients disabled (SURVEY §3.3)."""
     make, states = SCENES[scene]
     desc = make()
     N = 64 if scene == "box_stack" else 200
     q, qd, tau = states(N, 5)
-    world = BatchedWorld(desc, N)
+    world = BatchedWorld(PlainStepDescription(desc), N)
     world.setPositions(cuda(q)); world.setVelocities(cuda(qd)); world.setForces(cuda(tau))
     forwardPass(world)
     qn, qdn = world.getPositions().cpu().numpy(), world.getVelocities().cpu().numpy()
@@ -60,24 +73,40 @@ def test_contact_step_matches_oracle(scene):
             assert np.allclose(x[:len(r["x"])], r["x"], rtol=1e-8, atol=1e-11)
 
 
-def test_contact_rollout_carries_lcp_cache():
-    make, states = SCENES["two_box_stack"]
+@pytest.mark.parametrize("scene", sorted(SCENES))
+def test_forward_pass_rollout_active_set_bit_exact(scene):
+    """neural::forwardPass (gradient-enabled solve) over a rollout that carries the solver's cached solution: the active
+    set (ConstraintMapping per LCP row), contact / row / group counts and solver tier must equal the oracle's exactly;
+    next states within 1e-6 (north-star tolerance for contact-rich solves) for PGS worlds, 1e-9 otherwise."""
+    make, states = SCENES[scene]
     desc = make()
-    N, T = 32, 8
+    N, T = (24, 3) if scene == "box_stack" else (64, 4)
     q, qd, tau = states(N, 11)
     world = BatchedWorld(desc, N)
     world.setPositions(cuda(q)); world.setVelocities(cuda(qd))
     o = OracleWorld(desc)
     ref = [(q[w], qd[w], None) for w in range(N)]
+    tiers = set()
     for t in range(T):
         world.setForces(cuda(tau))
         forwardPass(world)
         qn, qdn = world.getPositions().cpu().numpy(), world.getVelocities().cpu().numpy()
+        active = world.last_active_set.cpu().numpy()
+        status = world.last_solver_status.cpu().numpy()
+        counts, _, _ = contact_debug(world, -1)
         for w in range(N):
-            r = o.step_contacts(ref[w][0], ref[w][1], tau[w], lcp_cache=ref[w][2])
+            r = o.step_contacts(ref[w][0], ref[w][1], tau[w], lcp_cache=ref[w][2], gradients=True)
             ref[w] = (r["q_next"], r["qd_next"], r["lcp_cache"])
-            assert np.allclose(qdn[w], r["qd_next"], rtol=1e-8, atol=1e-10), (t, w)
+            k = len(r["x"])
+            tiers.add(r["tier_mask"])
+            assert list(counts[w]) == [len(r["contacts"]), k, r["n_groups"], r["tier_mask"]], (t, w)
+            assert status[w] == r["tier_mask"]
+            assert np.array_equal(active[w, :k], r["active_set"]) and np.all(active[w, k:] == -4), (t, w)
+            tol = 1e-6 if r["tier_mask"] & 12 else 1e-9
+            assert np.allclose(qdn[w], r["qd_next"], rtol=tol, atol=tol), (t, w)
             assert np.allclose(qn[w], r["q_next"], rtol=0, atol=1e-12), (t, w)
+    if scene in ("sliding_box", "two_box_stack"):
+        assert 1 in tiers
 
 
 def test_backward_through_contacts_is_refused_not_faked():
