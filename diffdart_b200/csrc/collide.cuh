@@ -270,14 +270,17 @@ DDB_COL_DI int boxSphereImpl(const double* boxSize, const Pose& Tb, double r, co
   double d[3] = {c0[0] - Tb.p[0], c0[1] - Tb.p[1], c0[2] - Tb.p[2]};
   double p[3] = {colDot(Tb.R, 0, d), colDot(Tb.R, 1, d), colDot(Tb.R, 2, d)};
   bool inside = true;
+  int locks = 0;  // face{1,2,3}Locked (DARTCollide.cpp:1452-1493)
   for (int k = 0; k < 3; k++) {
-    if (p[k] < -half[k]) { p[k] = -half[k]; inside = false; }
-    if (p[k] > half[k]) { p[k] = half[k]; inside = false; }
+    if (p[k] < -half[k]) { p[k] = -half[k]; inside = false; locks |= 1 << k; }
+    if (p[k] > half[k]) { p[k] = half[k]; inside = false; locks |= 1 << k; }
   }
   ContactPoint& c = out[0];
   for (int i = 0; i < 3; i++) c.edgeAClosest[i] = c.edgeAFixed[i] = c.edgeADir[i] = c.edgeBClosest[i] = c.edgeBFixed[i] = c.edgeBDir[i] = 0;
   for (int i = 0; i < 3; i++) c.edgeAFixed[i] = c0[i];  // sphereCenter travels in edgeAFixed
   c.edgeADir[0] = r;                                      // sphereRadius
+  c.edgeADir[1] = (double)locks;                          // face lock mask; face normals = box axes:
+  for (int i = 0; i < 3; i++) { c.edgeBClosest[i] = Tb.R[3 * i]; c.edgeBFixed[i] = Tb.R[3 * i + 1]; c.edgeBDir[i] = Tb.R[3 * i + 2]; }
   c.type = sphereIsFirst ? CT_SPHERE_BOX : CT_BOX_SPHERE;
   auto nearestSide = [&](int& idx) {
     double mn = half[0] - fabs(p[0]);

@@ -1,12 +1,14 @@
 // TEST INFRASTRUCTURE ONLY — see dd_spatial.hpp.
 // C entry points of the CPU oracle for ctypes (tests/, smoke(), bench.py cpu_baseline).
 // Batched arrays are world-major: x[world * n + dof]; matrices [world][col][row].
+#include <cstring>
 #include <thread>
 #include <vector>
 #include <functional>
 #include "dd_step.hpp"
 #include "dd_lcp.hpp"
 #include "dd_contact.hpp"
+#include "dd_contact_grad.hpp"
 #include <dlfcn.h>
 
 using namespace ddo;
@@ -216,6 +218,73 @@ void ddo_step_contacts(void* h, const double* q, const double* qd, const double*
     tiers |= 1 << g.tier;
   }
   counts[1] = rows; counts[2] = (int)R.groups.size(); counts[3] = tiers;
+}
+
+// One world: forwardPass with contacts (gradient-enabled solve) + the BackpropSnapshot Jacobians through the contact
+// solution (reference recipe). Matrices n x n column-major; info[0..2] = numClamping, numUpperBound, pseudo-inverse branch.
+// mode 0: analytic (reference recipe); mode 1: central differences (eps) of the frozen-active-set velocity map with the
+// collision detector re-run at every perturbed state (posVel / velVel / forceVel only; info[3] = 1 when every
+// perturbed state kept the contact structure).
+void ddo_contact_jacobians(void* h, int mode, double eps, const double* q, const double* qd, const double* tau, const double* lcp_cache,
+                           int n_cache, double* posPos, double* posVel, double* velPos, double* velVel, double* forceVel, int* info,
+                           double* qn, double* qdn) {
+  const Model& M = ((OracleWorld*)h)->M;
+  const int n = M.nd;
+  std::vector<double> cache(lcp_cache, lcp_cache + n_cache);
+  ContactStepResult R;
+  stepWithContacts(M, q, qd, tau, cache, R, true);
+  if (qn) for (int i = 0; i < n; i++) { qn[i] = R.qNext[i]; qdn[i] = R.qdNext[i]; }
+  Jacobians J;
+  ContactGradInfo gi;
+  if (mode == 0) {
+    jacobiansReferenceContact(M, q, qd, tau, R, J, &gi);
+    info[0] = gi.numClamping; info[1] = gi.numUpperBound; info[2] = gi.pseudoInverseBranch ? 1 : 0; info[3] = 1;
+  } else {
+    J.resize(n);
+    bool ok = true;
+    std::vector<double> x(3 * n), xp, a, b;
+    for (int i = 0; i < n; i++) { x[i] = q[i]; x[n + i] = qd[i]; x[2 * n + i] = tau[i]; }
+    for (int i = 0; i < 3 * n; i++) {
+      xp = x; xp[i] += eps; ok = frozenSetVelocity(M, &xp[0], &xp[n], &xp[2 * n], R, a) && ok;
+      xp = x; xp[i] -= eps; ok = frozenSetVelocity(M, &xp[0], &xp[n], &xp[2 * n], R, b) && ok;
+      if (a.size() != (size_t)n || b.size() != (size_t)n) { ok = false; continue; }
+      std::vector<double>& out = i < n ? J.posVel : (i < 2 * n ? J.velVel : J.forceVel);
+      for (int r = 0; r < n; r++) out[(size_t)(i % n) * n + r] = (a[r] - b[r]) / (2 * eps);
+    }
+    info[0] = info[1] = info[2] = 0; info[3] = ok ? 1 : 0;
+  }
+  const size_t nn = (size_t)n * n * sizeof(double);
+  if (posPos) std::memcpy(posPos, J.posPos.data(), nn);
+  if (posVel) std::memcpy(posVel, J.posVel.data(), nn);
+  if (velPos) std::memcpy(velPos, J.velPos.data(), nn);
+  if (velVel) std::memcpy(velVel, J.velVel.data(), nn);
+  if (forceVel) std::memcpy(forceVel, J.forceVel.data(), nn);
+}
+
+// contact geometry gradients of ONE world at (q, qd, tau): out [constraint][dof][6] = d point / d q_dof, d normal / d q_dof
+// (getContactPositionGradient / getContactNormalGradient); returns the number of constraints (<= cmax written).
+int ddo_contact_geometry_gradients(void* h, const double* q, const double* qd, const double* tau, int cmax, double* out, double* points) {
+  const Model& M = ((OracleWorld*)h)->M;
+  const int n = M.nd;
+  std::vector<double> cache;
+  ContactStepResult R;
+  stepWithContacts(M, q, qd, tau, cache, R, true);
+  Dyn<double> d(M);
+  d.setState(q, qd);
+  const Screws sc = worldScrews(M, d);
+  int k = 0;
+  for (const Constraint& c : R.constraints) {
+    if (k >= cmax) break;
+    for (int w = 0; w < n; w++) {
+      const DofRole role = dofRole(M, c, w);
+      const Vec3<double> pg = contactPositionGradient(c, role, sc.pos[w]), ng = contactNormalGradient(c, role, sc.pos[w]);
+      for (int x = 0; x < 3; x++) { out[((size_t)k * n + w) * 6 + x] = pg[x]; out[((size_t)k * n + w) * 6 + 3 + x] = ng[x]; }
+    }
+    for (int x = 0; x < 3; x++) { points[k * 8 + x] = c.contact.point[x]; points[k * 8 + 3 + x] = c.contact.normal[x]; }
+    points[k * 8 + 6] = c.contact.type; points[k * 8 + 7] = c.contact.depth;
+    k++;
+  }
+  return (int)R.constraints.size();
 }
 
 }  // extern "C"

@@ -51,9 +51,10 @@ inline int boxSphere(const double* size, const double* Tb, double r, const doubl
   double d[3] = {c0[0] - Tb[9], c0[1] - Tb[10], c0[2] - Tb[11]}, p[3];
   for (int k = 0; k < 3; k++) p[k] = Tb[k] * d[0] + Tb[3 + k] * d[1] + Tb[6 + k] * d[2];
   bool inside = true;
+  int locks = 0;  // face{1,2,3}Locked (DARTCollide.cpp:1452-1493)
   for (int k = 0; k < 3; k++) {
-    if (p[k] < -half[k]) { p[k] = -half[k]; inside = false; }
-    if (p[k] > half[k]) { p[k] = half[k]; inside = false; }
+    if (p[k] < -half[k]) { p[k] = -half[k]; inside = false; locks |= 1 << k; }
+    if (p[k] > half[k]) { p[k] = half[k]; inside = false; locks |= 1 << k; }
   }
   auto side = [&](int& idx) { double mn = half[0] - std::abs(p[0]); double t = half[1] - std::abs(p[1]); idx = 0; if (t < mn) { mn = t; idx = 1; } t = half[2] - std::abs(p[2]); if (t < mn) { mn = t; idx = 2; } return mn; };
   auto axisNormal = [&](int idx) {
@@ -62,6 +63,10 @@ inline int boxSphere(const double* size, const double* Tb, double r, const doubl
     for (int i = 0; i < 3; i++) c.normal[i] = Tb[3 * i] * e[0] + Tb[3 * i + 1] * e[1] + Tb[3 * i + 2] * e[2];
   };
   for (double& m : c.meta) m = 0;
+  // Contact::sphereCenter / sphereRadius / face{1,2,3}Locked / face{1,2,3}Normal travel in the edge slots:
+  // edgeAFixed = centre, edgeADir = (radius, lock mask, 0), edgeBClosest / edgeBFixed / edgeBDir = box axes
+  for (int i = 0; i < 3; i++) { c.meta[3 + i] = c0[i]; c.meta[9 + i] = Tb[3 * i]; c.meta[12 + i] = Tb[3 * i + 1]; c.meta[15 + i] = Tb[3 * i + 2]; }
+  c.meta[6] = r; c.meta[7] = (double)locks;
   c.type = sphereFirst ? 4 : 5;
   if (inside) {
     int idx; double mn = side(idx);
@@ -87,7 +92,8 @@ inline int sphereSphere(double r0, const double* c0, double r1, const double* c1
   if (nsq > rsum * rsum) return 0;
   r0 /= rsum; r1 /= rsum;
   for (double& m : c.meta) m = 0;
-  for (int i = 0; i < 3; i++) c.point[i] = r1 * c0[i] + r0 * c1[i];
+  for (int i = 0; i < 3; i++) { c.point[i] = r1 * c0[i] + r0 * c1[i]; c.meta[3 + i] = c0[i]; c.meta[12 + i] = c1[i]; }  // centerA, centerB
+  c.meta[6] = r0 * rsum; c.meta[15] = r1 * rsum;  // radiusA, radiusB
   c.type = 6;
   if (nsq < 1e-6) { c.normal = zero3<double>(); c.depth = rsum; return 1; }
   nsq = std::sqrt(nsq);

@@ -140,6 +140,28 @@ class OracleWorld:
                 "hi": hi[:k], "findex": fi[:k], "x": x[:k], "n_groups": int(counts[2]), "tier_mask": int(counts[3]),
                 "lcp_cache": cache[:ncache.value].copy(), "active_set": mapping[:k].copy()}
 
+    def contact_jacobians(self, q, qd, tau, lcp_cache=None, mode="reference", eps=1e-6):
+        """forwardPass with contacts for ONE world + the BackpropSnapshot Jacobians through the contact solution.
+        mode 'reference': the reference's recipe; 'frozen_fd': central differences of the frozen-active-set velocity map
+        (collision detector re-run at every perturbed state). Matrices are returned [row][col]."""
+        mask = lib().ddo_load_ref_libs(REF_SO.encode(), BOXBOX_SO.encode())
+        if mask != 3:
+            raise RuntimeError("oracle/_ref libraries missing (mask %d)" % mask)
+        n = self.n
+        q, qd, tau = (np.ascontiguousarray(a, dtype=np.float64).reshape(n) for a in (q, qd, tau))
+        cache = np.zeros(1) if lcp_cache is None else np.ascontiguousarray(lcp_cache, dtype=np.float64)
+        nc = 0 if lcp_cache is None else len(lcp_cache)
+        out = [np.zeros((n, n)) for _ in range(5)]
+        info = np.zeros(4, dtype=np.int32)
+        qn, qdn = np.zeros(n), np.zeros(n)
+        lib().ddo_contact_jacobians(self.h, 0 if mode == "reference" else 1, C.c_double(eps), _ptr(q), _ptr(qd), _ptr(tau), _ptr(cache), nc,
+                                    *[_ptr(o) for o in out], info.ctypes.data_as(C.POINTER(C.c_int)), _ptr(qn), _ptr(qdn))
+        names = ("posPos", "posVel", "velPos", "velVel", "forceVel")
+        r = {k: np.ascontiguousarray(o.T) for k, o in zip(names, out)}
+        r.update(num_clamping=int(info[0]), num_upper_bound=int(info[1]), pseudo_inverse=bool(info[2]), structure_kept=bool(info[3]),
+                 q_next=qn, qd_next=qdn)
+        return r
+
     def spatial_inertias(self):
         out = np.empty((self.nb, 6, 6))
         lib().ddo_spatial_inertias(self.h, _ptr(out))

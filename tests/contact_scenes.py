@@ -140,11 +140,66 @@ def free_box_on_floor_states(N, seed):
     return q, qd, tau
 
 
+def box_on_pedestal():
+    """A FreeJoint box resting, yawed and slightly tilted, on a narrow welded pedestal: the manifold mixes VERTEX_FACE /
+    FACE_VERTEX and EDGE_EDGE contacts, and the tilt keeps the reference-face choice of dBoxBox away from a tie."""
+    w = skeletons.WorldDescription()
+    ped = skeletons.Skeleton("pedestal")
+    pb = ped.createWeldJointAndBodyNodePair(None).setTransformFromParentBodyNode(p=[0, 0, -0.5])
+    pb.setBoxShape([0.9, 0.9, 1.0])
+    w.addSkeleton(ped)
+    s = skeletons.Skeleton("box")
+    b = s.createFreeJointAndBodyNodePair(None, "box")
+    b.setBoxShape([1.0, 1.0, 0.5]).setMass(1.0)
+    w.addSkeleton(s)
+    return w
+
+
+def box_on_pedestal_states(N, seed):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 6))
+    q[:, 0:2] = rng.uniform(-0.004, 0.004, (N, 2))
+    q[:, 2] = rng.uniform(0.25, 0.6, N)
+    q[:, 3:5] = rng.uniform(-0.05, 0.05, (N, 2))
+    q[:, 5] = 0.25 - rng.uniform(2e-3, 4e-3, N)
+    qd = rng.uniform(-0.2, 0.2, (N, 6))
+    tau = rng.uniform(-1, 1, (N, 6))
+    return q, qd, tau
+
+
+def sphere_pendulum_on_floor():
+    """Two-link revolute pendulum whose tip sphere touches the floor (SPHERE_BOX / BOX_SPHERE contact gradients), next to
+    a second one-link pendulum whose tip sphere touches the first sphere (SPHERE_SPHERE)."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    s = skeletons.Skeleton("pendulum")
+    a = s.createRevoluteJointAndBodyNodePair(None).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, 1.494])
+    a.setLocalCOM([0, 0, -0.4])
+    b = s.createRevoluteJointAndBodyNodePair(a).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, -0.8])
+    b.setLocalCOM([0, 0, -0.3]).setSphereShape(0.1, p=[0, 0, -0.6])
+    w.addSkeleton(s)
+    t = skeletons.Skeleton("second")
+    c = t.createRevoluteJointAndBodyNodePair(None).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0.195, 0, 1.5])
+    c.setLocalCOM([0, 0, -0.7]).setSphereShape(0.1, p=[0, 0, -1.38])
+    w.addSkeleton(t)
+    return w
+
+
+def sphere_pendulum_on_floor_states(N, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-0.01, 0.01, (N, 3))
+    qd = rng.uniform(-0.5, 0.5, (N, 3))
+    tau = rng.uniform(-1, 1, (N, 3))
+    return q, qd, tau
+
+
 SCENES = {
     "box_stack": (box_stack, box_stack_states),
     "free_box_on_floor": (free_box_on_floor, free_box_on_floor_states),
+    "box_on_pedestal": (box_on_pedestal, box_on_pedestal_states),
     "sliding_box": (sliding_box, sliding_box_states),
     "two_box_stack": (two_box_stack, two_box_stack_states),
     "separate_groups": (separate_groups, separate_groups_states),
     "pendulum_on_floor": (pendulum_on_floor, pendulum_on_floor_states),
+    "sphere_pendulum_on_floor": (sphere_pendulum_on_floor, sphere_pendulum_on_floor_states),
 }
