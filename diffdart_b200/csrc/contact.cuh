@@ -26,7 +26,7 @@ struct ShapeDesc {  // per body collision shape (one ShapeNode per body)
 };
 struct ContactTopo {
   int n_pairs, cmax, kmax, nskel;
-  int gradients, pad0;  // 1: the gradient-enabled solve of forwardPass (short-circuit, standardisation, classification)
+  int gradients, bouncing;  // bouncing: some collidable pair has restitution > 1e-3 (the backward pass refuses those). gradients 1: the gradient-enabled solve of forwardPass (short-circuit, standardisation, classification)
   double clip_depth;
   int pairA[DDB_MAX_BODIES * 4], pairB[DDB_MAX_BODIES * 4];  // collidable pairs in collision-object order
   ShapeDesc shape[DDB_MAX_BODIES];
@@ -89,6 +89,25 @@ struct ContactWork {
   DDB_LCP_DI int* clampIdx() const { return i + 5 * L.cmax + 4 * L.kmax; }
   DDB_LCP_DI int* ubIdx() const { return i + 5 * L.cmax + 5 * L.kmax; }
   DDB_LCP_DI int* activeAll() const { return i + 5 * L.cmax + 6 * L.kmax; }  // active set of every row of the world
+};
+
+// What the backward pass needs of one step's contact stage, kept per snapshot slot (world-major):
+//   doubles  contacts [cmax][26] | massed M^-1 J^T [kmax][nd] | multipliers x [kmax] | pre-constraint velocity v_f [nd]
+//   ints     bodyA [cmax] | bodyB [cmax] | dim [cmax] | ConstraintMapping [kmax] | row info (constraint * 4 + direction) [kmax] | n_contacts, n_rows
+struct ContactSnapLayout {
+  int nd, cmax, kmax;
+  __host__ __device__ size_t oContacts() const { return 0; }
+  __host__ __device__ size_t oMassed() const { return (size_t)cmax * 26; }
+  __host__ __device__ size_t oX() const { return oMassed() + (size_t)kmax * nd; }
+  __host__ __device__ size_t oVf() const { return oX() + kmax; }
+  __host__ __device__ size_t doubles() const { return oVf() + nd; }
+  __host__ __device__ size_t oBodyA() const { return 0; }
+  __host__ __device__ size_t oBodyB() const { return cmax; }
+  __host__ __device__ size_t oDim() const { return 2 * (size_t)cmax; }
+  __host__ __device__ size_t oMapping() const { return 3 * (size_t)cmax; }
+  __host__ __device__ size_t oRowInfo() const { return 3 * (size_t)cmax + kmax; }
+  __host__ __device__ size_t oCounts() const { return 3 * (size_t)cmax + 2 * (size_t)kmax; }
+  __host__ __device__ size_t ints() const { return oCounts() + 2; }
 };
 
 DDB_LCP_DI SV ldSV6(const double* p) { return sv(mk(p[0], p[1], p[2]), mk(p[3], p[4], p[5])); }
@@ -190,7 +209,8 @@ struct ContactStepOut {
 // The whole contact stage for one world. qd_pre: velocities after the unconstrained update (in/out: becomes qd').
 // lcp_cache/n_cache: the solver's cached solution mX (in/out). lv: this world's LCP scratch view storage.
 DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, double* lcpD, int* lcpI, const double* qd_pre_in, double* qd_out,
-                                       int layout, int N, int w, double* lcp_cache, int* n_cache, const PgsOptions& pgs) {
+                                       int layout, int N, int w, double* lcp_cache, int* n_cache, const PgsOptions& pgs,
+                                       double* keepD = nullptr, int* keepI = nullptr) {
   const int nb = c_topo.nb, nd = c_topo.nd;
   const ContactTopo& ct = c_ctopo;
   ContactStepOut out = {0, 0, 0, 0};
@@ -346,6 +366,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         rv -= dotSV6(cw.NB(c, k), cw.V(bb));
         b[o + k] = rv;
         findex[o + k] = -1;
+        if (keepI) keepI[ContactSnapLayout{nd, ct.cmax, ct.kmax}.oRowInfo() + rowsTotal + o + k] = c * 4 + k;
       }
       lo[o] = 0.0; hi[o] = INFINITY;
       if (dim == 3) { for (int t = 1; t < 3; t++) { lo[o + t] = -mu; hi[o + t] = mu; findex[o + t] = o; } }
@@ -603,6 +624,22 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   out.n_rows = rowsTotal;
   if (rowsTotal < 0) out.tier_mask |= 1 << 8;
   *n_cache = mxSize;
+  if (keepD) {
+    const ContactSnapLayout KL{nd, ct.cmax, ct.kmax};
+    const int rows = rowsTotal < 0 ? 0 : rowsTotal;
+    for (int c = 0; c < nc; c++) {
+      for (int z = 0; z < 26; z++) keepD[KL.oContacts() + (size_t)c * 26 + z] = cw.contact(c)[z];
+      keepI[KL.oBodyA() + c] = cw.bodyA()[c]; keepI[KL.oBodyB() + c] = cw.bodyB()[c];
+      keepI[KL.oDim() + c] = cw.groupOf()[c] >= 0 ? cw.dim()[c] : 0;
+    }
+    for (int r = 0; r < rows; r++) {
+      for (int z = 0; z < nd; z++) keepD[KL.oMassed() + (size_t)r * nd + z] = cw.massed(r)[z];
+      keepD[KL.oX() + r] = cw.xall()[r];
+      keepI[KL.oMapping() + r] = ct.gradients ? cw.activeAll()[r] : -2;
+    }
+    for (int z = 0; z < nd; z++) keepD[KL.oVf() + z] = qd_pre_in[vidx(layout, N, nd, w, z)];
+    keepI[KL.oCounts()] = nc; keepI[KL.oCounts() + 1] = rows;
+  }
   // ---- apply the impulses (ContactConstraint::applyImpulse order: normal, t1, t2 per constraint) ----
   for (int i = 0; i < nb; i++) for (int z = 0; z < 6; z++) cw.imp(i)[z] = 0.0;
   bool any = false;

@@ -14,5 +14,14 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* work
 // the contact stage after k_forward: qd (in: unconstrained update, out: post-contact) ; lcp_cache [N][kmax], n_cache [N],
 // counts_out [N][4] = n_contacts, n_rows, n_groups, tier mask
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd_inout, double* lcp_cache,
-                          int* n_cache, int* counts_out, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i);
+                          int* n_cache, int* counts_out, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i,
+                          double* keep_d, int* keep_i);
+// per-slot storage of what the backward pass needs of the contact stage (doubles / ints for N worlds)
+void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* keep_doubles, size_t* keep_ints);
+// BackpropSnapshot::backprop through the contact solution retained in (snap, keep_d, keep_i); lim6 = 6 x [nd] limits or NULL
+cudaError_t contactBackwardLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, const double* keep_d,
+                                  const int* keep_i, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau, double* work_d,
+                                  int* work_i, double* lcp_d, int* lcp_i, const double* lim6, int* status);
+cudaError_t contactUnitVector(cudaStream_t s, int N, int n, int layout, int j, double* out);
+cudaError_t contactScatterRow(cudaStream_t s, int N, int n, int layout, int j, const double* src, double* dst);
 }  // namespace ddb

@@ -99,6 +99,10 @@ struct ddb_handle {
   int cmax = 0, kmax = 0;
   double *cwork_d = nullptr, *clcp_d = nullptr, *lcp_cache = nullptr;
   int *cwork_i = nullptr, *clcp_i = nullptr, *n_cache = nullptr, *ccounts = nullptr;
+  std::vector<double*> keepD;  // per snapshot slot: what the backward needs of the contact stage
+  std::vector<int*> keepI;
+  double* jacTmp = nullptr;    // 5 x [N][n] staging of ddb_jacobians with contacts
+  int* bwdStatus = nullptr;
   // host-buffer path
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
@@ -137,6 +141,18 @@ int enter(ddb_handle* h, cudaStream_t s) {
   DDB_CUDA(h, cudaGetDevice(&dev));
   if (dev != h->device) DDB_CUDA(h, cudaSetDevice(h->device));
   return bindTopology(h, s);
+}
+
+int allocKeep(ddb_handle* h, int slot) {
+  if (!h->hasContacts) return DDB_OK;
+  size_t kd, ki;
+  contactKeepSizes(h->N, h->n, h->cmax, h->kmax, &kd, &ki);
+  if ((int)h->keepD.size() <= slot) { h->keepD.resize(slot + 1, nullptr); h->keepI.resize(slot + 1, nullptr); }
+  if (h->keepD[slot]) return DDB_OK;
+  DDB_CUDA(h, cudaMalloc(&h->keepD[slot], kd * sizeof(double)));
+  DDB_CUDA(h, cudaMalloc(&h->keepI[slot], ki * sizeof(int)));
+  DDB_CUDA(h, cudaMemset(h->keepI[slot], 0, ki * sizeof(int)));
+  return DDB_OK;
 }
 
 size_t snapDoubles(const ddb_handle* h) { return snapDoublesPerWorld(h->topo.snapPairs, h->n, h->topo.has_limits != 0) * (size_t)h->N; }
@@ -255,6 +271,8 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
     DDB_CUDA(h, cudaMemset(h->ccounts, 0, (size_t)h->N * 4 * sizeof(int)));
     DDB_CUDA(h, cudaMemset(h->cwork_d, 0, wd * sizeof(double)));
     DDB_CUDA(h, cudaMemset(h->cwork_i, 0, wi * sizeof(int)));
+    DDB_CUDA(h, cudaMalloc(&h->bwdStatus, (size_t)h->N * sizeof(int)));
+    for (int i = 0; i < slots; i++) { int rk = allocKeep(h, i); if (rk) return rk; }
   }
   return DDB_OK;
 }
@@ -270,8 +288,11 @@ int ddb_destroy(ddb_handle* h) {
   for (double* s : h->slots) if (s) cudaFree(s);
   if (h->lim_dev) cudaFree(h->lim_dev);
   if (h->stage) cudaFree(h->stage);
-  for (void* p : {(void*)h->cwork_d, (void*)h->cwork_i, (void*)h->clcp_d, (void*)h->clcp_i, (void*)h->lcp_cache, (void*)h->n_cache, (void*)h->ccounts})
+  for (void* p : {(void*)h->cwork_d, (void*)h->cwork_i, (void*)h->clcp_d, (void*)h->clcp_i, (void*)h->lcp_cache, (void*)h->n_cache, (void*)h->ccounts,
+                  (void*)h->jacTmp, (void*)h->bwdStatus})
     if (p) cudaFree(p);
+  for (double* p : h->keepD) if (p) cudaFree(p);
+  for (int* p : h->keepI) if (p) cudaFree(p);
   if (h->hstream) cudaStreamDestroy(h->hstream);
   delete h;
   return DDB_OK;
@@ -297,6 +318,8 @@ int ddb_snapshot_reserve(ddb_handle* h, int32_t n_slots, int32_t* n_out) {
     DDB_CUDA(h, cudaMalloc(&p, snapDoubles(h) * sizeof(double)));
     h->slots.push_back(p);
     h->slotValid.push_back(0);
+    int rk = allocKeep(h, (int)h->slots.size() - 1);
+    if (rk) return rk;
   }
   if (n_out) *n_out = (int32_t)h->slots.size();
   return DDB_OK;
@@ -316,7 +339,7 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
     double* cache = lcp_cache_inout ? lcp_cache_inout : h->lcp_cache;
     int* ncache = n_rows_inout ? n_rows_inout : h->n_cache;
     DDB_CUDA(h, contactLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], qdn, cache, ncache, h->ccounts,
-                              active_set_out, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i));
+                              active_set_out, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i, h->keepD[h->cur], h->keepI[h->cur]));
     h->launches++;
     if (status_out)
       DDB_CUDA(h, cudaMemcpy2DAsync(status_out, sizeof(int), h->ccounts + 3, 4 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToDevice, s));
@@ -364,10 +387,17 @@ int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double
 int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau) {
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");
-  if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_backward: the backward pass through contacts is not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
+  if (h->hasContacts) {
+    if (h->ctopo.gradients == 0) return fail(h, DDB_ERR_STATE, "ddb_backward: this handle steps with the solver's gradients disabled (reserved[1] = 1)");
+    if (h->ctopo.bouncing) return fail(h, DDB_ERR_STATE, "ddb_backward: restitution > 0 (bouncing constraints) is not supported by the backward pass");
+    DDB_CUDA(h, contactBackwardLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], h->keepD[h->cur], h->keepI[h->cur],
+                                      gqn, gqdn, gq, gqd, gtau, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i, h->lim_dev, h->bwdStatus));
+    h->launches++;
+    return DDB_OK;
+  }
   h->k.bwd(s, h->N, h->slots[h->cur], gqn, gqdn, gq, gqd, gtau, h->lim);
   DDB_CUDA(h, cudaGetLastError());
   h->launches++;
@@ -377,10 +407,35 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
 int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* vp, double* vv, double* fv) {
   if (!h) return DDB_ERR_INVALID;
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_jacobians: no forward pass retained in the current snapshot slot");
-  if (h->hasContacts) return fail(h, DDB_ERR_STATE, "ddb_jacobians: Jacobians through contacts are not implemented yet (forward only)");
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
+  if (h->hasContacts) {
+    // rows of the five Jacobians by pulling unit loss gradients back through the step (2 n backward passes)
+    if (h->ctopo.gradients == 0) return fail(h, DDB_ERR_STATE, "ddb_jacobians: this handle steps with the solver's gradients disabled (reserved[1] = 1)");
+    if (h->ctopo.bouncing) return fail(h, DDB_ERR_STATE, "ddb_jacobians: restitution > 0 (bouncing constraints) is not supported by the backward pass");
+    const size_t V = (size_t)h->N * h->n;
+    if (!h->jacTmp) DDB_CUDA(h, cudaMalloc(&h->jacTmp, 5 * V * sizeof(double)));
+    double *unit = h->jacTmp, *zero = unit + V, *o1 = unit + 2 * V, *o2 = unit + 3 * V, *o3 = unit + 4 * V;
+    DDB_CUDA(h, cudaMemsetAsync(zero, 0, V * sizeof(double), s));
+    for (int pass = 0; pass < 2; pass++) {
+      if (pass == 0 && !pv && !vv && !fv) continue;
+      if (pass == 1 && !pp && !vp) continue;
+      for (int j = 0; j < h->n; j++) {
+        DDB_CUDA(h, contactUnitVector(s, h->N, h->n, h->topo.layout, j, unit));
+        DDB_CUDA(h, contactBackwardLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], h->keepD[h->cur],
+                                          h->keepI[h->cur], pass == 0 ? zero : unit, pass == 0 ? unit : zero, o1, o2, o3, h->cwork_d, h->cwork_i,
+                                          h->clcp_d, h->clcp_i, nullptr, nullptr));
+        h->launches++;
+        double* dq = pass == 0 ? pv : pp;
+        double* dqd = pass == 0 ? vv : vp;
+        if (dq) DDB_CUDA(h, contactScatterRow(s, h->N, h->n, h->topo.layout, j, o1, dq));
+        if (dqd) DDB_CUDA(h, contactScatterRow(s, h->N, h->n, h->topo.layout, j, o2, dqd));
+        if (pass == 0 && fv) DDB_CUDA(h, contactScatterRow(s, h->N, h->n, h->topo.layout, j, o3, fv));
+      }
+    }
+    return DDB_OK;
+  }
   h->k.jac(s, h->N, h->slots[h->cur], pp, pv, vp, vv, fv);
   DDB_CUDA(h, cudaGetLastError());
   h->launches++;

@@ -544,9 +544,14 @@ DDB_DI void freeJointPosJacobians(const double* q6, const double* qd6, double dt
     }
 }
 
-template <int NB, bool CHAIN, class Out, class OutFree>
-DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFree outFree) {
+// MODE 0: velocities / accelerations / gravity of the step as retained in the snapshot.
+// MODE 1: the same with dA[i] added to every body acceleration (the joint accelerations of the contact impulses).
+// MODE 2: V = 0, G = 0, A = dA: Phi = mu^T M(q) a, the bilinear mass-matrix form used for d(M^-1 w)/dq terms.
+template <int NB, bool CHAIN, int MODE, class Out, class OutFree>
+DDB_DI void idAdjointEx(const Snap& sn, int nb, BwdScratch<NB>& ws, const SV* dA, Out out, OutFree outFree) {
   typedef Tree<NB, CHAIN> TS;
+  auto accOf = [&](int i) { return MODE == 2 ? dA[i] : (MODE == 1 ? sn.ldSV(i, 9) + dA[i] : sn.ldSV(i, 9)); };
+  auto velOf = [&](int i) { return MODE == 2 ? svzero() : sn.ldSV(i, 6); };
   const double* mu = ws.mu;
   const SV* U = ws.U;
   SV *pU = ws.pU, *pA = ws.pA, *pV = ws.pV;
@@ -555,12 +560,12 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFr
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
-    const SV Vi = sn.ldSV(i, 6), Ai = sn.ldSV(i, 9);
+    const SV Vi = velOf(i), Ai = accOf(i);
     if (!CHAIN && b.type == DDB_JOINT_FREE) {
-      double qd6[6], qdd6[6];
-      ld6(sn, i, 48, qd6); ld6(sn, i, 51, qdd6);
+      double qd6[6] = {0, 0, 0, 0, 0, 0};
+      if (MODE != 2) ld6(sn, i, 48, qd6);
       const double2 g0 = sn.ld(i, 54), g1 = sn.ld(i, 55);
-      const V3 Gi = mk(g0.x, g0.y, g1.x);
+      const V3 Gi = MODE == 2 ? mk(0, 0, 0) : mk(g0.x, g0.y, g1.x);
       const SV Ui = U[i];
       SV IV = mul(b.I, Vi);
       SV Aeff = Ai;
@@ -574,7 +579,7 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFr
       Xf t = sn.ldT(i);
       // what the parent contributes, expressed in this body's frame
       SV XU = svzero(), XV = svzero(), XA = svzero();
-      if (p >= 0) { XU = AdInvT(t, U[p]); XV = AdInvT(t, sn.ldSV(p, 6)); XA = AdInvT(t, sn.ldSV(p, 9)); }
+      if (p >= 0) { XU = AdInvT(t, U[p]); XV = AdInvT(t, velOf(p)); XA = AdInvT(t, accOf(p)); }
       // joint coordinates of the FreeJoint: the child frame moves with twist S6 * jhat_k(q) per unit q_k,
       // jhat_k = [Jr(q_r) e_k; 0] (k < 3), [0; R(q_r)^T e_k] (k >= 3)
       double q6[6], dq6[6], dqd6[6];
@@ -599,9 +604,9 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFr
       }
       return;
     }
-    const double qdi = sn.ld(i, 15).y;
+    const double qdi = MODE == 2 ? 0.0 : sn.ld(i, 15).y;
     const double2 g0 = sn.ld(i, 16), g1 = sn.ld(i, 17);
-    const V3 Gi = mk(g0.x, g0.y, g1.x);
+    const V3 Gi = MODE == 2 ? mk(0, 0, 0) : mk(g0.x, g0.y, g1.x);
     const double qddi = g1.y;
     const SV Ui = U[i];
     SV IV = mul(b.I, Vi);
@@ -618,6 +623,7 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFr
       SV XU = Ui - mu[i] * b.S;
       SV XV = Vi - Sq;
       SV XA = Ai - qddi * b.S - ad(Vi, Sq);
+      if (MODE != 0) XA = (p >= 0) ? AdInvT(sn.ldT(i), accOf(p)) : svzero();
       double dq = -(dot(dad(b.S, Ub), XU) + dot(dad(b.S, Ab), XA) + dot(dad(b.S, Vb), XV)) - dot(Gb, cross(b.S.w, Gi));
       out(TS::dofOf(i), dq, dqd);
     }
@@ -639,6 +645,32 @@ DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFr
     for (int i = 0; i < nb; i++) init(i);
 #pragma unroll 1
     for (int i = nb - 1; i >= 0; i--) up(i);
+  }
+}
+
+template <int NB, bool CHAIN, class Out, class OutFree>
+DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFree outFree) {
+  idAdjointEx<NB, CHAIN, 0>(sn, nb, ws, nullptr, out, outFree);
+}
+
+// U_i = J_i mu: body twists under joint rates mu (fills ws.U / ws.mu exactly as solveInvMass leaves them)
+template <int NB, class RateF>
+DDB_DI void twistsFromRates(const Snap& sn, int nb, RateF rateOf, SV* U, double* mu) {
+#pragma unroll 1
+  for (int i = 0; i < nb; i++) {
+    const DevBody& b = c_topo.b[i];
+    SV Up = svzero();
+    if (b.parent >= 0) Up = AdInvT(sn.ldT(i), U[b.parent]);
+    if (b.type == DDB_JOINT_FREE) {
+      double r6[6];
+      for (int k = 0; k < 6; k++) r6[k] = rateOf(b.dof + k);
+      if (mu) mu[i] = 0.0;
+      U[i] = Up + mulS6(b, r6);
+    } else {
+      const double m = b.type != DDB_JOINT_WELD ? rateOf(b.dof) : 0.0;
+      if (mu) mu[i] = m;
+      U[i] = Up + m * b.S;
+    }
   }
 }
 

@@ -176,6 +176,7 @@ inline int foldContactTopology(const ddb_topology* topo, const ddb_params* param
         if (!ct.shape[i].reactive && !ct.shape[j].reactive) continue;    // such contacts never become active constraints
         if (np >= DDB_MAX_BODIES * 4) { err = "too many collidable pairs"; return DDB_ERR_INVALID; }
         ct.pairA[np] = i; ct.pairB[np] = j; np++;
+        if (ct.shape[i].restitution * ct.shape[j].restitution > 1e-3) ct.bouncing = 1;
       }
     ct.n_pairs = np;
     int cap = params->reserved[0] > 0 ? params->reserved[0] : 64;  // reserved[0]: max contacts per world

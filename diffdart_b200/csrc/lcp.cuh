@@ -718,6 +718,161 @@ DDB_LCP_DI int codSolveDev(const LcpView& v, int n) {
   return rank;
 }
 
+// The same complete orthogonal decomposition kept as a factorisation so that P b and P^T a (P = Q^+) come out of ONE
+// decomposition, as Eigen's `Qfactored.solve(b)` / `Qfactored.pseudoInverse()` do at BackpropSnapshot.cpp:3875-3876,
+// 3925-3932. Storage as codSolveDev; the QR reflector scales are kept in ell, those of the right-hand reflections in d.
+DDB_LCP_DI int codFactorDev(const LcpView& v, int n) {
+  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * 32]; };
+  const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
+  for (int j = 0; j < n; j++) {
+    v.p(j) = j;
+    double s = 0;
+    for (int i = 0; i < n; i++) s += Q(i, j) * Q(i, j);
+    v.Dell(j) = v.ell(j) = sqrt(s);
+  }
+  double maxNorm = 0;
+  for (int j = 0; j < n; j++) maxNorm = fmax(maxNorm, v.Dell(j));
+  const double thresholdHelper = (maxNorm * eps) * (maxNorm * eps) / double(n);
+  const double downdateThreshold = sqrt(eps);
+  int nonzeroPivots = n;
+  double maxPivot = 0;
+  for (int k = 0; k < n; k++) {
+    int big = k;
+    for (int j = k + 1; j < n; j++) if (v.Dell(j) > v.Dell(big)) big = j;
+    const double bigSq = v.Dell(big) * v.Dell(big);
+    if (nonzeroPivots == n && bigSq < thresholdHelper * double(n - k)) nonzeroPivots = k;
+    if (big != k) {
+      for (int i = 0; i < n; i++) { double t = Q(i, k); Q(i, k) = Q(i, big); Q(i, big) = t; }
+      double t = v.Dell(k); v.Dell(k) = v.Dell(big); v.Dell(big) = t;
+      t = v.ell(k); v.ell(k) = v.ell(big); v.ell(big) = t;
+      int ti = v.p(k); v.p(k) = v.p(big); v.p(big) = ti;
+    }
+    double c0 = Q(k, k), tailSq = 0;
+    for (int i = k + 1; i < n; i++) tailSq += Q(i, k) * Q(i, k);
+    double beta, t;
+    if (tailSq <= tiny) {
+      t = 0; beta = c0;
+      for (int i = k + 1; i < n; i++) Q(i, k) = 0;
+    } else {
+      beta = sqrt(c0 * c0 + tailSq);
+      if (c0 >= 0) beta = -beta;
+      for (int i = k + 1; i < n; i++) Q(i, k) /= (c0 - beta);
+      t = (beta - c0) / beta;
+    }
+    Q(k, k) = beta;
+    if (fabs(beta) > maxPivot) maxPivot = fabs(beta);
+    for (int j = k + 1; j < n; j++) {
+      double s = Q(k, j);
+      for (int i = k + 1; i < n; i++) s += Q(i, k) * Q(i, j);
+      s *= t;
+      Q(k, j) -= s;
+      for (int i = k + 1; i < n; i++) Q(i, j) -= s * Q(i, k);
+    }
+    for (int j = k + 1; j < n; j++) {
+      if (v.Dell(j) != 0) {
+        double temp = fabs(Q(k, j)) / v.Dell(j);
+        temp = (1.0 + temp) * (1.0 - temp);
+        temp = temp < 0 ? 0 : temp;
+        const double r = v.Dell(j) / v.ell(j);
+        const double temp2 = temp * r * r;
+        if (temp2 <= downdateThreshold) {
+          double s = 0;
+          for (int i = k + 1; i < n; i++) s += Q(i, j) * Q(i, j);
+          v.ell(j) = v.Dell(j) = sqrt(s);
+        } else {
+          v.Dell(j) *= sqrt(temp);
+        }
+      }
+    }
+    v.ell(k) = t;  // column k is final: its norm slots are free
+  }
+  int rank = 0;
+  const double premult = maxPivot * eps * double(n);
+  for (int i = 0; i < nonzeroPivots; i++) if (fabs(Q(i, i)) > premult) rank++;
+  if (rank > 0 && rank < n) {
+    for (int k = rank - 1; k >= 0; k--) {
+      double c0 = Q(k, k), tailSq = 0;
+      for (int j = rank; j < n; j++) tailSq += Q(k, j) * Q(k, j);
+      double beta, t;
+      if (tailSq <= tiny) { t = 0; beta = c0; for (int j = rank; j < n; j++) Q(k, j) = 0; }
+      else {
+        beta = sqrt(c0 * c0 + tailSq);
+        if (c0 >= 0) beta = -beta;
+        for (int j = rank; j < n; j++) Q(k, j) /= (c0 - beta);
+        t = (beta - c0) / beta;
+      }
+      for (int i = 0; i < k; i++) {
+        double s = Q(i, k);
+        for (int j = rank; j < n; j++) s += Q(i, j) * Q(k, j);
+        s *= t;
+        Q(i, k) -= s;
+        for (int j = rank; j < n; j++) Q(i, j) -= s * Q(k, j);
+      }
+      Q(k, k) = beta;
+      v.d(k) = t;
+    }
+  }
+  return rank;
+}
+// out = P rhs (transposed = false) or P^T rhs (transposed = true) from codFactorDev's factorisation; dw / tmp are scratch
+template <class RhsF, class OutF>
+DDB_LCP_DI void codApplyDev(const LcpView& v, int n, int rank, bool transposed, RhsF rhs, OutF out) {
+  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * 32]; };
+  if (rank == 0) { for (int j = 0; j < n; j++) out(j, 0.0); return; }
+  if (!transposed) {
+    for (int i = 0; i < n; i++) v.dw(i) = rhs(i);
+    for (int k = 0; k < n; k++) {
+      double s = v.dw(k);
+      for (int i = k + 1; i < n; i++) s += Q(i, k) * v.dw(i);
+      s *= v.ell(k);
+      v.dw(k) -= s;
+      for (int i = k + 1; i < n; i++) v.dw(i) -= s * Q(i, k);
+    }
+    for (int i = rank - 1; i >= 0; i--) {
+      double s = v.dw(i);
+      for (int j = i + 1; j < rank; j++) s -= Q(i, j) * v.tmp(j);
+      v.tmp(i) = s / Q(i, i);
+    }
+    for (int j = rank; j < n; j++) v.tmp(j) = 0.0;
+    if (rank < n) {
+      for (int k = 0; k < rank; k++) {
+        double s = v.tmp(k);
+        for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
+        s *= v.d(k);
+        v.tmp(k) -= s;
+        for (int j = rank; j < n; j++) v.tmp(j) -= s * Q(k, j);
+      }
+    }
+    for (int j = 0; j < n; j++) v.dw(v.p(j)) = v.tmp(j);
+    for (int j = 0; j < n; j++) out(j, v.dw(j));
+  } else {
+    for (int j = 0; j < n; j++) v.tmp(j) = rhs(v.p(j));
+    if (rank < n) {
+      for (int k = rank - 1; k >= 0; k--) {
+        double s = v.tmp(k);
+        for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
+        s *= v.d(k);
+        v.tmp(k) -= s;
+        for (int j = rank; j < n; j++) v.tmp(j) -= s * Q(k, j);
+      }
+    }
+    for (int i = 0; i < rank; i++) {  // T^T y = z
+      double s = v.tmp(i);
+      for (int j = 0; j < i; j++) s -= Q(j, i) * v.dw(j);
+      v.dw(i) = s / Q(i, i);
+    }
+    for (int j = rank; j < n; j++) v.dw(j) = 0.0;
+    for (int k = n - 1; k >= 0; k--) {
+      double s = v.dw(k);
+      for (int i = k + 1; i < n; i++) s += Q(i, k) * v.dw(i);
+      s *= v.ell(k);
+      v.dw(k) -= s;
+      for (int i = k + 1; i < n; i++) v.dw(i) -= s * Q(i, k);
+    }
+    for (int j = 0; j < n; j++) out(j, v.dw(j));
+  }
+}
+
 // LCPUtils::isLCPSolutionValid (LCPUtils.cpp:12-81), tol 1e-5. Af(i,j), xf, bf, hif, lof, fif are accessors
 // on the ORIGINAL problem (the solvers destroy their copies).
 template <class AF, class XF, class BF, class HF, class LF, class IF>

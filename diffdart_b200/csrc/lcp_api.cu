@@ -2,6 +2,7 @@
 #include <cstdio>
 #include "../../include/ddb.h"
 #include "contact.cuh"
+#include "contact_bwd.cuh"
 #include "contact_api.h"
 
 using namespace ddb;
@@ -72,22 +73,68 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
 __global__ void __launch_bounds__(64)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
           int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
-          int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs) {
+          int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
+          int* __restrict__ keep_i) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L};
+  const ContactSnapLayout KL{L.nd, L.cmax, L.kmax};
   const size_t warp = w >> 5, lane = w & 31;
   double* ld = lcp_d + warp * lcpScratchDoubles(L.kmax) * 32 + lane;
   int* li = lcp_i + warp * lcpScratchInts(L.kmax) * 32 + lane;
   int nc = n_cache[w];
-  ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs);
+  ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs,
+                                  keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr);
   n_cache[w] = nc;
   counts[4 * w] = o.n_contacts; counts[4 * w + 1] = o.n_rows; counts[4 * w + 2] = o.n_groups; counts[4 * w + 3] = o.tier_mask;
   if (active_out) {
     // ConstraintMapping per LCP row (ConstrainedGroupGradientMatrices.hpp:32-38); rows beyond n_rows are IRRELEVANT (-4)
     for (int k = 0; k < L.kmax; k++) active_out[(size_t)w * L.kmax + k] = (k < o.n_rows && c_ctopo.gradients) ? cw.activeAll()[k] : -4;
   }
+}
+
+// BackpropSnapshot::backprop through the contact solution of the step retained in this slot, one world per thread
+template <int NB>
+__global__ void __launch_bounds__(64)
+k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL, double* __restrict__ snap, const double* __restrict__ keep_d,
+                   const int* __restrict__ keep_i, const double* __restrict__ gqn, const double* __restrict__ gqdn, double* __restrict__ gq,
+                   double* __restrict__ gqd, double* __restrict__ gtau, double* __restrict__ work_d, int* __restrict__ work_i,
+                   double* __restrict__ lcp_d, int* __restrict__ lcp_i, Limits lim, int* __restrict__ status) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  ContactBwdWork bw{work_d + (size_t)w * BL.doubles(), work_i + (size_t)w * BL.ints(), BL};
+  const size_t warp = w >> 5, lane = w & 31;
+  double* ld = lcp_d + warp * lcpScratchDoubles(BL.kmax) * 32 + lane;
+  int* li = lcp_i + warp * lcpScratchInts(BL.kmax) * 32 + lane;
+  const int st = contactBackwardWorld<NB>(sn, KL, keep_d + (size_t)w * KL.doubles(), keep_i + (size_t)w * KL.ints(), bw, ld, li, gqn, gqdn, gq,
+                                          gqd, gtau, layout, N, w);
+  if (status) status[w] = st;
+  if (c_topo.has_limits) {
+    const int n = c_topo.nd;
+    const double* clip = clipSection(snap, c_topo.nb, N);
+    for (int d = 0; d < n; d++) {
+      const size_t ix = vidx(layout, N, n, w, d);
+      gq[ix] = clipGrad(gq[ix], clip[(size_t)d * N + w], lim.pos_lo[d], lim.pos_hi[d]);
+      gqd[ix] = clipGrad(gqd[ix], clip[(size_t)(n + d) * N + w], lim.vel_lo[d], lim.vel_hi[d]);
+      gtau[ix] = clipGrad(gtau[ix], clip[(size_t)(2 * n + d) * N + w], lim.frc_lo[d], lim.frc_hi[d]);
+    }
+  }
+}
+
+// helpers of ddb_jacobians with contacts: unit loss gradients in, one Jacobian row out
+__global__ void k_unit_vector(int N, int n, int layout, int j, double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * n) return;
+  const int w = i / n, d = i % n;
+  out[vidx(layout, N, n, w, d)] = d == j ? 1.0 : 0.0;
+}
+__global__ void k_scatter_row(int N, int n, int layout, int j, const double* __restrict__ src, double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * n) return;
+  const int w = i / n, d = i % n;
+  dst[(size_t)w * n * n + (size_t)d * n + j] = src[vidx(layout, N, n, w, d)];
 }
 
 }  // namespace
@@ -102,16 +149,48 @@ size_t contactTopoBytes() { return sizeof(ContactTopo); }
 void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, size_t* wi, size_t* ld, size_t* li) {
   ContactLayout L{nb, nd, cmax, kmax};
   const size_t warps = ((size_t)N + 31) / 32;
-  *wd = (size_t)N * L.doubles();
-  *wi = (size_t)N * L.ints();
+  ContactBwdLayout BL{nb, nd, kmax};
+  *wd = (size_t)N * (L.doubles() > BL.doubles() ? L.doubles() : BL.doubles());
+  *wi = (size_t)N * (L.ints() > BL.ints() ? L.ints() : BL.ints());
   *ld = warps * lcpScratchDoubles(kmax) * 32;
   *li = warps * lcpScratchInts(kmax) * 32;
 }
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd, double* lcp_cache,
-                          int* n_cache, int* counts, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i) {
+                          int* n_cache, int* counts, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i, double* keep_d,
+                          int* keep_i) {
   ContactLayout L{nb, nd, cmax, kmax};
   PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
-  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs);
+  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+                                         keep_d, keep_i);
+  return cudaGetLastError();
+}
+void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* kd, size_t* ki) {
+  ContactSnapLayout KL{nd, cmax, kmax};
+  *kd = (size_t)N * KL.doubles();
+  *ki = (size_t)N * KL.ints();
+}
+cudaError_t contactBackwardLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, const double* keep_d,
+                                  const int* keep_i, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau, double* work_d,
+                                  int* work_i, double* lcp_d, int* lcp_i, const double* lim6, int* status) {
+  ContactSnapLayout KL{nd, cmax, kmax};
+  ContactBwdLayout BL{nb, nd, kmax};
+  Limits lim{lim6, lim6 ? lim6 + nd : nullptr, lim6 ? lim6 + 2 * nd : nullptr, lim6 ? lim6 + 3 * nd : nullptr, lim6 ? lim6 + 4 * nd : nullptr,
+             lim6 ? lim6 + 5 * nd : nullptr};
+  const int grid = (N + 63) / 64;
+#define DDB_CB(NBV) k_contact_backward<NBV><<<grid, 64, 0, s>>>(N, layout, KL, BL, snap, keep_d, keep_i, gqn, gqdn, gq, gqd, gtau, work_d, work_i, lcp_d, lcp_i, lim, status)
+  if (nb <= 8) DDB_CB(8);
+  else if (nb <= 16) DDB_CB(16);
+  else if (nb <= 32) DDB_CB(32);
+  else DDB_CB(DDB_MAX_BODIES);
+#undef DDB_CB
+  return cudaGetLastError();
+}
+cudaError_t contactUnitVector(cudaStream_t s, int N, int n, int layout, int j, double* out) {
+  k_unit_vector<<<(N * n + 255) / 256, 256, 0, s>>>(N, n, layout, j, out);
+  return cudaGetLastError();
+}
+cudaError_t contactScatterRow(cudaStream_t s, int N, int n, int layout, int j, const double* src, double* dst) {
+  k_scatter_row<<<(N * n + 255) / 256, 256, 0, s>>>(N, n, layout, j, src, dst);
   return cudaGetLastError();
 }
 }  // namespace ddb

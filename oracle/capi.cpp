@@ -222,23 +222,31 @@ void ddo_step_contacts(void* h, const double* q, const double* qd, const double*
 
 // One world: forwardPass with contacts (gradient-enabled solve) + the BackpropSnapshot Jacobians through the contact
 // solution (reference recipe). Matrices n x n column-major; info[0..2] = numClamping, numUpperBound, pseudo-inverse branch.
+// x_override (optional, all rows of the world in group order): multipliers to evaluate the Jacobians at.
 // mode 0: analytic (reference recipe); mode 1: central differences (eps) of the frozen-active-set velocity map with the
 // collision detector re-run at every perturbed state (posVel / velVel / forceVel only; info[3] = 1 when every
 // perturbed state kept the contact structure).
 void ddo_contact_jacobians(void* h, int mode, double eps, const double* q, const double* qd, const double* tau, const double* lcp_cache,
                            int n_cache, double* posPos, double* posVel, double* velPos, double* velVel, double* forceVel, int* info,
-                           double* qn, double* qdn) {
+                           double* qn, double* qdn, const double* x_override, int n_override, double* fc_vs_ls) {
   const Model& M = ((OracleWorld*)h)->M;
   const int n = M.nd;
   std::vector<double> cache(lcp_cache, lcp_cache + n_cache);
   ContactStepResult R;
   stepWithContacts(M, q, qd, tau, cache, R, true);
   if (qn) for (int i = 0; i < n; i++) { qn[i] = R.qNext[i]; qdn[i] = R.qdNext[i]; }
+  if (x_override) {
+    // The LCP multipliers of a rank-deficient group are determined only up to the null space of A (the next state does not
+    // depend on it, the reference's Jacobian formulas do): evaluate the Jacobians at the caller's multipliers.
+    int row = 0;
+    for (GroupLCP& g : R.groups) for (int i = 0; i < g.n && row < n_override; i++) g.x[i] = x_override[row++];
+  }
   Jacobians J;
   ContactGradInfo gi;
   if (mode == 0) {
     jacobiansReferenceContact(M, q, qd, tau, R, J, &gi);
     info[0] = gi.numClamping; info[1] = gi.numUpperBound; info[2] = gi.pseudoInverseBranch ? 1 : 0; info[3] = 1;
+    if (fc_vs_ls) *fc_vs_ls = gi.fcVsLeastSquares;
   } else {
     J.resize(n);
     bool ok = true;

@@ -23,6 +23,8 @@
 #pragma once
 #include "dd_contact.hpp"
 #include "dd_step.hpp"
+#include <cstdio>
+#include <cstdlib>
 
 namespace ddo {
 
@@ -277,6 +279,7 @@ inline Mat codSolveMat(const Mat& Q, const Mat& B) {
 struct ContactGradInfo {  // what the test compares / reports
   int numClamping = 0, numUpperBound = 0;
   bool pseudoInverseBranch = false;
+  double fcVsLeastSquares = 0.0;  // max |f_c - Q^+ b|: 0 when the multipliers were standardised
 };
 
 // BackpropSnapshot Jacobians of one step with contacts, from the result of stepWithContacts(gradients = true).
@@ -419,6 +422,7 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
       return add(o, mm(tr(E), add(dAubT(MAcr), mm(tr(Aub), inner))));
     };
     const std::vector<double> r1 = matvec(P, bc);
+    if (info) for (int i = 0; i < nc; i++) info->fcVsLeastSquares = std::max(info->fcVsLeastSquares, std::abs(r1[i] - fc[i]));
     const Mat imprecision = add(I_c, mm(Q, P), -1.0);
     double sq = 0;
     for (double v : imprecision.a) sq += v * v;

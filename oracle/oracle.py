@@ -140,10 +140,12 @@ class OracleWorld:
                 "hi": hi[:k], "findex": fi[:k], "x": x[:k], "n_groups": int(counts[2]), "tier_mask": int(counts[3]),
                 "lcp_cache": cache[:ncache.value].copy(), "active_set": mapping[:k].copy()}
 
-    def contact_jacobians(self, q, qd, tau, lcp_cache=None, mode="reference", eps=1e-6):
+    def contact_jacobians(self, q, qd, tau, lcp_cache=None, mode="reference", eps=1e-6, x_override=None):
         """forwardPass with contacts for ONE world + the BackpropSnapshot Jacobians through the contact solution.
         mode 'reference': the reference's recipe; 'frozen_fd': central differences of the frozen-active-set velocity map
-        (collision detector re-run at every perturbed state). Matrices are returned [row][col]."""
+        (collision detector re-run at every perturbed state). Matrices are returned [row][col]. x_override: evaluate the
+        Jacobians at these LCP multipliers (all rows, group order) instead of the oracle's own solution — the multipliers of a
+        rank-deficient group are fixed only up to the null space of A."""
         mask = lib().ddo_load_ref_libs(REF_SO.encode(), BOXBOX_SO.encode())
         if mask != 3:
             raise RuntimeError("oracle/_ref libraries missing (mask %d)" % mask)
@@ -154,12 +156,15 @@ class OracleWorld:
         out = [np.zeros((n, n)) for _ in range(5)]
         info = np.zeros(4, dtype=np.int32)
         qn, qdn = np.zeros(n), np.zeros(n)
+        xo = None if x_override is None else np.ascontiguousarray(x_override, dtype=np.float64)
+        fc_ls = C.c_double(0.0)
         lib().ddo_contact_jacobians(self.h, 0 if mode == "reference" else 1, C.c_double(eps), _ptr(q), _ptr(qd), _ptr(tau), _ptr(cache), nc,
-                                    *[_ptr(o) for o in out], info.ctypes.data_as(C.POINTER(C.c_int)), _ptr(qn), _ptr(qdn))
+                                    *[_ptr(o) for o in out], info.ctypes.data_as(C.POINTER(C.c_int)), _ptr(qn), _ptr(qdn), _ptr(xo),
+                                    0 if xo is None else len(xo), C.byref(fc_ls))
         names = ("posPos", "posVel", "velPos", "velVel", "forceVel")
         r = {k: np.ascontiguousarray(o.T) for k, o in zip(names, out)}
         r.update(num_clamping=int(info[0]), num_upper_bound=int(info[1]), pseudo_inverse=bool(info[2]), structure_kept=bool(info[3]),
-                 q_next=qn, qd_next=qdn)
+                 q_next=qn, qd_next=qdn, fc_vs_least_squares=fc_ls.value)
         return r
 
     def spatial_inertias(self):

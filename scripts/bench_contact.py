@@ -22,8 +22,21 @@ for _ in range(steps):
     world.setForces(cu(tau)); forwardPass(world)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
+# backward through the contact solution of the last step
+from diffdart_b200.world import LossGradient
+snap = forwardPass(world, idempotent=True)
+nxt, this = LossGradient(), LossGradient()
+g = torch.randn(N, q.shape[1], dtype=torch.float64, device="cuda")
+nxt.lossWrtPosition, nxt.lossWrtVelocity = g, g.clone()
+snap.backprop(world, this, nxt)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(steps):
+    snap.backprop(world, this, nxt)
+e1.record(); torch.cuda.synchronize()
+ms_bwd = e0.elapsed_time(e1) / steps
 counts = np.zeros((N, 4), dtype=np.int32)
 world._lib.ddb_contact_debug_host(world._h, counts.ctypes.data_as(C.c_void_p), -1, None, None, None, None, None, None, None, None, None)
 tiers = {int(k): int(v) for k, v in zip(*np.unique(counts[:, 3], return_counts=True))}
-print(json.dumps({"workload": "box_stack forward only", "N": N, "ms_per_step": ms, "world_steps_per_s": N / (ms * 1e-3),
+print(json.dumps({"workload": "box_stack forward, backward", "N": N, "ms_per_step": ms, "ms_backward": ms_bwd, "world_steps_per_s": N / ((ms + ms_bwd) * 1e-3),
                   "contacts_mean": float(counts[:, 0].mean()), "rows_mean": float(counts[:, 1].mean()), "tier_mask_hist": tiers}))

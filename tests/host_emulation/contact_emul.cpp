@@ -8,6 +8,7 @@ static dim3_ blockIdx, threadIdx, blockDim;
 inline void sincos(double x, double* s, double* c);
 #include "kernels_nocuda.cuh"
 #include "contact_nocuda.cuh"
+#include "contact_bwd_nocuda.cuh"
 #include "fold.h"
 using namespace ddb;
 
@@ -56,5 +57,55 @@ extern "C" int emul_step_backward(const ddb_topology* topo, const ddb_params* pa
   k_backward<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), gqn, gqdn, gq, gqd, gtau, lim);
   k_jacobians<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), posPos, posVel, velPos, velVel, forceVel);
   k_inv_mass<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), minv);
+  return 0;
+}
+
+// forwardPass with contacts (gradient-enabled solve) followed by the backward through the contact solution, one world
+extern "C" int emul_contact_step_backward(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
+                                          double* lcp_cache, int* n_cache, const double* gqn, const double* gqdn, double* qn, double* qdn,
+                                          double* gq, double* gqd, double* gtau, int* status_out, double* x_out, int* rows_out) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
+  const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  ContactLayout L{nb, nd, cmax, kmax};
+  ContactSnapLayout KL{nd, cmax, kmax};
+  ContactBwdLayout BL{nb, nd, kmax};
+  std::vector<double> wd(std::max(L.doubles(), BL.doubles()), 0.0), ld(lcpScratchDoubles(kmax) * 32, 0.0), kd(KL.doubles(), 0.0);
+  std::vector<int> wi(std::max(L.ints(), BL.ints()), 0), li(lcpScratchInts(kmax) * 32, 0), ki(KL.ints(), 0);
+  Snap sn{reinterpret_cast<double2*>(snap.data()), N, 0};
+  ContactWork cw{wd.data(), wi.data(), L};
+  PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
+  if (c_ctopo.n_pairs > 0) contactStage(sn, cw, ld.data() + 3, li.data() + 3, qdn, qdn, c_topo.layout, N, 0, lcp_cache, n_cache, pgs, kd.data(), ki.data());
+  ContactBwdWork bw{wd.data(), wi.data(), BL};
+  const int st = contactBackwardWorld<DDB_MAX_BODIES>(sn, KL, kd.data(), ki.data(), bw, ld.data() + 3, li.data() + 3, gqn, gqdn, gq, gqd, gtau,
+                                                      c_topo.layout, N, 0);
+  if (status_out) *status_out = st;
+  const int rows = ki[KL.oCounts() + 1];
+  if (rows_out) *rows_out = rows;
+  if (x_out) for (int r = 0; r < rows; r++) x_out[r] = kd[KL.oX() + r];
+  return 0;
+}
+
+// d/dq [mu_a^T M(q) a_b] through the MODE-2 reverse sweep (the bilinear mass-matrix terms of the contact backward)
+extern "C" int emul_mass_bilinear_grad(const ddb_topology* topo, const ddb_params* params, const double* q, const double* mu_a, const double* a_b,
+                                       double* dq_out) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  const int N = 1, nb = c_topo.nb, nd = c_topo.nd;
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0), zero(nd, 0.0), qn(nd), qdn(nd);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, zero.data(), zero.data(), qn.data(), qdn.data(), snap.data());
+  Snap sn{reinterpret_cast<double2*>(snap.data()), N, 0};
+  ContactBwdLocals<DDB_MAX_BODIES> loc;
+  twistsFromRates<DDB_MAX_BODIES>(sn, nb, [&](int d) { return mu_a[d]; }, loc.ws.U, loc.ws.mu);
+  twistsFromRates<DDB_MAX_BODIES>(sn, nb, [&](int d) { return a_b[d]; }, loc.dA, nullptr);
+  idAdjointEx<DDB_MAX_BODIES, false, 2>(sn, nb, loc.ws, loc.dA, [&](int d, double dq, double) { dq_out[d] = dq; },
+                                        [&](int body, const double* dq6, const double*) { for (int k = 0; k < 6; k++) dq_out[c_topo.b[body].dof + k] = dq6[k]; });
   return 0;
 }

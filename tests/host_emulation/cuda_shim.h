@@ -5,6 +5,8 @@
 #include <cmath>
 #include <cstddef>
 #include <cstring>
+#include <cstdio>
+#include <cstdlib>
 #define __device__
 #define __host__
 #define __forceinline__ inline
