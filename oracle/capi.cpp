@@ -228,7 +228,8 @@ void ddo_step_contacts(void* h, const double* q, const double* qd, const double*
 // perturbed state kept the contact structure).
 void ddo_contact_jacobians(void* h, int mode, double eps, const double* q, const double* qd, const double* tau, const double* lcp_cache,
                            int n_cache, double* posPos, double* posVel, double* velPos, double* velVel, double* forceVel, int* info,
-                           double* qn, double* qdn, const double* x_override, int n_override, double* fc_vs_ls) {
+                           double* qn, double* qdn, const double* x_override, int n_override, double* fc_vs_ls, const int* mapping_override, double q_noise) {
+  qNoise() = q_noise;
   const Model& M = ((OracleWorld*)h)->M;
   const int n = M.nd;
   std::vector<double> cache(lcp_cache, lcp_cache + n_cache);
@@ -239,7 +240,13 @@ void ddo_contact_jacobians(void* h, int mode, double eps, const double* q, const
     // The LCP multipliers of a rank-deficient group are determined only up to the null space of A (the next state does not
     // depend on it, the reference's Jacobian formulas do): evaluate the Jacobians at the caller's multipliers.
     int row = 0;
-    for (GroupLCP& g : R.groups) for (int i = 0; i < g.n && row < n_override; i++) g.x[i] = x_override[row++];
+    for (GroupLCP& g : R.groups) {
+      const int base = row;
+      for (int i = 0; i < g.n && row < n_override; i++, row++) {
+        g.x[i] = x_override[row];
+        if (mapping_override) g.mapping[i] = mapping_override[row] >= 0 ? mapping_override[row] - base : mapping_override[row];  // world rows -> group rows
+      }
+    }
   }
   Jacobians J;
   ContactGradInfo gi;

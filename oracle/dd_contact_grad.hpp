@@ -276,6 +276,11 @@ inline Mat codSolveMat(const Mat& Q, const Mat& B) {
   return X;
 }
 
+// Conditioning probe: relative noise (a few ulps) applied to Q = A_c^T M^-1 A before it is decomposed. Where the numerical
+// rank of Q sits on the edge of the decomposition's threshold, the reference's pseudo-inverse formulas amplify rounding
+// differences by ||Q^+||^2; the tests measure that amplification with this knob and widen their tolerance by it.
+inline double& qNoise() { static double v = 0.0; return v; }
+
 struct ContactGradInfo {  // what the test compares / reports
   int numClamping = 0, numUpperBound = 0;
   bool pseudoInverseBranch = false;
@@ -342,7 +347,9 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
   }
   const Mat A = nu ? add(Ac, mm(Aub, E)) : Ac;
   const Mat AcT = tr(Ac);
-  const Mat Q = mm(AcT, mm(Minv, A));
+  Mat Qm = mm(AcT, mm(Minv, A));
+  if (qNoise() != 0.0) { unsigned st = 12345u; for (double& x : Qm.a) { st = st * 1664525u + 1013904223u; x *= 1.0 + qNoise() * ((st >> 8) / 16777216.0 - 0.5); } }
+  const Mat Q = Qm;
   const Mat I_n = eye(n), I_c = eye(nc);
   // finite-difference helpers (the reference's recipes)
   std::vector<double> tw(n), vp(n), vm(n);

@@ -140,12 +140,14 @@ class OracleWorld:
                 "hi": hi[:k], "findex": fi[:k], "x": x[:k], "n_groups": int(counts[2]), "tier_mask": int(counts[3]),
                 "lcp_cache": cache[:ncache.value].copy(), "active_set": mapping[:k].copy()}
 
-    def contact_jacobians(self, q, qd, tau, lcp_cache=None, mode="reference", eps=1e-6, x_override=None):
+    def contact_jacobians(self, q, qd, tau, lcp_cache=None, mode="reference", eps=1e-6, x_override=None, mapping_override=None, q_noise=0.0):
         """forwardPass with contacts for ONE world + the BackpropSnapshot Jacobians through the contact solution.
         mode 'reference': the reference's recipe; 'frozen_fd': central differences of the frozen-active-set velocity map
         (collision detector re-run at every perturbed state). Matrices are returned [row][col]. x_override: evaluate the
         Jacobians at these LCP multipliers (all rows, group order) instead of the oracle's own solution — the multipliers of a
-        rank-deficient group are fixed only up to the null space of A."""
+        rank-deficient group are fixed only up to the null space of A. mapping_override: the ConstraintMapping per row that goes
+        with those multipliers (world row numbering). q_noise: relative noise applied to Q before its decomposition, to
+        measure how strongly the pseudo-inverse formulas amplify rounding in this world."""
         mask = lib().ddo_load_ref_libs(REF_SO.encode(), BOXBOX_SO.encode())
         if mask != 3:
             raise RuntimeError("oracle/_ref libraries missing (mask %d)" % mask)
@@ -160,7 +162,9 @@ class OracleWorld:
         fc_ls = C.c_double(0.0)
         lib().ddo_contact_jacobians(self.h, 0 if mode == "reference" else 1, C.c_double(eps), _ptr(q), _ptr(qd), _ptr(tau), _ptr(cache), nc,
                                     *[_ptr(o) for o in out], info.ctypes.data_as(C.POINTER(C.c_int)), _ptr(qn), _ptr(qdn), _ptr(xo),
-                                    0 if xo is None else len(xo), C.byref(fc_ls))
+                                    0 if xo is None else len(xo), C.byref(fc_ls),
+                                    None if mapping_override is None else np.ascontiguousarray(mapping_override, dtype=np.int32).ctypes.data_as(C.POINTER(C.c_int)),
+                                    C.c_double(q_noise))
         names = ("posPos", "posVel", "velPos", "velVel", "forceVel")
         r = {k: np.ascontiguousarray(o.T) for k, o in zip(names, out)}
         r.update(num_clamping=int(info[0]), num_upper_bound=int(info[1]), pseudo_inverse=bool(info[2]), structure_kept=bool(info[3]),

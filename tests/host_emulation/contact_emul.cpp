@@ -109,3 +109,15 @@ extern "C" int emul_mass_bilinear_grad(const ddb_topology* topo, const ddb_param
                                         [&](int body, const double* dq6, const double*) { for (int k = 0; k < 6; k++) dq_out[c_topo.b[body].dof + k] = dq6[k]; });
   return 0;
 }
+
+// P rhs / P^T rhs with P = Q^+ from one complete orthogonal decomposition (codFactorDev / codApplyDev); returns the rank
+extern "C" int emul_cod_apply(int n, const double* Q, const double* rhs, int transposed, double* out) {
+  std::vector<double> ld(lcpScratchDoubles(n) * 32, 0.0);
+  std::vector<int> li(lcpScratchInts(n) * 32, 0);
+  LcpView v;
+  v.init(ld.data() + 5, li.data() + 5, n, n);
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) v.db[(size_t)(v.oL + i * n + j) * 32] = Q[i * n + j];
+  const int rank = codFactorDev(v, n);
+  codApplyDev(v, n, rank, transposed != 0, [&](int i) { return rhs[i]; }, [&](int i, double x) { out[i] = x; });
+  return rank;
+}

@@ -74,23 +74,38 @@ def emul_backward():
     return run
 
 
+def vjp_check(o, q, qd, tau, x, mapping, gqn, gqdn, gq, gqd, gtau, tag):
+    """Compare one world's backward with the oracle's Jacobians applied to the same loss gradients at 1e-8, widened by the
+    measured amplification of a few-ulp perturbation of Q where the numerical rank of Q sits on the edge of the
+    decomposition's threshold (there the reference's pseudo-inverse formulas are themselves only that well determined)."""
+    J = o.contact_jacobians(q, qd, tau, mode="reference", x_override=x, mapping_override=mapping)
+    Jn = o.contact_jacobians(q, qd, tau, mode="reference", x_override=x, mapping_override=mapping, q_noise=4e-16)
+    for name, got, f in (("dL/dq", gq, lambda K: K["posPos"].T @ gqn + K["posVel"].T @ gqdn),
+                         ("dL/dqd", gqd, lambda K: K["velPos"].T @ gqn + K["velVel"].T @ gqdn),
+                         ("dL/dtau", gtau, lambda K: K["forceVel"].T @ gqdn)):
+        ref, refn = f(J), f(Jn)
+        tol = 1e-8 + 20.0 * rel(refn, ref)
+        assert tol < 1e-2, (tag, name, "the oracle itself is not determined here", tol)
+        assert rel(got, ref) < tol, (tag, name, rel(got, ref), tol)
+    return J
+
+
 @pytest.mark.parametrize("scene", sorted(SCENES))
 def test_device_contact_backward_matches_oracle(emul_backward, scene):
     make, states = SCENES[scene]
     desc = make()
     o = OracleWorld(desc)
     n = o.n
-    q, qd, tau = states(4 if scene == "box_stack" else 12, 3)
+    q, qd, tau = states(8 if scene == "box_stack" else 12, 21)
     rng = np.random.default_rng(5)
     seen = 0
-    for w in range(len(q)):
+    # box_stack (n = 30, up to 66 classified rows) is slow on the CPU: one well-conditioned world and world 7, whose Q has
+    # its numerical rank on the edge of the decomposition's threshold (friction dropped, f_c != Q^+ b)
+    for w in ((0, 7) if scene == "box_stack" else range(len(q))):
         gqn, gqdn = rng.normal(size=n), rng.normal(size=n)
         (qn, qdn, gq, gqd, gtau), status, x = emul_backward(desc, q[w], qd[w], tau[w], gqn, gqdn)
-        J = o.contact_jacobians(q[w], qd[w], tau[w], mode="reference", x_override=x)
+        J = vjp_check(o, q[w], qd[w], tau[w], x, None, gqn, gqdn, gq, gqd, gtau, (scene, w))
         seen |= status
         assert (status & 1) == (J["num_clamping"] > 0)
         assert np.allclose(qdn, J["qd_next"], rtol=1e-6, atol=1e-6)
-        assert rel(gq, J["posPos"].T @ gqn + J["posVel"].T @ gqdn) < 1e-8, (scene, w)
-        assert rel(gqd, J["velPos"].T @ gqn + J["velVel"].T @ gqdn) < 1e-8, (scene, w)
-        assert rel(gtau, J["forceVel"].T @ gqdn) < 1e-8, (scene, w)
     assert seen & 1  # some world had clamping contacts
