@@ -41,8 +41,8 @@ struct ContactLayout {
   __host__ __device__ size_t oNB() const { return oNA() + (size_t)cmax * 18; }
   __host__ __device__ size_t oMassed() const { return oNB() + (size_t)cmax * 18; }    // [kmax][nd]
   __host__ __device__ size_t oA() const { return oMassed() + (size_t)kmax * nd; }     // [kmax][kmax] (per group, n x n packed)
-  __host__ __device__ size_t oB() const { return oA() + (size_t)kmax * kmax; }        // b lo hi x0 x xall xs xnew colnorm: 9 x [kmax]
-  __host__ __device__ size_t oW() const { return oB() + (size_t)9 * kmax; }           // [nb][12] world transforms
+  __host__ __device__ size_t oB() const { return oA() + (size_t)kmax * kmax; }        // b lo hi x0 x xall xs xnew colnorm mx: 10 x [kmax]
+  __host__ __device__ size_t oW() const { return oB() + (size_t)10 * kmax; }           // [nb][12] world transforms
   __host__ __device__ size_t oV() const { return oW() + (size_t)nb * 12; }            // [nb][6] body velocities (pre-constraint)
   __host__ __device__ size_t oImp() const { return oV() + (size_t)nb * 6; }           // [nb][6] constraint impulses
   __host__ __device__ size_t oBias() const { return oImp() + (size_t)nb * 6; }        // [nb][6]
@@ -71,6 +71,7 @@ struct ContactWork {
   DDB_LCP_DI double* xs() const { return d + L.oB() + 6 * (size_t)L.kmax; }
   DDB_LCP_DI double* xnew() const { return d + L.oB() + 7 * (size_t)L.kmax; }
   DDB_LCP_DI double* colnorm() const { return d + L.oB() + 8 * (size_t)L.kmax; }
+  DDB_LCP_DI double* mx() const { return d + L.oB() + 9 * (size_t)L.kmax; }  // the solver's cached solution while the groups are solved
   DDB_LCP_DI double* W(int body) const { return d + L.oW() + (size_t)body * 12; }
   DDB_LCP_DI double* V(int body) const { return d + L.oV() + (size_t)body * 6; }
   DDB_LCP_DI double* imp(int body) const { return d + L.oImp() + (size_t)body * 6; }
@@ -204,16 +205,28 @@ DDB_LCP_DI void tangentBasis(const double* n, double* t1, double* t2) {
 
 struct ContactStepOut {
   int n_contacts, n_rows, n_groups, tier_mask;
+  int pending;  // a PGS solve was handed to the warp-cooperative solver: nothing was committed, the stage is run again
+};
+
+// Deferred PGS: the projected Gauss-Seidel solves of the fallback chain run in their own kernel, one warp per world with
+// the matrix in shared memory (k_pgs_warp in lcp_api.cu). The stage is deterministic, so it is simply run again with the
+// answers of the solves it has already asked for: request k of a world is answered from ansX[k] / ansOk[k] when
+// k < answered, otherwise the reduced problem is left in the world's LCP view and the stage returns `pending`.
+struct PgsDefer {
+  int answered, seen, kmax, pendingN;
+  int cap;             // answer slots per world; further solves of the same step run inline
+  const double* ansX;  // [requests][kmax]
+  const int* ansOk;    // [requests]
 };
 
 // The whole contact stage for one world. qd_pre: velocities after the unconstrained update (in/out: becomes qd').
 // lcp_cache/n_cache: the solver's cached solution mX (in/out). lv: this world's LCP scratch view storage.
 DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, double* lcpD, int* lcpI, const double* qd_pre_in, double* qd_out,
                                        int layout, int N, int w, double* lcp_cache, int* n_cache, const PgsOptions& pgs,
-                                       double* keepD = nullptr, int* keepI = nullptr) {
+                                       double* keepD = nullptr, int* keepI = nullptr, PgsDefer* defer = nullptr) {
   const int nb = c_topo.nb, nd = c_topo.nd;
   const ContactTopo& ct = c_ctopo;
-  ContactStepOut out = {0, 0, 0, 0};
+  ContactStepOut out = {0, 0, 0, 0, 0};
   // ---- world transforms and body velocities under the unconstrained velocity update ----
   for (int i = 0; i < nb; i++) {
     const DevBody& b = c_topo.b[i];
@@ -339,6 +352,20 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   for (int i = 0; i < nb; i++) for (int k = 0; k < 6; k++) cw.imp(i)[k] = 0.0;
   int groupBase[DDB_MAX_BODIES];
   int mxSize = *n_cache;  // the solver's mX persists across groups and steps while its size is unchanged
+  double* mx = cw.mx();   // committed to lcp_cache only when the whole stage has run
+  for (int k = 0; k < mxSize && k < ct.kmax; k++) mx[k] = lcp_cache[k];
+  // returns the solver's bool, or -1 when the solve was deferred to the warp-cooperative kernel
+  auto runPgs = [&](const LcpView& vv) -> int {
+    if (!defer) return pgsSolve(vv, pgs) ? 1 : 0;
+    const int k = defer->seen++;
+    if (k >= defer->cap) return pgsSolve(vv, pgs) ? 1 : 0;
+    if (k < defer->answered) {
+      for (int i = 0; i < vv.n; i++) vv.x(i) = defer->ansX[(size_t)k * defer->kmax + i];
+      return defer->ansOk[k];
+    }
+    defer->pendingN = vv.n;
+    return -1;
+  };
   int rowsTotal = 0;
   double* A = cw.A();
   for (int g = 0; g < ng; g++) {
@@ -404,7 +431,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     // ---- squared column norms of A (aColNormGradientBackup) ----
     for (int j = 0; j < n; j++) { double sacc = 0.0; for (int r = 0; r < n; r++) sacc += A[(size_t)r * n + j] * A[(size_t)r * n + j]; cw.colnorm()[j] = sacc; }
     // ---- the solver's cached solution ----
-    if (mxSize == n) { for (int k = 0; k < n; k++) x0[k] = lcp_cache[k]; }
+    if (mxSize == n) { for (int k = 0; k < n; k++) x0[k] = mx[k]; }
     else { for (int k = 0; k < n; k++) x0[k] = 0.0; }
     for (int k = 0; k < n; k++) x[k] = x0[k];
     // ---- LCPUtils::reduce: merge duplicate columns (index map + column scale instead of explicit matrices) ----
@@ -592,14 +619,16 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       if (!success) {
         tier = 2;
         buildReduced(false);
-        success = pgsSolve(v, pgs);
+        const int pr = runPgs(v);
+        if (pr < 0) { out.pending = 1; return out; }
+        success = pr != 0;
         if (success) { mapOut(); if (!isValid()) success = false; }
       }
       if (!success) {
         tier = 3;
         ignoreFrictionFinal = true;
         buildReduced(true);
-        pgsSolve(v, pgs);
+        if (runPgs(v) < 0) { out.pending = 1; return out; }
         mapOut();
       }
       if (hasNaN()) { for (int k = 0; k < n; k++) x[k] = 0.0; }
@@ -615,7 +644,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     out.tier_mask |= 1 << tier;
     // the solution becomes the solver's mX
     mxSize = n;
-    for (int k = 0; k < n; k++) lcp_cache[k] = x[k];
+    for (int k = 0; k < n; k++) mx[k] = x[k];
     // remember the multipliers of this group's rows for the final impulse accumulation
     groupBase[g] = rowsTotal;
     for (int k = 0; k < n; k++) cw.xall()[rowsTotal + k] = x[k];
@@ -624,6 +653,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   out.n_rows = rowsTotal;
   if (rowsTotal < 0) out.tier_mask |= 1 << 8;
   *n_cache = mxSize;
+  for (int k = 0; k < mxSize && k < ct.kmax; k++) lcp_cache[k] = mx[k];
   if (keepD) {
     const ContactSnapLayout KL{nd, ct.cmax, ct.kmax};
     const int rows = rowsTotal < 0 ? 0 : rowsTotal;

@@ -15,7 +15,9 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* work
 // counts_out [N][4] = n_contacts, n_rows, n_groups, tier mask
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd_inout, double* lcp_cache,
                           int* n_cache, int* counts_out, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i,
-                          double* keep_d, int* keep_i);
+                          double* keep_d, int* keep_i, int* pgs_ctrl, double* pgs_ans_x, int* pgs_ans_ok, int* launches);
+// control words and answer buffers of the deferred PGS solves (ints, doubles, ints for N worlds)
+void contactPgsSizes(int N, int kmax, size_t* ctrl_ints, size_t* ans_doubles, size_t* ans_ints);
 // per-slot storage of what the backward pass needs of the contact stage (doubles / ints for N worlds)
 void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* keep_doubles, size_t* keep_ints);
 // BackpropSnapshot::backprop through the contact solution retained in (snap, keep_d, keep_i); lim6 = 6 x [nd] limits or NULL

@@ -103,6 +103,8 @@ struct ddb_handle {
   std::vector<int*> keepI;
   double* jacTmp = nullptr;    // 5 x [N][n] staging of ddb_jacobians with contacts
   int* bwdStatus = nullptr;
+  int *pgsCtrl = nullptr, *pgsOk = nullptr;  // deferred PGS solves (contact_api.h)
+  double* pgsX = nullptr;
   // host-buffer path
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
@@ -272,6 +274,13 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
     DDB_CUDA(h, cudaMemset(h->cwork_d, 0, wd * sizeof(double)));
     DDB_CUDA(h, cudaMemset(h->cwork_i, 0, wi * sizeof(int)));
     DDB_CUDA(h, cudaMalloc(&h->bwdStatus, (size_t)h->N * sizeof(int)));
+    {
+      size_t ci, ad, ai;
+      contactPgsSizes(h->N, h->kmax, &ci, &ad, &ai);
+      DDB_CUDA(h, cudaMalloc(&h->pgsCtrl, ci * sizeof(int)));
+      DDB_CUDA(h, cudaMalloc(&h->pgsX, ad * sizeof(double)));
+      DDB_CUDA(h, cudaMalloc(&h->pgsOk, ai * sizeof(int)));
+    }
     for (int i = 0; i < slots; i++) { int rk = allocKeep(h, i); if (rk) return rk; }
   }
   return DDB_OK;
@@ -289,7 +298,7 @@ int ddb_destroy(ddb_handle* h) {
   if (h->lim_dev) cudaFree(h->lim_dev);
   if (h->stage) cudaFree(h->stage);
   for (void* p : {(void*)h->cwork_d, (void*)h->cwork_i, (void*)h->clcp_d, (void*)h->clcp_i, (void*)h->lcp_cache, (void*)h->n_cache, (void*)h->ccounts,
-                  (void*)h->jacTmp, (void*)h->bwdStatus})
+                  (void*)h->jacTmp, (void*)h->bwdStatus, (void*)h->pgsCtrl, (void*)h->pgsX, (void*)h->pgsOk})
     if (p) cudaFree(p);
   for (double* p : h->keepD) if (p) cudaFree(p);
   for (int* p : h->keepI) if (p) cudaFree(p);
@@ -338,9 +347,11 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
     // collision, contact rows, LCP assembly and solve, impulses: qdn holds the unconstrained update on entry
     double* cache = lcp_cache_inout ? lcp_cache_inout : h->lcp_cache;
     int* ncache = n_rows_inout ? n_rows_inout : h->n_cache;
+    int nl = 0;
     DDB_CUDA(h, contactLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], qdn, cache, ncache, h->ccounts,
-                              active_set_out, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i, h->keepD[h->cur], h->keepI[h->cur]));
-    h->launches++;
+                              active_set_out, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i, h->keepD[h->cur], h->keepI[h->cur], h->pgsCtrl, h->pgsX,
+                              h->pgsOk, &nl));
+    h->launches += nl;
     if (status_out)
       DDB_CUDA(h, cudaMemcpy2DAsync(status_out, sizeof(int), h->ccounts + 3, 4 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToDevice, s));
   }

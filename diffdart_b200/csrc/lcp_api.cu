@@ -69,14 +69,147 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PgsBoxedLcpSolver::solve (PgsBoxedLcpSolver.cpp:79-262), one warp per world, the matrix in shared memory.
+// Gauss-Seidel is sequential in the rows, so the warp works on blocks of 32 consecutive rows with lane r owning row r:
+//   phase 1 (parallel)    acc_r = b_r - sum_{j before the block} A_rj x_j(new) - sum_{j > r} A_rj x_j(old)
+//   phase 2 (32 steps)    lane j clamps acc_j into x_j and broadcasts it (one shuffle); lanes r > j subtract A_rj x_j
+// The sweep order, the projections (friction bounds from the live normal impulse) and the stopping rules are the
+// reference's; the summation order inside a row is not (the reference accumulates left to right), so the result agrees
+// with a scalar run to rounding, not bit for bit. Rows whose diagonal is below epsilonForDivision are left at 0.
+// Shared-memory rows are padded to an odd stride: the 32 lanes read 32 different rows without bank conflicts.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kPgsRequests = 4;  // PGS solves a world can hand over per step (2 tiers x 2 constrained groups); more run inline
+
+template <int CAP>
+__global__ void __launch_bounds__(32)
+k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
+           double* __restrict__ ans_x, int* __restrict__ ans_ok, PgsOptions opt) {
+  const int w = blockIdx.x, lane = threadIdx.x;
+  const int n = ctrl[4 * w + 2];
+  if (ctrl[4 * w] || n <= nLow || n > CAP) return;
+  constexpr int LD = CAP + 1;
+  extern __shared__ double sm[];
+  double* As = sm;                 // [CAP][LD]
+  double* bs = As + CAP * LD;      // [CAP]
+  double* los = bs + CAP;
+  double* his = los + CAP;
+  double* xs = his + CAP;
+  int* fis = reinterpret_cast<int*>(xs + CAP);
+  int* act = fis + CAP;
+  LcpView v;
+  const size_t warp = w >> 5, wl = w & 31;
+  v.init(lcp_d + warp * lcpScratchDoubles(kmax) * 32 + wl, lcp_i + warp * lcpScratchInts(kmax) * 32 + wl, n, kmax);
+  for (int r = 0; r < n; r++)
+    for (int j = lane; j < n; j += 32) As[r * LD + j] = v.Araw(r, j);
+  for (int i = lane; i < n; i += 32) { bs[i] = v.b(i); los[i] = v.lo(i); his[i] = v.hi(i); xs[i] = v.x(i); fis[i] = v.findex(i); }
+  __syncwarp();
+  const int nblk = (n + 31) >> 5;
+  bool converged = false;
+  // sweep 0 works on the raw matrix (divides by the diagonal, absolute stopping rule); later sweeps on the normalised rows
+  for (int iter = 0; iter < opt.maxIteration; iter++) {
+    bool mine = true;  // possibleToTerminate restricted to this lane's rows
+    for (int blk = 0; blk < nblk; blk++) {
+      const int blk0 = blk << 5, r = blk0 + lane;
+      const bool valid = r < n;
+      const double* Ar = As + (valid ? r : 0) * LD;
+      bool active = false;
+      double diag = 1.0, old_x = 0.0, hi_r = 0.0, lo_r = 0.0, xf = 0.0;
+      int fi = -1;
+      if (valid) {
+        old_x = xs[r]; hi_r = his[r]; lo_r = los[r]; fi = fis[r];
+        if (iter == 0) { diag = Ar[r]; active = !(diag < opt.epsilonForDivision); act[r] = active ? 1 : 0; }
+        else active = act[r] != 0;
+        if (fi >= 0 && fi < blk0) xf = xs[fi];  // a normal row of an earlier block: already final in this sweep
+      }
+      // phase 1
+      double a0 = valid ? bs[r] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      int j = 0;
+      for (; j + 3 < blk0; j += 4) {
+        a0 -= Ar[j] * xs[j]; a1 -= Ar[j + 1] * xs[j + 1]; a2 -= Ar[j + 2] * xs[j + 2]; a3 -= Ar[j + 3] * xs[j + 3];
+      }
+      for (; j < blk0; j++) a0 -= Ar[j] * xs[j];
+      const int blkEnd = min(blk0 + 32, n);
+      for (j = blk0; j < blkEnd; j++) if (j > r) a1 -= Ar[j] * xs[j];
+      for (j = blkEnd; j + 3 < n; j += 4) {
+        a0 -= Ar[j] * xs[j]; a1 -= Ar[j + 1] * xs[j + 1]; a2 -= Ar[j + 2] * xs[j + 2]; a3 -= Ar[j + 3] * xs[j + 3];
+      }
+      for (; j < n; j++) a0 -= Ar[j] * xs[j];
+      double acc = (a0 + a1) + (a2 + a3);
+      // phase 2
+      double x_new = old_x;
+      if (valid && iter == 0 && !active) x_new = 0.0;
+      for (int jj = 0; jj < blkEnd - blk0; jj++) {
+        if (lane == jj && active) {
+          double nx = iter == 0 ? acc / diag : acc;
+          if (fi >= 0) { const double h = hi_r * xf; nx = nx > h ? h : (nx < -h ? -h : nx); }
+          else nx = nx > hi_r ? hi_r : (nx < lo_r ? lo_r : nx);
+          x_new = nx;
+        }
+        const double xj = __shfl_sync(0xffffffffu, x_new, jj);
+        if (lane > jj && valid) acc -= Ar[blk0 + jj] * xj;
+        if (fi == blk0 + jj) xf = xj;
+      }
+      if (valid) {
+        xs[r] = x_new;
+        if (active) {
+          if (iter == 0) { if (fabs(x_new - old_x) > opt.deltaXThreshold) mine = false; }
+          else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs((x_new - old_x) / x_new) > opt.relativeDeltaXTolerance) mine = false; }
+        }
+      }
+      __syncwarp();
+    }
+    converged = __all_sync(0xffffffffu, mine);
+    if (converged) break;
+    if (iter == 0) {
+      // row normalisation (PgsBoxedLcpSolver.cpp:171-178)
+      for (int r = lane; r < n; r += 32) {
+        if (!act[r]) continue;
+        const double dummy = 1.0 / As[r * LD + r];
+        bs[r] *= dummy;
+        for (int j = 0; j < n; j++) As[r * LD + j] *= dummy;
+      }
+      __syncwarp();
+    }
+  }
+  const int slot = ctrl[4 * w + 1];
+  double* ax = ans_x + ((size_t)w * kPgsRequests + slot) * kmax;
+  for (int i = lane; i < n; i += 32) ax[i] = xs[i];
+  if (lane == 0) {
+    ans_ok[(size_t)w * kPgsRequests + slot] = converged ? 1 : 0;
+    ctrl[4 * w + 1] = slot + 1;
+    ctrl[4 * w + 2] = 0;
+  }
+}
+
+// problems too large for shared memory: the scalar solver, one world per thread
+__global__ void __launch_bounds__(64)
+k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i, double* __restrict__ ans_x,
+             int* __restrict__ ans_ok, PgsOptions opt) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= N) return;
+  const int n = ctrl[4 * w + 2];
+  if (ctrl[4 * w] || n <= nLow) return;
+  LcpView v;
+  const size_t warp = w >> 5, wl = w & 31;
+  v.init(lcp_d + warp * lcpScratchDoubles(kmax) * 32 + wl, lcp_i + warp * lcpScratchInts(kmax) * 32 + wl, n, kmax);
+  const bool ok = pgsSolve(v, opt);
+  const int slot = ctrl[4 * w + 1];
+  for (int i = 0; i < n; i++) ans_x[((size_t)w * kPgsRequests + slot) * kmax + i] = v.x(i);
+  ans_ok[(size_t)w * kPgsRequests + slot] = ok ? 1 : 0;
+  ctrl[4 * w + 1] = slot + 1;
+  ctrl[4 * w + 2] = 0;
+}
+
 // the contact stage of World::step, one world per thread
 __global__ void __launch_bounds__(64)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
           int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
-          int* __restrict__ keep_i) {
+          int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
+  if (ctrl && ctrl[4 * w]) return;  // this world's stage has been committed by an earlier pass
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L};
   const ContactSnapLayout KL{L.nd, L.cmax, L.kmax};
@@ -84,8 +217,12 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
   double* ld = lcp_d + warp * lcpScratchDoubles(L.kmax) * 32 + lane;
   int* li = lcp_i + warp * lcpScratchInts(L.kmax) * 32 + lane;
   int nc = n_cache[w];
+  PgsDefer df{ctrl ? ctrl[4 * w + 1] : 0, 0, L.kmax, 0, kPgsRequests, ans_x + (size_t)w * kPgsRequests * L.kmax, ans_ok + (size_t)w * kPgsRequests};
   ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs,
-                                  keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr);
+                                  keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr,
+                                  ctrl ? &df : nullptr);
+  if (o.pending) { ctrl[4 * w + 2] = df.pendingN; return; }  // the reduced problem waits in this world's LCP view
+  if (ctrl) { ctrl[4 * w] = 1; ctrl[4 * w + 2] = 0; }
   n_cache[w] = nc;
   counts[4 * w] = o.n_contacts; counts[4 * w + 1] = o.n_rows; counts[4 * w + 2] = o.n_groups; counts[4 * w + 3] = o.tier_mask;
   if (active_out) {
@@ -155,14 +292,48 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, 
   *ld = warps * lcpScratchDoubles(kmax) * 32;
   *li = warps * lcpScratchInts(kmax) * 32;
 }
+template <int CAP>
+static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
+                                 const PgsOptions& pgs) {
+  const size_t bytes = (size_t)(CAP * (CAP + 1) + 4 * CAP) * sizeof(double) + 2 * CAP * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(k_pgs_warp<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  k_pgs_warp<CAP><<<N, 32, bytes, s>>>(N, kmax, nLow, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+  return cudaGetLastError();
+}
+void contactPgsSizes(int N, int kmax, size_t* ctrl_ints, size_t* ans_doubles, size_t* ans_ints) {
+  *ctrl_ints = (size_t)N * 4;
+  *ans_doubles = (size_t)N * kPgsRequests * kmax;
+  *ans_ints = (size_t)N * kPgsRequests;
+}
 cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, double* qd, double* lcp_cache,
                           int* n_cache, int* counts, int* active_out, double* work_d, int* work_i, double* lcp_d, int* lcp_i, double* keep_d,
-                          int* keep_i) {
+                          int* keep_i, int* ctrl, double* ans_x, int* ans_ok, int* launches) {
   ContactLayout L{nb, nd, cmax, kmax};
   PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
-  k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
-                                         keep_d, keep_i);
-  return cudaGetLastError();
+  cudaError_t e = cudaMemsetAsync(ctrl, 0, (size_t)N * 4 * sizeof(int), s);
+  if (e != cudaSuccess) return e;
+  // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
+  for (int pass = 0; pass <= kPgsRequests; pass++) {
+    k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+                                           keep_d, keep_i, ctrl, ans_x, ans_ok);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) (*launches)++;
+    if (pass == kPgsRequests) break;
+    if ((e = launchPgsWarp<64>(s, N, kmax, 0, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
+    if (kmax > 64 && (e = launchPgsWarp<92>(s, N, kmax, 64, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
+    if (kmax > 92 && (e = launchPgsWarp<160>(s, N, kmax, 92, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
+    if (kmax > 160) {
+      k_pgs_thread<<<(N + 63) / 64, 64, 0, s>>>(N, kmax, 160, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 92) + (kmax > 160);
+  }
+  return cudaSuccess;
 }
 void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* kd, size_t* ki) {
   ContactSnapLayout KL{nd, cmax, kmax};
