@@ -50,7 +50,8 @@ struct ContactLayout {
   __host__ __device__ size_t oU() const { return oDelV() + (size_t)nb * 6; }          // [nb] + dqd [nd]
   __host__ __device__ size_t doubles() const { return oU() + (size_t)nb + nd; }
   // ints: bodyA bodyB dim type group [cmax each], findex keep mapTo [kmax each], misc
-  __host__ __device__ size_t ints() const { return (size_t)5 * cmax + (size_t)7 * kmax + 8; }
+  __host__ __device__ size_t oSaved() const { return (size_t)5 * cmax + (size_t)7 * kmax + 8; }  // loop state kept across a deferred PGS solve
+  __host__ __device__ size_t ints() const { return oSaved() + 8 + DDB_MAX_BODIES; }
 };
 
 struct ContactWork {
@@ -90,6 +91,7 @@ struct ContactWork {
   DDB_LCP_DI int* clampIdx() const { return i + 5 * L.cmax + 4 * L.kmax; }
   DDB_LCP_DI int* ubIdx() const { return i + 5 * L.cmax + 5 * L.kmax; }
   DDB_LCP_DI int* activeAll() const { return i + 5 * L.cmax + 6 * L.kmax; }  // active set of every row of the world
+  DDB_LCP_DI int* saved() const { return i + L.oSaved(); }
 };
 
 // What the backward pass needs of one step's contact stage, kept per snapshot slot (world-major):
@@ -212,9 +214,12 @@ struct ContactStepOut {
 // the matrix in shared memory (k_pgs_warp in lcp_api.cu). The stage is deterministic, so it is simply run again with the
 // answers of the solves it has already asked for: request k of a world is answered from ansX[k] / ansOk[k] when
 // k < answered, otherwise the reduced problem is left in the world's LCP view and the stage returns `pending`.
+// Everything the stage had computed up to the request lives in the world's scratch, so the next pass does not start over:
+// it re-enters the group loop right behind the answered solve (resumeKind; loop scalars in ContactWork::saved()).
 struct PgsDefer {
   int answered, seen, kmax, pendingN;
   int cap;             // answer slots per world; further solves of the same step run inline
+  int resumeKind;      // in: 0 = run from the start, 2 / 3 = continue behind the answered PGS solve of that tier; out: tier of the solve just deferred
   const double* ansX;  // [requests][kmax]
   const int* ansOk;    // [requests]
 };
@@ -227,6 +232,12 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   const int nb = c_topo.nb, nd = c_topo.nd;
   const ContactTopo& ct = c_ctopo;
   ContactStepOut out = {0, 0, 0, 0, 0};
+  const bool resuming = defer && defer->resumeKind != 0;
+  int* sv = cw.saved();
+  int* offs = cw.i + 3 * cw.L.cmax;  // first LCP row of each constraint inside its group
+  int nc = 0, ng = 0;
+  if (resuming) { nc = sv[1]; ng = sv[2]; out.n_contacts = nc; out.n_groups = ng; }
+  else {
   // ---- world transforms and body velocities under the unconstrained velocity update ----
   for (int i = 0; i < nb; i++) {
     const DevBody& b = c_topo.b[i];
@@ -254,7 +265,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     }
   }
   // ---- collision pass ----
-  int nc = 0;
+  nc = 0;
   for (int pi = 0; pi < ct.n_pairs; pi++) {
     const int a = ct.pairA[pi], bb = ct.pairB[pi];
     const ShapeDesc& sa = ct.shape[a];
@@ -290,7 +301,6 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   }
   out.n_contacts = nc;
   // ---- constraints: contacts with a non-zero normal, depth in [0, clip], at least one reactive body ----
-  int* offs = cw.i + 3 * cw.L.cmax;  // first LCP row of each constraint inside its group
   for (int c = 0; c < nc; c++) {
     const double* o = cw.contact(c);
     const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
@@ -337,7 +347,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     if (usize[sa] < usize[sb]) { root[sa] = sb; usize[sb] += usize[sa]; }
     else { root[sb] = sa; usize[sa] += usize[sb]; }
   }
-  int ng = 0;
+  ng = 0;
   for (int c = 0; c < nc; c++) {
     cw.groupOf()[c] = -1;
     if (!cw.dim()[c]) continue;
@@ -350,10 +360,11 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   }
   out.n_groups = ng;
   for (int i = 0; i < nb; i++) for (int k = 0; k < 6; k++) cw.imp(i)[k] = 0.0;
+  }
   int groupBase[DDB_MAX_BODIES];
   int mxSize = *n_cache;  // the solver's mX persists across groups and steps while its size is unchanged
   double* mx = cw.mx();   // committed to lcp_cache only when the whole stage has run
-  for (int k = 0; k < mxSize && k < ct.kmax; k++) mx[k] = lcp_cache[k];
+  if (!resuming) for (int k = 0; k < mxSize && k < ct.kmax; k++) mx[k] = lcp_cache[k];
   // returns the solver's bool, or -1 when the solve was deferred to the warp-cooperative kernel
   auto runPgs = [&](const LcpView& vv) -> int {
     if (!defer) return pgsSolve(vv, pgs) ? 1 : 0;
@@ -368,7 +379,19 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   };
   int rowsTotal = 0;
   double* A = cw.A();
-  for (int g = 0; g < ng; g++) {
+  if (resuming) {
+    rowsTotal = sv[3]; mxSize = sv[4]; out.tier_mask = sv[5];
+    for (int i = 0; i < sv[0]; i++) groupBase[i] = sv[8 + i];
+    defer->seen = defer->answered;
+  }
+  // the loop scalars a later pass needs to continue behind a deferred solve of tier `kind` in group g
+  auto saveState = [&](int g, int kind, int nReduced) {
+    sv[0] = g; sv[1] = nc; sv[2] = ng; sv[3] = rowsTotal; sv[4] = mxSize; sv[5] = out.tier_mask; sv[6] = nReduced;
+    for (int i = 0; i < g; i++) sv[8 + i] = groupBase[i];
+    defer->resumeKind = kind;
+  };
+  for (int g = resuming ? sv[0] : 0; g < ng; g++) {
+    const bool resumeHere = resuming && g == sv[0];
     // rows of this group
     int n = 0;
     for (int c = 0; c < nc; c++) if (cw.groupOf()[c] == g) { offs[c] = n; n += cw.dim()[c]; }
@@ -379,6 +402,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     }
     double* b = cw.b(); double* lo = cw.lo(); double* hi = cw.hi(); double* x0 = cw.x0(); double* x = cw.x();
     int* findex = cw.findex();
+    if (!resumeHere) {
     // ---- assembly by impulse tests ----
     for (int c = 0; c < nc; c++) {
       if (cw.groupOf()[c] != g) continue;
@@ -434,6 +458,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     if (mxSize == n) { for (int k = 0; k < n; k++) x0[k] = mx[k]; }
     else { for (int k = 0; k < n; k++) x0[k] = 0.0; }
     for (int k = 0; k < n; k++) x[k] = x0[k];
+    }
     // ---- LCPUtils::reduce: merge duplicate columns (index map + column scale instead of explicit matrices) ----
     int* keep = cw.keep();
     int* mapTo = cw.mapTo();
@@ -584,7 +609,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       return true;
     };
     const bool gradients = ct.gradients != 0;
-    if (gradients && mxSize != n) {
+    if (!resumeHere && gradients && mxSize != n) {
       // LCPUtils::guessSolution: least squares on {normal rows with b > 0} + {all friction rows}
       int ncl = 0;
       for (int i = 0; i < n; i++) { if (findex[i] == -1) { if (b[i] > 0) keep[ncl++] = i; } else keep[ncl++] = i; }
@@ -603,32 +628,47 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     bool success = false;
     int tier = 1;
     bool ignoreFrictionFinal = false;
-    if (gradients) {
+    const int stage = resumeHere ? defer->resumeKind : 0;  // 2 / 3: continue behind the answered PGS solve of that tier
+    // the answer of the solve this pass was waiting for, put where mapOut() expects it
+    auto loadAnswer = [&]() -> int {
+      const int k = defer->answered - 1;
+      v.init(lcpD, lcpI, sv[6], ct.kmax);
+      for (int i = 0; i < v.n; i++) v.x(i) = defer->ansX[(size_t)k * defer->kmax + i];
+      return defer->ansOk[k];
+    };
+    if (stage == 0 && gradients) {
       success = constructAndStandardize(x, false);
       if (success) tier = 0;
       else for (int k = 0; k < n; k++) x[k] = x0[k];
     }
     if (!success) {
-      tier = 1;
-      {
+      if (stage == 0) {
+        tier = 1;
         buildReduced(false);
         success = dantzigSolve(v, 0, true);
         if (success) { mapOut(); if (!isValid()) success = false; }
+        if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
       }
-      if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
-      if (!success) {
+      if (stage == 2 || (stage == 0 && !success)) {
         tier = 2;
-        buildReduced(false);
-        const int pr = runPgs(v);
-        if (pr < 0) { out.pending = 1; return out; }
+        int pr;
+        if (stage == 2) pr = loadAnswer();
+        else {
+          buildReduced(false);
+          pr = runPgs(v);
+          if (pr < 0) { saveState(g, 2, v.n); out.pending = 1; return out; }
+        }
         success = pr != 0;
         if (success) { mapOut(); if (!isValid()) success = false; }
       }
-      if (!success) {
+      if (stage == 3 || !success) {
         tier = 3;
         ignoreFrictionFinal = true;
-        buildReduced(true);
-        if (runPgs(v) < 0) { out.pending = 1; return out; }
+        if (stage == 3) loadAnswer();
+        else {
+          buildReduced(true);
+          if (runPgs(v) < 0) { saveState(g, 3, v.n); out.pending = 1; return out; }
+        }
         mapOut();
       }
       if (hasNaN()) { for (int k = 0; k < n; k++) x[k] = 0.0; }

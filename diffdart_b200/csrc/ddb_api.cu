@@ -395,6 +395,15 @@ int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double
   return DDB_OK;
 }
 
+// Statistics of the last ddb_forward: Gauss-Seidel sweeps spent per world by the warp-cooperative PGS solver (host array [N]).
+int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out) {
+  if (!h || !h->hasContacts || !sweeps_out) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  DDB_CUDA(h, cudaDeviceSynchronize());
+  DDB_CUDA(h, cudaMemcpy2D(sweeps_out, sizeof(int), h->pgsCtrl + 3, 8 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToHost));
+  return DDB_OK;
+}
+
 int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau) {
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");

@@ -81,13 +81,32 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kPgsRequests = 4;  // PGS solves a world can hand over per step (2 tiers x 2 constrained groups); more run inline
 
+// The 32 sequential steps of one row block (phase 2 of k_pgs_warp). Per step the critical path is one shuffle, one DFMA
+// and the two min/max of the projection; the matrix element of the next step is fetched ahead of the shuffle.
+template <bool FIRST>
+__device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ ArBlk, int cnt, int lane, bool active, int fiLocal, double hi_r,
+                                              double diag, double& acc, double& hi_e, double& lo_e, double& x_new) {
+  double a_next = ArBlk[0];
+#pragma unroll 8
+  for (int jj = 0; jj < cnt; jj++) {
+    const double a = a_next;
+    a_next = ArBlk[jj + 1 < cnt ? jj + 1 : jj];
+    double nx = FIRST ? acc / diag : acc;
+    nx = fmax(lo_e, fmin(nx, hi_e));
+    if (lane == jj && active) x_new = nx;
+    const double xj = __shfl_sync(0xffffffffu, x_new, jj);
+    if (lane > jj) acc -= a * xj;
+    if (fiLocal == jj) { hi_e = hi_r * xj; lo_e = -hi_e; }  // the friction bound follows the live normal impulse
+  }
+}
+
 template <int CAP>
 __global__ void __launch_bounds__(32)
 k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
            double* __restrict__ ans_x, int* __restrict__ ans_ok, PgsOptions opt) {
   const int w = blockIdx.x, lane = threadIdx.x;
-  const int n = ctrl[4 * w + 2];
-  if (ctrl[4 * w] || n <= nLow || n > CAP) return;
+  const int n = ctrl[8 * w + 2];
+  if (ctrl[8 * w] || n <= nLow || n > CAP) return;
   constexpr int LD = CAP + 1;
   extern __shared__ double sm[];
   double* As = sm;                 // [CAP][LD]
@@ -106,15 +125,17 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
   __syncwarp();
   const int nblk = (n + 31) >> 5;
   bool converged = false;
+  int sweeps = 0;
   // sweep 0 works on the raw matrix (divides by the diagonal, absolute stopping rule); later sweeps on the normalised rows
   for (int iter = 0; iter < opt.maxIteration; iter++) {
     bool mine = true;  // possibleToTerminate restricted to this lane's rows
+    sweeps++;
     for (int blk = 0; blk < nblk; blk++) {
       const int blk0 = blk << 5, r = blk0 + lane;
       const bool valid = r < n;
       const double* Ar = As + (valid ? r : 0) * LD;
       bool active = false;
-      double diag = 1.0, old_x = 0.0, hi_r = 0.0, lo_r = 0.0, xf = 0.0;
+      double diag = 1.0, old_x = 0.0, hi_r = 0.0, lo_r = 0.0, xf = 0.0;  // xf: the normal impulse bounding a friction row
       int fi = -1;
       if (valid) {
         old_x = xs[r]; hi_r = his[r]; lo_r = los[r]; fi = fis[r];
@@ -136,20 +157,14 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
       }
       for (; j < n; j++) a0 -= Ar[j] * xs[j];
       double acc = (a0 + a1) + (a2 + a3);
-      // phase 2
+      // phase 2: branch-free; every lane clamps its own candidate each step, only the owner's is kept
       double x_new = old_x;
       if (valid && iter == 0 && !active) x_new = 0.0;
-      for (int jj = 0; jj < blkEnd - blk0; jj++) {
-        if (lane == jj && active) {
-          double nx = iter == 0 ? acc / diag : acc;
-          if (fi >= 0) { const double h = hi_r * xf; nx = nx > h ? h : (nx < -h ? -h : nx); }
-          else nx = nx > hi_r ? hi_r : (nx < lo_r ? lo_r : nx);
-          x_new = nx;
-        }
-        const double xj = __shfl_sync(0xffffffffu, x_new, jj);
-        if (lane > jj && valid) acc -= Ar[blk0 + jj] * xj;
-        if (fi == blk0 + jj) xf = xj;
-      }
+      const int cnt = blkEnd - blk0;
+      double hi_e = hi_r, lo_e = lo_r;
+      if (fi >= 0) { hi_e = hi_r * xf; lo_e = -hi_e; }
+      if (iter == 0) pgsBlockSteps<true>(Ar + blk0, cnt, lane, active, fi - blk0, hi_r, diag, acc, hi_e, lo_e, x_new);
+      else pgsBlockSteps<false>(Ar + blk0, cnt, lane, active, fi - blk0, hi_r, diag, acc, hi_e, lo_e, x_new);
       if (valid) {
         xs[r] = x_new;
         if (active) {
@@ -172,13 +187,14 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
       __syncwarp();
     }
   }
-  const int slot = ctrl[4 * w + 1];
+  const int slot = ctrl[8 * w + 1];
   double* ax = ans_x + ((size_t)w * kPgsRequests + slot) * kmax;
   for (int i = lane; i < n; i += 32) ax[i] = xs[i];
   if (lane == 0) {
     ans_ok[(size_t)w * kPgsRequests + slot] = converged ? 1 : 0;
-    ctrl[4 * w + 1] = slot + 1;
-    ctrl[4 * w + 2] = 0;
+    ctrl[8 * w + 1] = slot + 1;
+    ctrl[8 * w + 2] = 0;
+    ctrl[8 * w + 3] += sweeps;  // statistics: Gauss-Seidel sweeps spent on this world in this step
   }
 }
 
@@ -188,17 +204,17 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
              int* __restrict__ ans_ok, PgsOptions opt) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
-  const int n = ctrl[4 * w + 2];
-  if (ctrl[4 * w] || n <= nLow) return;
+  const int n = ctrl[8 * w + 2];
+  if (ctrl[8 * w] || n <= nLow) return;
   LcpView v;
   const size_t warp = w >> 5, wl = w & 31;
   v.init(lcp_d + warp * lcpScratchDoubles(kmax) * 32 + wl, lcp_i + warp * lcpScratchInts(kmax) * 32 + wl, n, kmax);
   const bool ok = pgsSolve(v, opt);
-  const int slot = ctrl[4 * w + 1];
+  const int slot = ctrl[8 * w + 1];
   for (int i = 0; i < n; i++) ans_x[((size_t)w * kPgsRequests + slot) * kmax + i] = v.x(i);
   ans_ok[(size_t)w * kPgsRequests + slot] = ok ? 1 : 0;
-  ctrl[4 * w + 1] = slot + 1;
-  ctrl[4 * w + 2] = 0;
+  ctrl[8 * w + 1] = slot + 1;
+  ctrl[8 * w + 2] = 0;
 }
 
 // the contact stage of World::step, one world per thread
@@ -209,7 +225,7 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
           int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= N) return;
-  if (ctrl && ctrl[4 * w]) return;  // this world's stage has been committed by an earlier pass
+  if (ctrl && ctrl[8 * w]) return;  // this world's stage has been committed by an earlier pass
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L};
   const ContactSnapLayout KL{L.nd, L.cmax, L.kmax};
@@ -217,12 +233,13 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
   double* ld = lcp_d + warp * lcpScratchDoubles(L.kmax) * 32 + lane;
   int* li = lcp_i + warp * lcpScratchInts(L.kmax) * 32 + lane;
   int nc = n_cache[w];
-  PgsDefer df{ctrl ? ctrl[4 * w + 1] : 0, 0, L.kmax, 0, kPgsRequests, ans_x + (size_t)w * kPgsRequests * L.kmax, ans_ok + (size_t)w * kPgsRequests};
+  PgsDefer df{ctrl ? ctrl[8 * w + 1] : 0, 0, L.kmax, 0, kPgsRequests, ctrl ? ctrl[8 * w + 4] : 0, ans_x + (size_t)w * kPgsRequests * L.kmax,
+              ans_ok + (size_t)w * kPgsRequests};
   ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs,
                                   keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr,
                                   ctrl ? &df : nullptr);
-  if (o.pending) { ctrl[4 * w + 2] = df.pendingN; return; }  // the reduced problem waits in this world's LCP view
-  if (ctrl) { ctrl[4 * w] = 1; ctrl[4 * w + 2] = 0; }
+  if (o.pending) { ctrl[8 * w + 2] = df.pendingN; ctrl[8 * w + 4] = df.resumeKind; return; }  // the reduced problem waits in this world's LCP view
+  if (ctrl) { ctrl[8 * w] = 1; ctrl[8 * w + 2] = 0; }
   n_cache[w] = nc;
   counts[4 * w] = o.n_contacts; counts[4 * w + 1] = o.n_rows; counts[4 * w + 2] = o.n_groups; counts[4 * w + 3] = o.tier_mask;
   if (active_out) {
@@ -305,8 +322,29 @@ static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int*
   k_pgs_warp<CAP><<<N, 32, bytes, s>>>(N, kmax, nLow, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
   return cudaGetLastError();
 }
+// helper streams of the concurrent PGS size classes, one set per device
+struct PgsStreams {
+  cudaStream_t st[5];
+  cudaEvent_t fork, join[5];
+};
+static PgsStreams* pgsStreams() {
+  static PgsStreams sets[64];
+  static bool ready[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!ready[dev]) {
+    PgsStreams& p = sets[dev];
+    for (int i = 0; i < 5; i++) {
+      if (cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&p.fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    ready[dev] = true;
+  }
+  return &sets[dev];
+}
 void contactPgsSizes(int N, int kmax, size_t* ctrl_ints, size_t* ans_doubles, size_t* ans_ints) {
-  *ctrl_ints = (size_t)N * 4;
+  *ctrl_ints = (size_t)N * 8;  // done, answered, pending rows, sweeps (statistics), resume tier, 3 spare
   *ans_doubles = (size_t)N * kPgsRequests * kmax;
   *ans_ints = (size_t)N * kPgsRequests;
 }
@@ -315,7 +353,7 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
                           int* keep_i, int* ctrl, double* ans_x, int* ans_ok, int* launches) {
   ContactLayout L{nb, nd, cmax, kmax};
   PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
-  cudaError_t e = cudaMemsetAsync(ctrl, 0, (size_t)N * 4 * sizeof(int), s);
+  cudaError_t e = cudaMemsetAsync(ctrl, 0, (size_t)N * 8 * sizeof(int), s);
   if (e != cudaSuccess) return e;
   // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
   for (int pass = 0; pass <= kPgsRequests; pass++) {
@@ -324,14 +362,25 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (pass == kPgsRequests) break;
-    if ((e = launchPgsWarp<64>(s, N, kmax, 0, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
-    if (kmax > 64 && (e = launchPgsWarp<92>(s, N, kmax, 64, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
-    if (kmax > 92 && (e = launchPgsWarp<160>(s, N, kmax, 92, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs)) != cudaSuccess) return e;
-    if (kmax > 160) {
-      k_pgs_thread<<<(N + 63) / 64, 64, 0, s>>>(N, kmax, 160, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
-    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 92) + (kmax > 160);
+    // size classes by shared-memory footprint: 6, 4, 3, 2 and 1 resident worlds per SM. The classes touch disjoint worlds,
+    // so they run side by side on helper streams (fork / join on events): the small problems fill the SMs while the few
+    // worlds that need all 10000 sweeps finish.
+    PgsStreams* ps = pgsStreams();
+    if (!ps) return cudaErrorUnknown;
+    if ((e = cudaEventRecord(ps->fork, s)) != cudaSuccess) return e;
+    auto onHelper = [&](int i, auto launch) -> cudaError_t {
+      cudaError_t r = cudaStreamWaitEvent(ps->st[i], ps->fork, 0);
+      if (r != cudaSuccess) return r;
+      if ((r = launch(ps->st[i])) != cudaSuccess) return r;
+      if ((r = cudaEventRecord(ps->join[i], ps->st[i])) != cudaSuccess) return r;
+      return cudaStreamWaitEvent(s, ps->join[i], 0);
+    };
+    if ((e = onHelper(0, [&](cudaStream_t hs) { return launchPgsWarp<64>(hs, N, kmax, 0, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (kmax > 64 && (e = onHelper(1, [&](cudaStream_t hs) { return launchPgsWarp<76>(hs, N, kmax, 64, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (kmax > 76 && (e = onHelper(2, [&](cudaStream_t hs) { return launchPgsWarp<92>(hs, N, kmax, 76, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (kmax > 92 && (e = onHelper(3, [&](cudaStream_t hs) { return launchPgsWarp<116>(hs, N, kmax, 92, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (kmax > 116 && (e = onHelper(4, [&](cudaStream_t hs) { return launchPgsWarp<160>(hs, N, kmax, 116, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 76) + (kmax > 92) + (kmax > 116) + (kmax > 160);
   }
   return cudaSuccess;
 }

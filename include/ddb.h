@@ -177,6 +177,9 @@ int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t
 int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims,
                            double* A, double* b, double* lo, double* hi, double* x, int32_t* findex);
 
+/* Statistics of the last ddb_forward: Gauss-Seidel sweeps the PGS fallback spent per world (host array [N]). */
+int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out);
+
 /* Replaces BackpropSnapshot::getInvMassMatrix / getMassMatrix helpers
    (python/_diffdart/neural/BackpropSnapshot.cpp:42-146): [N][n][n] col-major. */
 int ddb_inv_mass_matrix(ddb_handle* h, void* cuda_stream, double* minv_dev);

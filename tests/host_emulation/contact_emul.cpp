@@ -121,3 +121,47 @@ extern "C" int emul_cod_apply(int n, const double* Q, const double* rhs, int tra
   codApplyDev(v, n, rank, transposed != 0, [&](int i) { return rhs[i]; }, [&](int i, double x) { out[i] = x; });
   return rank;
 }
+
+// The deferred-PGS control flow of the GPU (k_contact passes + PGS kernel) on the host: the stage is re-entered behind every
+// answered solve; the solves themselves use the scalar pgsSolve, so the result must equal emul_contact_step bit for bit.
+extern "C" int emul_contact_step_deferred(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
+                                          double* lcp_cache, int* n_cache, double* qn, double* qdn, int* counts, double* x_out, int* active_out,
+                                          int* passes_out) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
+  const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  if (c_ctopo.n_pairs == 0) { counts[0] = counts[1] = counts[2] = counts[3] = 0; *passes_out = 0; return 0; }
+  ContactLayout L{nb, nd, cmax, kmax};
+  std::vector<double> wd(L.doubles(), 0.0), ld(lcpScratchDoubles(kmax) * 32, 0.0);
+  std::vector<int> wi(L.ints(), 0), li(lcpScratchInts(kmax) * 32, 0);
+  Snap sn{reinterpret_cast<double2*>(snap.data()), N, 0};
+  ContactWork cw{wd.data(), wi.data(), L};
+  PgsOptions pgs{10000, 1e-10, 1e-8, 1e-8};
+  const int cap = 4;
+  std::vector<double> ansX((size_t)cap * kmax, 0.0);
+  std::vector<int> ansOk(cap, 0);
+  int answered = 0, resumeKind = 0, passes = 0;
+  for (;;) {
+    PgsDefer df{answered, 0, kmax, 0, cap, resumeKind, ansX.data(), ansOk.data()};
+    ContactStepOut o = contactStage(sn, cw, ld.data() + 3, li.data() + 3, qdn, qdn, c_topo.layout, N, 0, lcp_cache, n_cache, pgs, nullptr, nullptr, &df);
+    passes++;
+    if (!o.pending) {
+      counts[0] = o.n_contacts; counts[1] = o.n_rows; counts[2] = o.n_groups; counts[3] = o.tier_mask;
+      break;
+    }
+    resumeKind = df.resumeKind;
+    LcpView v;
+    v.init(ld.data() + 3, li.data() + 3, df.pendingN, kmax);
+    const bool ok = pgsSolve(v, pgs);
+    for (int i = 0; i < df.pendingN; i++) ansX[(size_t)answered * kmax + i] = v.x(i);
+    ansOk[answered++] = ok ? 1 : 0;
+  }
+  *passes_out = passes;
+  for (int k = 0; k < kmax; k++) { x_out[k] = cw.xall()[k]; if (active_out) active_out[k] = cw.activeAll()[k]; }
+  return 0;
+}

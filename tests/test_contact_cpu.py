@@ -39,6 +39,7 @@ def emul():
                                    counts.ctypes.data_as(ip), contacts.ctypes.data_as(dp), bodies.ctypes.data_as(ip), dims.ctypes.data_as(ip),
                                    A.ctypes.data_as(dp), b.ctypes.data_as(dp), x.ctypes.data_as(dp), caps.ctypes.data_as(ip), act.ctypes.data_as(ip))
         assert rc == 0
+        step.lib = lib
         return {"q_next": qn, "qd_next": qdn, "counts": counts, "contacts": contacts.reshape(64, 26)[:counts[0]],
                 "x": x[:max(counts[1], 0)], "lcp_cache": cachebuf[:nc.value].copy(), "active_set": act[:max(counts[1], 0)].copy()}
 
@@ -128,3 +129,38 @@ def test_cod_min_norm_properties(emul):
         assert np.allclose(A.T @ (A @ x - b), 0, atol=1e-8 * max(1.0, np.abs(A).max() ** 2))
         xp = np.linalg.pinv(A, rcond=1e-12) @ b
         assert np.allclose(x, xp, rtol=1e-8, atol=1e-9 * max(1.0, np.abs(xp).max()))
+
+
+@pytest.mark.parametrize("scene", sorted(SCENES))
+def test_deferred_pgs_control_flow_equals_inline(emul, scene):
+    """The GPU hands its PGS solves to a warp-cooperative kernel and re-enters the stage behind each answered solve. The same
+    control flow on the host (scalar PGS for the solves) must reproduce the single-pass stage bit for bit over a rollout."""
+    make, states = SCENES[scene]
+    desc = make()
+    nw = 3 if scene == "box_stack" else 12
+    q, qd, tau = states(nw, 9)
+    n = q.shape[1]
+    most_passes = 1
+    for w in range(nw):
+        qi, qdi, ci = q[w], qd[w], None
+        qe, qde, cache, nc = q[w].copy(), qd[w].copy(), np.zeros(1024), C.c_int(0)
+        for t in range(3):
+            a = emul(desc, qi, qdi, tau[w], cache=ci)
+            topo, params, keep = desc.to_ctypes()
+            qn, qdn = np.zeros(n), np.zeros(n)
+            counts, x, act, passes = np.zeros(4, dtype=np.int32), np.zeros(192), np.zeros(192, dtype=np.int32), C.c_int(0)
+            rc = emul.lib.emul_contact_step_deferred(C.byref(topo), C.byref(params), qe.ctypes.data_as(dp), qde.ctypes.data_as(dp),
+                                                     np.ascontiguousarray(tau[w]).ctypes.data_as(dp), cache.ctypes.data_as(dp), C.byref(nc),
+                                                     qn.ctypes.data_as(dp), qdn.ctypes.data_as(dp), counts.ctypes.data_as(ip), x.ctypes.data_as(dp),
+                                                     act.ctypes.data_as(ip), C.byref(passes))
+            assert rc == 0
+            most_passes = max(most_passes, passes.value)
+            k = max(int(a["counts"][1]), 0)
+            assert list(counts) == list(a["counts"]), (w, t)
+            assert np.array_equal(x[:k], a["x"]) and np.array_equal(act[:k], a["active_set"]), (w, t)
+            assert np.array_equal(qdn, a["qd_next"]) and np.array_equal(qn, a["q_next"]), (w, t)
+            assert np.array_equal(cache[:nc.value], a["lcp_cache"]), (w, t)
+            qi, qdi, ci = a["q_next"], a["qd_next"], a["lcp_cache"]
+            qe, qde = qn, qdn
+    if scene in ("box_stack", "pendulum_on_floor"):
+        assert most_passes >= 2  # some world did hand a PGS solve over
