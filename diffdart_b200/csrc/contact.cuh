@@ -58,6 +58,12 @@ struct ContactWork {
   double* d;
   int* i;
   ContactLayout L;
+  long long* prof = nullptr;  // optional: clock64 ticks per section, summed over worlds (DDB_CONTACT_PROFILE=1)
+  DDB_LCP_DI void mark(int section, long long& t) const {
+#ifdef __CUDA_ARCH__
+    if (prof) { const long long now = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(prof) + section, (unsigned long long)(now - t)); t = now; }
+#endif
+  }
   DDB_LCP_DI double* contact(int c) const { return d + L.oContacts() + (size_t)c * 26; }
   DDB_LCP_DI double* NA(int c, int k) const { return d + L.oNA() + ((size_t)c * 3 + k) * 6; }
   DDB_LCP_DI double* NB(int c, int k) const { return d + L.oNB() + ((size_t)c * 3 + k) * 6; }
@@ -228,10 +234,14 @@ struct PgsDefer {
 // lcp_cache/n_cache: the solver's cached solution mX (in/out). lv: this world's LCP scratch view storage.
 DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, double* lcpD, int* lcpI, const double* qd_pre_in, double* qd_out,
                                        int layout, int N, int w, double* lcp_cache, int* n_cache, const PgsOptions& pgs,
-                                       double* keepD = nullptr, int* keepI = nullptr, PgsDefer* defer = nullptr) {
+                                       double* keepD = nullptr, int* keepI = nullptr, PgsDefer* defer = nullptr, int lcpStride = 32) {
   const int nb = c_topo.nb, nd = c_topo.nd;
   const ContactTopo& ct = c_ctopo;
   ContactStepOut out = {0, 0, 0, 0, 0};
+  long long tmark = 0;
+#ifdef __CUDA_ARCH__
+  if (cw.prof) tmark = clock64();
+#endif
   const bool resuming = defer && defer->resumeKind != 0;
   int* sv = cw.saved();
   int* offs = cw.i + 3 * cw.L.cmax;  // first LCP row of each constraint inside its group
@@ -361,6 +371,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   out.n_groups = ng;
   for (int i = 0; i < nb; i++) for (int k = 0; k < 6; k++) cw.imp(i)[k] = 0.0;
   }
+  cw.mark(0, tmark);  // collision, constraints, groups
   int groupBase[DDB_MAX_BODIES];
   int mxSize = *n_cache;  // the solver's mX persists across groups and steps while its size is unchanged
   double* mx = cw.mx();   // committed to lcp_cache only when the whole stage has run
@@ -459,6 +470,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     else { for (int k = 0; k < n; k++) x0[k] = 0.0; }
     for (int k = 0; k < n; k++) x[k] = x0[k];
     }
+    cw.mark(1, tmark);  // assembly by impulse tests
     // ---- LCPUtils::reduce: merge duplicate columns (index map + column scale instead of explicit matrices) ----
     int* keep = cw.keep();
     int* mapTo = cw.mapTo();
@@ -473,16 +485,17 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       int nr = 0;
       if (frictionless) {
         for (int k = 0; k < n; k++) { if (findex[k] == -1) { mapTo[k] = nr; keep[nr++] = k; } else mapTo[k] = -1; }
-        v.init(lcpD, lcpI, nr, ct.kmax);
+        v.init(lcpD, lcpI, nr, ct.kmax, lcpStride);
         for (int a = 0; a < nr; a++) {
           for (int c2 = 0; c2 < nr; c2++) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]];
           v.b(a) = b[keep[a]]; v.lo(a) = lo[keep[a]]; v.hi(a) = hi[keep[a]]; v.findex(a) = -1; v.x(a) = x0[keep[a]];
+          v.tmp(a) = 1.0;  // column scale (read by the warp-cooperative PGS)
         }
         return nr;
       }
       nr = n;
       // scale[] and fidx[] of the reduced problem are kept in the view's d / C arrays until the copy below
-      v.init(lcpD, lcpI, n, ct.kmax);
+      v.init(lcpD, lcpI, n, ct.kmax, lcpStride);
       for (int k = 0; k < n; k++) { keep[k] = k; mapTo[k] = k; v.d(k) = 1.0; v.C(k) = findex[k]; }
       for (;;) {
         bool found = false;
@@ -569,8 +582,8 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
           if (validWith(xn, ignoreFriction)) { for (int k = 0; k < n; k++) xv[k] = 0.0; return true; }
           return false;
         }
-        v.init(lcpD, lcpI, nc2, ct.kmax);
-        auto Qm = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * nc2 + j) * 32]; };
+        v.init(lcpD, lcpI, nc2, ct.kmax, lcpStride);
+        auto Qm = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * nc2 + j) * v.st]; };
         int* rowOfClamp = keep;
         for (int j = 0; j < n; j++) if (clampIdx[j] >= 0) rowOfClamp[clampIdx[j]] = j;
         for (int a = 0; a < nc2; a++) {
@@ -615,16 +628,17 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       for (int i = 0; i < n; i++) { if (findex[i] == -1) { if (b[i] > 0) keep[ncl++] = i; } else keep[ncl++] = i; }
       for (int k = 0; k < n; k++) x0[k] = 0.0;
       if (ncl > 0) {
-        v.init(lcpD, lcpI, ncl, ct.kmax);
+        v.init(lcpD, lcpI, ncl, ct.kmax, lcpStride);
         for (int a = 0; a < ncl; a++) {
           v.dw(a) = b[keep[a]];
-          for (int c2 = 0; c2 < ncl; c2++) v.db[(size_t)(v.oL + a * ncl + c2) * 32] = A[(size_t)keep[a] * n + keep[c2]];
+          for (int c2 = 0; c2 < ncl; c2++) v.db[(size_t)(v.oL + a * ncl + c2) * v.st] = A[(size_t)keep[a] * n + keep[c2]];
         }
         codSolveDev(v, ncl);
         for (int a = 0; a < ncl; a++) x0[keep[a]] = v.dx(a);
       }
       for (int k = 0; k < n; k++) x[k] = x0[k];
     }
+    cw.mark(2, tmark);  // guessSolution
     bool success = false;
     int tier = 1;
     bool ignoreFrictionFinal = false;
@@ -632,7 +646,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     // the answer of the solve this pass was waiting for, put where mapOut() expects it
     auto loadAnswer = [&]() -> int {
       const int k = defer->answered - 1;
-      v.init(lcpD, lcpI, sv[6], ct.kmax);
+      v.init(lcpD, lcpI, sv[6], ct.kmax, lcpStride);
       for (int i = 0; i < v.n; i++) v.x(i) = defer->ansX[(size_t)k * defer->kmax + i];
       return defer->ansOk[k];
     };
@@ -641,6 +655,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       if (success) tier = 0;
       else for (int k = 0; k < n; k++) x[k] = x0[k];
     }
+    cw.mark(3, tmark);  // short-circuit through the cached solution (classification + least squares)
     if (!success) {
       if (stage == 0) {
         tier = 1;
@@ -648,6 +663,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         success = dantzigSolve(v, 0, true);
         if (success) { mapOut(); if (!isValid()) success = false; }
         if (hasNaN()) { success = false; for (int k = 0; k < n; k++) x[k] = 0.0; }
+        cw.mark(4, tmark);  // reduce + Dantzig + validity
       }
       if (stage == 2 || (stage == 0 && !success)) {
         tier = 2;
@@ -656,6 +672,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         else {
           buildReduced(false);
           pr = runPgs(v);
+          cw.mark(5, tmark);  // reduce for PGS
           if (pr < 0) { saveState(g, 2, v.n); out.pending = 1; return out; }
         }
         success = pr != 0;
@@ -677,6 +694,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         for (int k = 0; k < n; k++) xs[k] = x[k];
         if (constructAndStandardize(xs, ignoreFrictionFinal)) { for (int k = 0; k < n; k++) x[k] = xs[k]; }
       }
+      cw.mark(6, tmark);  // after the PGS answers: validity, classification + least squares
     }
     if (gradients) {
       for (int k = 0; k < n; k++) cw.activeAll()[rowsTotal + k] = mapping[k] >= 0 ? mapping[k] + rowsTotal : mapping[k];
@@ -731,6 +749,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     const size_t ix = vidx(layout, N, nd, w, z);
     qd_out[ix] = qd_pre_in[ix] + cw.dqd()[z];
   }
+  cw.mark(7, tmark);  // commit, per-slot record, final impulse pass
   return out;
 }
 

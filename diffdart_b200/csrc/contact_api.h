@@ -19,6 +19,8 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
 // control words and answer buffers of the deferred PGS solves (ints, doubles, ints for N worlds)
 void contactPgsSizes(int N, int kmax, size_t* ctrl_ints, size_t* ans_doubles, size_t* ans_ints);
 // per-slot storage of what the backward pass needs of the contact stage (doubles / ints for N worlds)
+// DDB_CONTACT_PROFILE=1: read (and reset) the clock64 ticks summed over worlds per section of the contact stage
+int contactProfileRead(long long* out16);
 void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* keep_doubles, size_t* keep_ints);
 // BackpropSnapshot::backprop through the contact solution retained in (snap, keep_d, keep_i); lim6 = 6 x [nd] limits or NULL
 cudaError_t contactBackwardLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int kmax, int layout, double* snap, const double* keep_d,

@@ -202,7 +202,7 @@ struct ContactBwdLocals {  // one object: see the note on BwdScratch (stack colo
 template <int NB>
 DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, const double* keepD, const int* keepI, const ContactBwdWork& bw,
                                 double* lcpD, int* lcpI, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
-                                int layout, int N, int w) {
+                                int layout, int N, int w, int lcpStride = 32) {
   const int nb = c_topo.nb, nd = c_topo.nd;
   const double dt = c_topo.dt;
   const ContactTopo& ctp = c_ctopo;
@@ -322,7 +322,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     }
     // ---- Q = A_c^T M^-1 A and the pseudo-inverse products ----
     LcpView v;
-    v.init(lcpD, lcpI, c, ctp.kmax);
+    v.init(lcpD, lcpI, c, ctp.kmax, lcpStride);
     for (int i = 0; i < c; i++) {
       const double* col = bw.Ac(i);
       for (int j = 0; j < c; j++) {
@@ -333,7 +333,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       }
     }
     // one decomposition of Q serves P b, P^T a, P y1 and P^T r1 (BackpropSnapshot.cpp:3875-3876,3925-3932)
-    for (int i = 0; i < c; i++) for (int j = 0; j < c; j++) v.db[(size_t)(v.oL + i * c + j) * 32] = v.Araw(i, j);
+    for (int i = 0; i < c; i++) for (int j = 0; j < c; j++) v.db[(size_t)(v.oL + i * c + j) * v.st] = v.Araw(i, j);
     const int rank = codFactorDev(v, c);
     codApplyDev(v, c, rank, true, [&](int i) { return va[i]; }, [&](int i, double x) { y1[i] = x; });
     codApplyDev(v, c, rank, false, [&](int i) { return vb[i]; }, [&](int i, double x) { r1[i] = x; });

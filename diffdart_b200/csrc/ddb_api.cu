@@ -395,6 +395,9 @@ int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double
   return DDB_OK;
 }
 
+// DDB_CONTACT_PROFILE=1: clock ticks per section of the contact stage, summed over worlds since the last call (host array [16])
+int ddb_contact_profile_host(int64_t* ticks_out) { return contactProfileRead(reinterpret_cast<long long*>(ticks_out)) ? DDB_OK : DDB_ERR_STATE; }
+
 // Statistics of the last ddb_forward: Gauss-Seidel sweeps spent per world by the warp-cooperative PGS solver (host array [N]).
 int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out) {
   if (!h || !h->hasContacts || !sweeps_out) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");

@@ -39,21 +39,28 @@ struct LcpView {
   double* db;  // this world's double scratch, lane-interleaved
   int* ib;     // this world's int scratch, lane-interleaved
   int n, nskip;
+  int st;  // element stride: 32 = interleaved across the worlds of a warp (one world per thread), 1 = one world per warp
+  int lane, nl;  // one world per warp: this thread's lane and 32, so that loops over independent columns / rows are split
+                 // across the warp (each column is still summed by one lane in the scalar order: results do not change)
   // offsets (elements)
   int oA, oL, ox, ob, ow, olo, ohi, od, odw, odx, oDell, oell, otmp;
   int op, oC, ofi, oar, ost;
-  DDB_LCP_DI void init(double* d, int* i, int n_, int nmax) {
-    db = d; ib = i; n = n_; nskip = dpad(n_);
+  DDB_LCP_DI void init(double* d, int* i, int n_, int nmax, int stride = 32) {
+    db = d; ib = i; n = n_; nskip = dpad(n_); st = stride;
+    lane = 0; nl = 1;
+#ifdef __CUDA_ARCH__
+    if (stride == 1) { lane = threadIdx.x & 31; nl = 32; }
+#endif
     int nsm = dpad(nmax);
     oA = 0; oL = nmax * nsm; ox = 2 * nmax * nsm; ob = ox + nmax; ow = ob + nmax; olo = ow + nmax; ohi = olo + nmax;
     od = ohi + nmax; odw = od + nmax; odx = odw + nmax; oDell = odx + nmax; oell = oDell + nmax; otmp = oell + nmax;
     op = 0; oC = nmax; ofi = 2 * nmax; oar = 3 * nmax; ost = 4 * nmax;
   }
-  DDB_LCP_DI double& D(int off, int i) const { return db[(size_t)(off + i) * 32]; }
-  DDB_LCP_DI int& I(int off, int i) const { return ib[(size_t)(off + i) * 32]; }
-  DDB_LCP_DI double& A(int i, int j) const { return db[(size_t)(oA + I(oar, i) * nskip + j) * 32]; }  // row pointers
-  DDB_LCP_DI double& Araw(int r, int j) const { return db[(size_t)(oA + r * nskip + j) * 32]; }
-  DDB_LCP_DI double& L(int i, int j) const { return db[(size_t)(oL + i * nskip + j) * 32]; }
+  DDB_LCP_DI double& D(int off, int i) const { return db[(size_t)(off + i) * st]; }
+  DDB_LCP_DI int& I(int off, int i) const { return ib[(size_t)(off + i) * st]; }
+  DDB_LCP_DI double& A(int i, int j) const { return db[(size_t)(oA + I(oar, i) * nskip + j) * st]; }  // row pointers
+  DDB_LCP_DI double& Araw(int r, int j) const { return db[(size_t)(oA + r * nskip + j) * st]; }
+  DDB_LCP_DI double& L(int i, int j) const { return db[(size_t)(oL + i * nskip + j) * st]; }
   DDB_LCP_DI double& x(int i) const { return D(ox, i); }
   DDB_LCP_DI double& b(int i) const { return D(ob, i); }
   DDB_LCP_DI double& w(int i) const { return D(ow, i); }
@@ -600,15 +607,45 @@ DDB_LCP_DI bool pgsSolve(const LcpView& v, const PgsOptions& opt) {
 // reflections from the right that annihilate R12 (stored in place), back-substitution, un-permutation.
 // Storage: Q in the view's L area (leading dimension n), rhs in dw (overwritten), result in dx; Dell/ell/d/tmp and the
 // int array p are scratch.
-DDB_LCP_DI int codSolveDev(const LcpView& v, int n) {
-  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * 32]; };
+DDB_LCP_DI void coopSync(const LcpView& v) {
+#ifdef __CUDA_ARCH__
+  if (v.nl > 1) __syncwarp();
+#endif
+}
+// first index of the largest value over j in [from, n), evaluated by the whole warp (or by the one thread)
+template <class F>
+DDB_LCP_DI int coopArgMaxFirst(const LcpView& v, int from, int n, F val) {
+  int best = -1;
+  double bv = 0.0;
+  for (int j = from + v.lane; j < n; j += v.nl) { const double x = val(j); if (best < 0 || x > bv) { best = j; bv = x; } }
+#ifdef __CUDA_ARCH__
+  if (v.nl > 1) {
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, bv, off);
+      const int ob = __shfl_xor_sync(0xffffffffu, best, off);
+      if (ob >= 0 && (best < 0 || ov > bv || (ov == bv && ob < best))) { best = ob; bv = ov; }
+    }
+  }
+#endif
+  return best;
+}
+
+// Householder QR with column pivoting + the right-hand reflections of the complete orthogonal decomposition.
+// WITH_RHS: the left reflections are applied to dw on the fly (codSolveDev); otherwise their scales are kept in ell
+// (codFactorDev). Loops over independent columns / rows are split across the lanes when one warp owns the world.
+template <bool WITH_RHS>
+DDB_LCP_DI int codFactorImpl(const LcpView& v, int n) {
+  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * v.st]; };
   const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
-  for (int j = 0; j < n; j++) {
+  const int lane = v.lane, nl = v.nl;
+  coopSync(v);  // the lanes filled the matrix redundantly: all of those stores land before any lane starts to transform it
+  for (int j = lane; j < n; j += nl) {
     v.p(j) = j;
     double s = 0;
     for (int i = 0; i < n; i++) s += Q(i, j) * Q(i, j);
     v.Dell(j) = v.ell(j) = sqrt(s);
   }
+  coopSync(v);
   double maxNorm = 0;
   for (int j = 0; j < n; j++) maxNorm = fmax(maxNorm, v.Dell(j));
   const double thresholdHelper = (maxNorm * eps) * (maxNorm * eps) / double(n);
@@ -616,175 +653,68 @@ DDB_LCP_DI int codSolveDev(const LcpView& v, int n) {
   int nonzeroPivots = n;
   double maxPivot = 0;
   for (int k = 0; k < n; k++) {
-    int big = k;
-    for (int j = k + 1; j < n; j++) if (v.Dell(j) > v.Dell(big)) big = j;
+    const int big = coopArgMaxFirst(v, k, n, [&](int j) { return v.Dell(j); });
     const double bigSq = v.Dell(big) * v.Dell(big);
     if (nonzeroPivots == n && bigSq < thresholdHelper * double(n - k)) nonzeroPivots = k;
+    coopSync(v);
     if (big != k) {
-      for (int i = 0; i < n; i++) { double t = Q(i, k); Q(i, k) = Q(i, big); Q(i, big) = t; }
-      double t = v.Dell(k); v.Dell(k) = v.Dell(big); v.Dell(big) = t;
-      t = v.ell(k); v.ell(k) = v.ell(big); v.ell(big) = t;
-      int ti = v.p(k); v.p(k) = v.p(big); v.p(big) = ti;
+      for (int i = lane; i < n; i += nl) { double t = Q(i, k); Q(i, k) = Q(i, big); Q(i, big) = t; }
+      if (lane == 0) {
+        double t = v.Dell(k); v.Dell(k) = v.Dell(big); v.Dell(big) = t;
+        t = v.ell(k); v.ell(k) = v.ell(big); v.ell(big) = t;
+        int ti = v.p(k); v.p(k) = v.p(big); v.p(big) = ti;
+      }
+      coopSync(v);
     }
     double c0 = Q(k, k), tailSq = 0;
     for (int i = k + 1; i < n; i++) tailSq += Q(i, k) * Q(i, k);
     double beta, t;
+    coopSync(v);
     if (tailSq <= tiny) {
       t = 0; beta = c0;
-      for (int i = k + 1; i < n; i++) Q(i, k) = 0;
+      for (int i = k + 1 + lane; i < n; i += nl) Q(i, k) = 0;
     } else {
       beta = sqrt(c0 * c0 + tailSq);
       if (c0 >= 0) beta = -beta;
-      for (int i = k + 1; i < n; i++) Q(i, k) /= (c0 - beta);
+      for (int i = k + 1 + lane; i < n; i += nl) Q(i, k) /= (c0 - beta);
       t = (beta - c0) / beta;
     }
-    Q(k, k) = beta;
+    if (lane == 0) Q(k, k) = beta;
     if (fabs(beta) > maxPivot) maxPivot = fabs(beta);
-    for (int j = k + 1; j < n; j++) {
+    coopSync(v);
+    for (int j = k + 1 + lane; j < n; j += nl) {
       double s = Q(k, j);
       for (int i = k + 1; i < n; i++) s += Q(i, k) * Q(i, j);
       s *= t;
       Q(k, j) -= s;
       for (int i = k + 1; i < n; i++) Q(i, j) -= s * Q(i, k);
+      // LAPACK-style column norm downdate of the same column
+      if (v.Dell(j) != 0) {
+        double temp = fabs(Q(k, j)) / v.Dell(j);
+        temp = (1.0 + temp) * (1.0 - temp);
+        temp = temp < 0 ? 0 : temp;
+        const double r = v.Dell(j) / v.ell(j);
+        const double temp2 = temp * r * r;
+        if (temp2 <= downdateThreshold) {
+          double s2 = 0;
+          for (int i = k + 1; i < n; i++) s2 += Q(i, j) * Q(i, j);
+          v.ell(j) = v.Dell(j) = sqrt(s2);
+        } else {
+          v.Dell(j) *= sqrt(temp);
+        }
+      }
     }
-    {
+    if (WITH_RHS) {
       double s = v.dw(k);
       for (int i = k + 1; i < n; i++) s += Q(i, k) * v.dw(i);
       s *= t;
-      v.dw(k) -= s;
-      for (int i = k + 1; i < n; i++) v.dw(i) -= s * Q(i, k);
-    }
-    for (int j = k + 1; j < n; j++) {
-      if (v.Dell(j) != 0) {
-        double temp = fabs(Q(k, j)) / v.Dell(j);
-        temp = (1.0 + temp) * (1.0 - temp);
-        temp = temp < 0 ? 0 : temp;
-        const double r = v.Dell(j) / v.ell(j);
-        const double temp2 = temp * r * r;
-        if (temp2 <= downdateThreshold) {
-          double s = 0;
-          for (int i = k + 1; i < n; i++) s += Q(i, j) * Q(i, j);
-          v.ell(j) = v.Dell(j) = sqrt(s);
-        } else {
-          v.Dell(j) *= sqrt(temp);
-        }
-      }
-    }
-  }
-  int rank = 0;
-  const double premult = maxPivot * eps * double(n);
-  for (int i = 0; i < nonzeroPivots; i++) if (fabs(Q(i, i)) > premult) rank++;
-  for (int j = 0; j < n; j++) v.dx(j) = 0.0;
-  if (rank == 0) return 0;
-  if (rank < n) {
-    for (int k = rank - 1; k >= 0; k--) {
-      double c0 = Q(k, k), tailSq = 0;
-      for (int j = rank; j < n; j++) tailSq += Q(k, j) * Q(k, j);
-      double beta, t;
-      if (tailSq <= tiny) { t = 0; beta = c0; for (int j = rank; j < n; j++) Q(k, j) = 0; }
-      else {
-        beta = sqrt(c0 * c0 + tailSq);
-        if (c0 >= 0) beta = -beta;
-        for (int j = rank; j < n; j++) Q(k, j) /= (c0 - beta);  // reflector vector kept in place of the annihilated row
-        t = (beta - c0) / beta;
-      }
-      for (int i = 0; i < k; i++) {
-        double s = Q(i, k);
-        for (int j = rank; j < n; j++) s += Q(i, j) * Q(k, j);
-        s *= t;
-        Q(i, k) -= s;
-        for (int j = rank; j < n; j++) Q(i, j) -= s * Q(k, j);
-      }
-      Q(k, k) = beta;
-      v.d(k) = t;
-    }
-  }
-  for (int i = rank - 1; i >= 0; i--) {
-    double s = v.dw(i);
-    for (int j = i + 1; j < rank; j++) s -= Q(i, j) * v.tmp(j);
-    v.tmp(i) = s / Q(i, i);
-  }
-  for (int j = rank; j < n; j++) v.tmp(j) = 0.0;
-  if (rank < n) {
-    for (int k = 0; k < rank; k++) {
-      double s = v.tmp(k);
-      for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
-      s *= v.d(k);
-      v.tmp(k) -= s;
-      for (int j = rank; j < n; j++) v.tmp(j) -= s * Q(k, j);
-    }
-  }
-  for (int j = 0; j < n; j++) v.dx(v.p(j)) = v.tmp(j);
-  return rank;
-}
-
-// The same complete orthogonal decomposition kept as a factorisation so that P b and P^T a (P = Q^+) come out of ONE
-// decomposition, as Eigen's `Qfactored.solve(b)` / `Qfactored.pseudoInverse()` do at BackpropSnapshot.cpp:3875-3876,
-// 3925-3932. Storage as codSolveDev; the QR reflector scales are kept in ell, those of the right-hand reflections in d.
-DDB_LCP_DI int codFactorDev(const LcpView& v, int n) {
-  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * 32]; };
-  const double eps = 2.220446049250313e-16, tiny = 2.2250738585072014e-308;
-  for (int j = 0; j < n; j++) {
-    v.p(j) = j;
-    double s = 0;
-    for (int i = 0; i < n; i++) s += Q(i, j) * Q(i, j);
-    v.Dell(j) = v.ell(j) = sqrt(s);
-  }
-  double maxNorm = 0;
-  for (int j = 0; j < n; j++) maxNorm = fmax(maxNorm, v.Dell(j));
-  const double thresholdHelper = (maxNorm * eps) * (maxNorm * eps) / double(n);
-  const double downdateThreshold = sqrt(eps);
-  int nonzeroPivots = n;
-  double maxPivot = 0;
-  for (int k = 0; k < n; k++) {
-    int big = k;
-    for (int j = k + 1; j < n; j++) if (v.Dell(j) > v.Dell(big)) big = j;
-    const double bigSq = v.Dell(big) * v.Dell(big);
-    if (nonzeroPivots == n && bigSq < thresholdHelper * double(n - k)) nonzeroPivots = k;
-    if (big != k) {
-      for (int i = 0; i < n; i++) { double t = Q(i, k); Q(i, k) = Q(i, big); Q(i, big) = t; }
-      double t = v.Dell(k); v.Dell(k) = v.Dell(big); v.Dell(big) = t;
-      t = v.ell(k); v.ell(k) = v.ell(big); v.ell(big) = t;
-      int ti = v.p(k); v.p(k) = v.p(big); v.p(big) = ti;
-    }
-    double c0 = Q(k, k), tailSq = 0;
-    for (int i = k + 1; i < n; i++) tailSq += Q(i, k) * Q(i, k);
-    double beta, t;
-    if (tailSq <= tiny) {
-      t = 0; beta = c0;
-      for (int i = k + 1; i < n; i++) Q(i, k) = 0;
+      coopSync(v);
+      if (lane == 0) v.dw(k) -= s;
+      for (int i = k + 1 + lane; i < n; i += nl) v.dw(i) -= s * Q(i, k);
     } else {
-      beta = sqrt(c0 * c0 + tailSq);
-      if (c0 >= 0) beta = -beta;
-      for (int i = k + 1; i < n; i++) Q(i, k) /= (c0 - beta);
-      t = (beta - c0) / beta;
+      if (lane == 0) v.ell(k) = t;  // column k is final: its norm slots are free
     }
-    Q(k, k) = beta;
-    if (fabs(beta) > maxPivot) maxPivot = fabs(beta);
-    for (int j = k + 1; j < n; j++) {
-      double s = Q(k, j);
-      for (int i = k + 1; i < n; i++) s += Q(i, k) * Q(i, j);
-      s *= t;
-      Q(k, j) -= s;
-      for (int i = k + 1; i < n; i++) Q(i, j) -= s * Q(i, k);
-    }
-    for (int j = k + 1; j < n; j++) {
-      if (v.Dell(j) != 0) {
-        double temp = fabs(Q(k, j)) / v.Dell(j);
-        temp = (1.0 + temp) * (1.0 - temp);
-        temp = temp < 0 ? 0 : temp;
-        const double r = v.Dell(j) / v.ell(j);
-        const double temp2 = temp * r * r;
-        if (temp2 <= downdateThreshold) {
-          double s = 0;
-          for (int i = k + 1; i < n; i++) s += Q(i, j) * Q(i, j);
-          v.ell(j) = v.Dell(j) = sqrt(s);
-        } else {
-          v.Dell(j) *= sqrt(temp);
-        }
-      }
-    }
-    v.ell(k) = t;  // column k is final: its norm slots are free
+    coopSync(v);
   }
   int rank = 0;
   const double premult = maxPivot * eps * double(n);
@@ -794,83 +724,126 @@ DDB_LCP_DI int codFactorDev(const LcpView& v, int n) {
       double c0 = Q(k, k), tailSq = 0;
       for (int j = rank; j < n; j++) tailSq += Q(k, j) * Q(k, j);
       double beta, t;
-      if (tailSq <= tiny) { t = 0; beta = c0; for (int j = rank; j < n; j++) Q(k, j) = 0; }
+      coopSync(v);
+      if (tailSq <= tiny) { t = 0; beta = c0; for (int j = rank + lane; j < n; j += nl) Q(k, j) = 0; }
       else {
         beta = sqrt(c0 * c0 + tailSq);
         if (c0 >= 0) beta = -beta;
-        for (int j = rank; j < n; j++) Q(k, j) /= (c0 - beta);
+        for (int j = rank + lane; j < n; j += nl) Q(k, j) /= (c0 - beta);  // reflector vector kept in place of the annihilated row
         t = (beta - c0) / beta;
       }
-      for (int i = 0; i < k; i++) {
+      coopSync(v);
+      for (int i = lane; i < k; i += nl) {
         double s = Q(i, k);
         for (int j = rank; j < n; j++) s += Q(i, j) * Q(k, j);
         s *= t;
         Q(i, k) -= s;
         for (int j = rank; j < n; j++) Q(i, j) -= s * Q(k, j);
       }
-      Q(k, k) = beta;
-      v.d(k) = t;
+      if (lane == 0) { Q(k, k) = beta; v.d(k) = t; }
+      coopSync(v);
     }
   }
   return rank;
 }
+// tmp <- solution of the triangular system + the right-hand reflections; every lane runs it (O(n^2), sequential sums)
+DDB_LCP_DI void codBackSolve(const LcpView& v, int n, int rank) {
+  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * v.st]; };
+  coopSync(v);
+  for (int i = rank - 1; i >= 0; i--) {
+    double s = v.dw(i);
+    for (int j = i + 1; j < rank; j++) s -= Q(i, j) * v.tmp(j);
+    coopSync(v);
+    if (v.lane == 0) v.tmp(i) = s / Q(i, i);
+    coopSync(v);
+  }
+  for (int j = rank + v.lane; j < n; j += v.nl) v.tmp(j) = 0.0;
+  coopSync(v);
+  if (rank < n) {
+    for (int k = 0; k < rank; k++) {
+      double s = v.tmp(k);
+      for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
+      s *= v.d(k);
+      coopSync(v);
+      if (v.lane == 0) v.tmp(k) -= s;
+      for (int j = rank + v.lane; j < n; j += v.nl) v.tmp(j) -= s * Q(k, j);
+      coopSync(v);
+    }
+  }
+}
+DDB_LCP_DI int codSolveDev(const LcpView& v, int n) {
+  const int rank = codFactorImpl<true>(v, n);
+  for (int j = v.lane; j < n; j += v.nl) v.dx(j) = 0.0;
+  coopSync(v);
+  if (rank == 0) return 0;
+  codBackSolve(v, n, rank);
+  for (int j = v.lane; j < n; j += v.nl) v.dx(v.p(j)) = v.tmp(j);
+  coopSync(v);
+  return rank;
+}
+
+// The same complete orthogonal decomposition kept as a factorisation so that P b and P^T a (P = Q^+) come out of ONE
+// decomposition, as Eigen's `Qfactored.solve(b)` / `Qfactored.pseudoInverse()` do at BackpropSnapshot.cpp:3875-3876,
+// 3925-3932. Storage as codSolveDev; the QR reflector scales are kept in ell, those of the right-hand reflections in d.
+DDB_LCP_DI int codFactorDev(const LcpView& v, int n) { return codFactorImpl<false>(v, n); }
 // out = P rhs (transposed = false) or P^T rhs (transposed = true) from codFactorDev's factorisation; dw / tmp are scratch
 template <class RhsF, class OutF>
 DDB_LCP_DI void codApplyDev(const LcpView& v, int n, int rank, bool transposed, RhsF rhs, OutF out) {
-  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * 32]; };
+  auto Q = [&](int i, int j) -> double& { return v.db[(size_t)(v.oL + i * n + j) * v.st]; };
+  const int lane = v.lane, nl = v.nl;
   if (rank == 0) { for (int j = 0; j < n; j++) out(j, 0.0); return; }
+  coopSync(v);
   if (!transposed) {
-    for (int i = 0; i < n; i++) v.dw(i) = rhs(i);
+    for (int i = lane; i < n; i += nl) v.dw(i) = rhs(i);
+    coopSync(v);
     for (int k = 0; k < n; k++) {
       double s = v.dw(k);
       for (int i = k + 1; i < n; i++) s += Q(i, k) * v.dw(i);
       s *= v.ell(k);
-      v.dw(k) -= s;
-      for (int i = k + 1; i < n; i++) v.dw(i) -= s * Q(i, k);
+      coopSync(v);
+      if (lane == 0) v.dw(k) -= s;
+      for (int i = k + 1 + lane; i < n; i += nl) v.dw(i) -= s * Q(i, k);
+      coopSync(v);
     }
-    for (int i = rank - 1; i >= 0; i--) {
-      double s = v.dw(i);
-      for (int j = i + 1; j < rank; j++) s -= Q(i, j) * v.tmp(j);
-      v.tmp(i) = s / Q(i, i);
-    }
-    for (int j = rank; j < n; j++) v.tmp(j) = 0.0;
-    if (rank < n) {
-      for (int k = 0; k < rank; k++) {
-        double s = v.tmp(k);
-        for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
-        s *= v.d(k);
-        v.tmp(k) -= s;
-        for (int j = rank; j < n; j++) v.tmp(j) -= s * Q(k, j);
-      }
-    }
-    for (int j = 0; j < n; j++) v.dw(v.p(j)) = v.tmp(j);
+    codBackSolve(v, n, rank);
+    for (int j = lane; j < n; j += nl) v.dw(v.p(j)) = v.tmp(j);
+    coopSync(v);
     for (int j = 0; j < n; j++) out(j, v.dw(j));
   } else {
-    for (int j = 0; j < n; j++) v.tmp(j) = rhs(v.p(j));
+    for (int j = lane; j < n; j += nl) v.tmp(j) = rhs(v.p(j));
+    coopSync(v);
     if (rank < n) {
       for (int k = rank - 1; k >= 0; k--) {
         double s = v.tmp(k);
         for (int j = rank; j < n; j++) s += Q(k, j) * v.tmp(j);
         s *= v.d(k);
-        v.tmp(k) -= s;
-        for (int j = rank; j < n; j++) v.tmp(j) -= s * Q(k, j);
+        coopSync(v);
+        if (lane == 0) v.tmp(k) -= s;
+        for (int j = rank + lane; j < n; j += nl) v.tmp(j) -= s * Q(k, j);
+        coopSync(v);
       }
     }
     for (int i = 0; i < rank; i++) {  // T^T y = z
       double s = v.tmp(i);
       for (int j = 0; j < i; j++) s -= Q(j, i) * v.dw(j);
-      v.dw(i) = s / Q(i, i);
+      coopSync(v);
+      if (lane == 0) v.dw(i) = s / Q(i, i);
+      coopSync(v);
     }
-    for (int j = rank; j < n; j++) v.dw(j) = 0.0;
+    for (int j = rank + lane; j < n; j += nl) v.dw(j) = 0.0;
+    coopSync(v);
     for (int k = n - 1; k >= 0; k--) {
       double s = v.dw(k);
       for (int i = k + 1; i < n; i++) s += Q(i, k) * v.dw(i);
       s *= v.ell(k);
-      v.dw(k) -= s;
-      for (int i = k + 1; i < n; i++) v.dw(i) -= s * Q(i, k);
+      coopSync(v);
+      if (lane == 0) v.dw(k) -= s;
+      for (int i = k + 1 + lane; i < n; i += nl) v.dw(i) -= s * Q(i, k);
+      coopSync(v);
     }
     for (int j = 0; j < n; j++) out(j, v.dw(j));
   }
+  coopSync(v);
 }
 
 // LCPUtils::isLCPSolutionValid (LCPUtils.cpp:12-81), tol 1e-5. Af(i,j), xf, bf, hif, lof, fif are accessors

@@ -1,5 +1,6 @@
 // lcp_api.cu — batched boxed-LCP entry points of the C ABI (compiled with -fmad=false, see lcp.cuh).
 #include <cstdio>
+#include <cstdlib>
 #include "../../include/ddb.h"
 #include "contact.cuh"
 #include "contact_bwd.cuh"
@@ -69,37 +70,49 @@ k_collide_pairs(int N, const int* __restrict__ shape1, const double* __restrict_
   }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// PgsBoxedLcpSolver::solve (PgsBoxedLcpSolver.cpp:79-262), one warp per world, the matrix in shared memory.
-// Gauss-Seidel is sequential in the rows, so the warp works on blocks of 32 consecutive rows with lane r owning row r:
-//   phase 1 (parallel)    acc_r = b_r - sum_{j before the block} A_rj x_j(new) - sum_{j > r} A_rj x_j(old)
-//   phase 2 (32 steps)    lane j clamps acc_j into x_j and broadcasts it (one shuffle); lanes r > j subtract A_rj x_j
-// The sweep order, the projections (friction bounds from the live normal impulse) and the stopping rules are the
-// reference's; the summation order inside a row is not (the reference accumulates left to right), so the result agrees
-// with a scalar run to rounding, not bit for bit. Rows whose diagonal is below epsilonForDivision are left at 0.
-// Shared-memory rows are padded to an odd stride: the 32 lanes read 32 different rows without bank conflicts.
-// ---------------------------------------------------------------------------------------------------------------
 constexpr int kPgsRequests = 4;  // PGS solves a world can hand over per step (2 tiers x 2 constrained groups); more run inline
 
-// The 32 sequential steps of one row block (phase 2 of k_pgs_warp). Per step the critical path is one shuffle, one DFMA
-// and the two min/max of the projection; the matrix element of the next step is fetched ahead of the shuffle.
+// The 32 sequential steps of one row block (phase 2 of k_pgs_warp). Every lane projects its own candidate each step and the
+// owner's is broadcast, so the critical path of a step is one shuffle, one DFMA and the min / max of the projection; the
+// matrix element of the next step is fetched (and scaled) ahead of the shuffle. Rows that are not iterated (zero
+// diagonal) carry lo = hi = their value, so the projection returns it unchanged.
 template <bool FIRST>
-__device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ ArBlk, int cnt, int lane, bool active, int fiLocal, double hi_r,
-                                              double diag, double& acc, double& hi_e, double& lo_e, double& x_new) {
-  double a_next = ArBlk[0];
+__device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, const double* __restrict__ sc, int blk0, int r, int cnt, int lane,
+                                              int fiLocal, double hi_r, double diag, double f_r, double& acc, double& hi_e, double& lo_e,
+                                              double& x_new) {
+  // S[r][blk0 + jj]: below the diagonal (jj < lane) it sits in this lane's packed row, above it in row blk0 + jj
+  auto elem = [&](int jj) {
+    const int j = blk0 + jj;
+    const int idx = jj <= lane ? (r * (r + 1)) / 2 + j : (j * (j + 1)) / 2 + r;
+    return S[idx] * sc[j] * f_r;
+  };
+  double a_next = elem(0);
 #pragma unroll 8
   for (int jj = 0; jj < cnt; jj++) {
     const double a = a_next;
-    a_next = ArBlk[jj + 1 < cnt ? jj + 1 : jj];
+    a_next = elem(jj + 1 < cnt ? jj + 1 : jj);
     double nx = FIRST ? acc / diag : acc;
     nx = fmax(lo_e, fmin(nx, hi_e));
-    if (lane == jj && active) x_new = nx;
-    const double xj = __shfl_sync(0xffffffffu, x_new, jj);
-    if (lane > jj) acc -= a * xj;
+    if (lane == jj) x_new = nx;
+    const double xj = __shfl_sync(0xffffffffu, nx, jj);
+    if (lane > jj) acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
     if (fiLocal == jj) { hi_e = hi_r * xj; lo_e = -hi_e; }  // the friction bound follows the live normal impulse
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// PgsBoxedLcpSolver::solve (PgsBoxedLcpSolver.cpp:79-262), one warp per world, the matrix in shared memory.
+// Gauss-Seidel is sequential in the rows, so the warp works on blocks of 32 consecutive rows with lane r owning row r:
+//   phase 1 (parallel)    acc_r = b_r - sum_{j before the block} A_rj x_j(new) - sum_{j > r} A_rj x_j(old)
+//   phase 2 (32 steps)    lane j projects acc_j into x_j and broadcasts it (one shuffle); lanes r > j subtract A_rj x_j
+// The sweep order, the projections (friction bounds from the live normal impulse) and the stopping rules are the
+// reference's; the summation order inside a row is not (the reference accumulates left to right), so the result agrees
+// with a scalar run to rounding, not bit for bit. Rows whose diagonal is below epsilonForDivision are left at 0.
+// The reduced matrix is A[keep][keep] * diag(scale) with A symmetric (LCPUtils::reduce merges duplicate columns by
+// doubling one of them): only the packed lower triangle of the symmetric part is kept, which halves the shared-memory
+// footprint and doubles the worlds resident on an SM. Triangular offsets of 16 consecutive rows are distinct modulo
+// 16, so the lane-owns-row reads are free of bank conflicts in both halves of the triangle.
+// ---------------------------------------------------------------------------------------------------------------
 template <int CAP>
 __global__ void __launch_bounds__(32)
 k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
@@ -107,21 +120,25 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
   const int w = blockIdx.x, lane = threadIdx.x;
   const int n = ctrl[8 * w + 2];
   if (ctrl[8 * w] || n <= nLow || n > CAP) return;
-  constexpr int LD = CAP + 1;
   extern __shared__ double sm[];
-  double* As = sm;                 // [CAP][LD]
-  double* bs = As + CAP * LD;      // [CAP]
+  double* S = sm;                          // packed lower triangle, row i at i (i + 1) / 2
+  double* bs = S + (CAP * (CAP + 1)) / 2;  // [CAP] each:
   double* los = bs + CAP;
   double* his = los + CAP;
-  double* xs = his + CAP;
-  int* fis = reinterpret_cast<int*>(xs + CAP);
-  int* act = fis + CAP;
+  double* xs = his + CAP;   // x
+  double* ys = xs + CAP;    // scale * x
+  double* sc = ys + CAP;    // column scale of the reduced problem
+  int* fis = reinterpret_cast<int*>(sc + CAP);
   LcpView v;
-  const size_t warp = w >> 5, wl = w & 31;
-  v.init(lcp_d + warp * lcpScratchDoubles(kmax) * 32 + wl, lcp_i + warp * lcpScratchInts(kmax) * 32 + wl, n, kmax);
+  v.init(lcp_d + (size_t)w * lcpScratchDoubles(kmax), lcp_i + (size_t)w * lcpScratchInts(kmax), n, kmax, 1);
+  for (int i = lane; i < n; i += 32) {
+    bs[i] = v.b(i); los[i] = v.lo(i); his[i] = v.hi(i); xs[i] = v.x(i); fis[i] = v.findex(i);
+    sc[i] = v.tmp(i);  // buildReduced leaves the column scales here (powers of two)
+  }
+  __syncwarp();
   for (int r = 0; r < n; r++)
-    for (int j = lane; j < n; j += 32) As[r * LD + j] = v.Araw(r, j);
-  for (int i = lane; i < n; i += 32) { bs[i] = v.b(i); los[i] = v.lo(i); his[i] = v.hi(i); xs[i] = v.x(i); fis[i] = v.findex(i); }
+    for (int j = lane; j <= r; j += 32) S[(r * (r + 1)) / 2 + j] = v.Araw(r, j) / sc[j];
+  for (int i = lane; i < n; i += 32) ys[i] = sc[i] * xs[i];
   __syncwarp();
   const int nblk = (n + 31) >> 5;
   bool converged = false;
@@ -131,42 +148,38 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
     bool mine = true;  // possibleToTerminate restricted to this lane's rows
     sweeps++;
     for (int blk = 0; blk < nblk; blk++) {
-      const int blk0 = blk << 5, r = blk0 + lane;
-      const bool valid = r < n;
-      const double* Ar = As + (valid ? r : 0) * LD;
-      bool active = false;
-      double diag = 1.0, old_x = 0.0, hi_r = 0.0, lo_r = 0.0, xf = 0.0;  // xf: the normal impulse bounding a friction row
-      int fi = -1;
-      if (valid) {
-        old_x = xs[r]; hi_r = his[r]; lo_r = los[r]; fi = fis[r];
-        if (iter == 0) { diag = Ar[r]; active = !(diag < opt.epsilonForDivision); act[r] = active ? 1 : 0; }
-        else active = act[r] != 0;
-        if (fi >= 0 && fi < blk0) xf = xs[fi];  // a normal row of an earlier block: already final in this sweep
-      }
+      const int blk0 = blk << 5, blkEnd = min(blk0 + 32, n);
+      const bool valid = blk0 + lane < n;
+      const int r = valid ? blk0 + lane : blkEnd - 1;  // idle lanes shadow the last row (their results are dropped)
+      const int tr = (r * (r + 1)) / 2;
+      const double diag = S[tr + r] * sc[r];
+      const bool active = !(diag < opt.epsilonForDivision);
+      const double old_x = xs[r], hi_r = his[r];
+      const int fi = fis[r];
+      const double f_r = iter == 0 ? 1.0 : 1.0 / diag;  // row normalisation (PgsBoxedLcpSolver.cpp:171-178)
       // phase 1
-      double a0 = valid ? bs[r] : 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int j = 0;
       for (; j + 3 < blk0; j += 4) {
-        a0 -= Ar[j] * xs[j]; a1 -= Ar[j + 1] * xs[j + 1]; a2 -= Ar[j + 2] * xs[j + 2]; a3 -= Ar[j + 3] * xs[j + 3];
+        a0 = __fma_rn(S[tr + j], ys[j], a0); a1 = __fma_rn(S[tr + j + 1], ys[j + 1], a1); a2 = __fma_rn(S[tr + j + 2], ys[j + 2], a2); a3 = __fma_rn(S[tr + j + 3], ys[j + 3], a3);
       }
-      for (; j < blk0; j++) a0 -= Ar[j] * xs[j];
-      const int blkEnd = min(blk0 + 32, n);
-      for (j = blk0; j < blkEnd; j++) if (j > r) a1 -= Ar[j] * xs[j];
+      for (; j < blk0; j++) a0 += S[tr + j] * ys[j];
+      for (j = blk0; j < blkEnd; j++) if (j > r) a1 += S[(j * (j + 1)) / 2 + r] * ys[j];
       for (j = blkEnd; j + 3 < n; j += 4) {
-        a0 -= Ar[j] * xs[j]; a1 -= Ar[j + 1] * xs[j + 1]; a2 -= Ar[j + 2] * xs[j + 2]; a3 -= Ar[j + 3] * xs[j + 3];
+        a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], ys[j], a0); a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], ys[j + 1], a1);
+        a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], ys[j + 2], a2); a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], ys[j + 3], a3);
       }
-      for (; j < n; j++) a0 -= Ar[j] * xs[j];
-      double acc = (a0 + a1) + (a2 + a3);
-      // phase 2: branch-free; every lane clamps its own candidate each step, only the owner's is kept
+      for (; j < n; j++) a0 += S[(j * (j + 1)) / 2 + r] * ys[j];
+      double acc = (bs[r] - ((a0 + a1) + (a2 + a3))) * f_r;
+      // phase 2
       double x_new = old_x;
-      if (valid && iter == 0 && !active) x_new = 0.0;
-      const int cnt = blkEnd - blk0;
-      double hi_e = hi_r, lo_e = lo_r;
-      if (fi >= 0) { hi_e = hi_r * xf; lo_e = -hi_e; }
-      if (iter == 0) pgsBlockSteps<true>(Ar + blk0, cnt, lane, active, fi - blk0, hi_r, diag, acc, hi_e, lo_e, x_new);
-      else pgsBlockSteps<false>(Ar + blk0, cnt, lane, active, fi - blk0, hi_r, diag, acc, hi_e, lo_e, x_new);
+      double hi_e = hi_r, lo_e = los[r];
+      if (fi >= 0) { hi_e = hi_r * xs[fi]; lo_e = -hi_e; }  // a normal row of an earlier block is final; one of this block is replaced in its step
+      if (!active) { hi_e = lo_e = iter == 0 ? 0.0 : old_x; }
+      if (iter == 0) pgsBlockSteps<true>(S, sc, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, hi_r, active ? diag : 1.0, f_r, acc, hi_e, lo_e, x_new);
+      else pgsBlockSteps<false>(S, sc, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, hi_r, diag, f_r, acc, hi_e, lo_e, x_new);
       if (valid) {
-        xs[r] = x_new;
+        xs[r] = x_new; ys[r] = sc[r] * x_new;
         if (active) {
           if (iter == 0) { if (fabs(x_new - old_x) > opt.deltaXThreshold) mine = false; }
           else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs((x_new - old_x) / x_new) > opt.relativeDeltaXTolerance) mine = false; }
@@ -176,16 +189,6 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
     }
     converged = __all_sync(0xffffffffu, mine);
     if (converged) break;
-    if (iter == 0) {
-      // row normalisation (PgsBoxedLcpSolver.cpp:171-178)
-      for (int r = lane; r < n; r += 32) {
-        if (!act[r]) continue;
-        const double dummy = 1.0 / As[r * LD + r];
-        bs[r] *= dummy;
-        for (int j = 0; j < n; j++) As[r * LD + j] *= dummy;
-      }
-      __syncwarp();
-    }
   }
   const int slot = ctrl[8 * w + 1];
   double* ax = ans_x + ((size_t)w * kPgsRequests + slot) * kmax;
@@ -207,8 +210,7 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
   const int n = ctrl[8 * w + 2];
   if (ctrl[8 * w] || n <= nLow) return;
   LcpView v;
-  const size_t warp = w >> 5, wl = w & 31;
-  v.init(lcp_d + warp * lcpScratchDoubles(kmax) * 32 + wl, lcp_i + warp * lcpScratchInts(kmax) * 32 + wl, n, kmax);
+  v.init(lcp_d + (size_t)w * lcpScratchDoubles(kmax), lcp_i + (size_t)w * lcpScratchInts(kmax), n, kmax, 1);
   const bool ok = pgsSolve(v, opt);
   const int slot = ctrl[8 * w + 1];
   for (int i = 0; i < n; i++) ans_x[((size_t)w * kPgsRequests + slot) * kmax + i] = v.x(i);
@@ -217,27 +219,30 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
   ctrl[8 * w + 2] = 0;
 }
 
-// the contact stage of World::step, one world per thread
-__global__ void __launch_bounds__(64)
+// The contact stage of World::step, one world per WARP: the 32 lanes run the same scalar code on the same data (loads are
+// broadcasts, stores coincide), so a batch of N worlds keeps N warps in flight instead of N / 32. The stage is a chain of
+// dependent memory accesses (pivoting solvers, Householder sweeps); what bounds it is how many of those chains the SMs
+// can overlap, not arithmetic, and the redundant lanes cost nothing that matters (FP64 issue stays far below the pipe).
+__global__ void __launch_bounds__(128)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
           int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
-          int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+          int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok, long long* __restrict__ prof) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= N) return;
   if (ctrl && ctrl[8 * w]) return;  // this world's stage has been committed by an earlier pass
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
-  ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L};
+  ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L, prof};
   const ContactSnapLayout KL{L.nd, L.cmax, L.kmax};
-  const size_t warp = w >> 5, lane = w & 31;
-  double* ld = lcp_d + warp * lcpScratchDoubles(L.kmax) * 32 + lane;
-  int* li = lcp_i + warp * lcpScratchInts(L.kmax) * 32 + lane;
+  double* ld = lcp_d + (size_t)w * lcpScratchDoubles(L.kmax);
+  int* li = lcp_i + (size_t)w * lcpScratchInts(L.kmax);
   int nc = n_cache[w];
   PgsDefer df{ctrl ? ctrl[8 * w + 1] : 0, 0, L.kmax, 0, kPgsRequests, ctrl ? ctrl[8 * w + 4] : 0, ans_x + (size_t)w * kPgsRequests * L.kmax,
               ans_ok + (size_t)w * kPgsRequests};
   ContactStepOut o = contactStage(sn, cw, ld, li, qd, qd, layout, N, w, lcp_cache + (size_t)w * L.kmax, &nc, pgs,
                                   keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr,
-                                  ctrl ? &df : nullptr);
+                                  ctrl ? &df : nullptr, 1);
+  __syncwarp();  // every lane has read the control words before any lane rewrites them
   if (o.pending) { ctrl[8 * w + 2] = df.pendingN; ctrl[8 * w + 4] = df.resumeKind; return; }  // the reduced problem waits in this world's LCP view
   if (ctrl) { ctrl[8 * w] = 1; ctrl[8 * w + 2] = 0; }
   n_cache[w] = nc;
@@ -255,15 +260,14 @@ k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL,
                    const int* __restrict__ keep_i, const double* __restrict__ gqn, const double* __restrict__ gqdn, double* __restrict__ gq,
                    double* __restrict__ gqd, double* __restrict__ gtau, double* __restrict__ work_d, int* __restrict__ work_i,
                    double* __restrict__ lcp_d, int* __restrict__ lcp_i, Limits lim, int* __restrict__ status) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one world per warp, lanes redundant (see k_contact)
   if (w >= N) return;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactBwdWork bw{work_d + (size_t)w * BL.doubles(), work_i + (size_t)w * BL.ints(), BL};
-  const size_t warp = w >> 5, lane = w & 31;
-  double* ld = lcp_d + warp * lcpScratchDoubles(BL.kmax) * 32 + lane;
-  int* li = lcp_i + warp * lcpScratchInts(BL.kmax) * 32 + lane;
+  double* ld = lcp_d + (size_t)w * lcpScratchDoubles(BL.kmax);
+  int* li = lcp_i + (size_t)w * lcpScratchInts(BL.kmax);
   const int st = contactBackwardWorld<NB>(sn, KL, keep_d + (size_t)w * KL.doubles(), keep_i + (size_t)w * KL.ints(), bw, ld, li, gqn, gqdn, gq,
-                                          gqd, gtau, layout, N, w);
+                                          gqd, gtau, layout, N, w, 1);
   if (status) status[w] = st;
   if (c_topo.has_limits) {
     const int n = c_topo.nd;
@@ -306,13 +310,25 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, 
   ContactBwdLayout BL{nb, nd, kmax};
   *wd = (size_t)N * (L.doubles() > BL.doubles() ? L.doubles() : BL.doubles());
   *wi = (size_t)N * (L.ints() > BL.ints() ? L.ints() : BL.ints());
-  *ld = warps * lcpScratchDoubles(kmax) * 32;
-  *li = warps * lcpScratchInts(kmax) * 32;
+  *ld = warps * lcpScratchDoubles(kmax) * 32;  // one slice per world (contact kernels: stride 1; the rounding keeps the
+  *li = warps * lcpScratchInts(kmax) * 32;     // interleaved layout of k_lcp_solve's callers valid too)
+}
+// DDB_CONTACT_PROFILE=1: clock64 ticks summed over worlds per section of the contact stage (see ContactWork::mark)
+static long long* contactProfileBuffer() {
+  static long long* buf = nullptr;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("DDB_CONTACT_PROFILE");
+    if (e && e[0] == '1' && cudaMalloc(&buf, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(buf, 0, 16 * sizeof(long long));
+    else buf = nullptr;
+  }
+  return buf;
 }
 template <int CAP>
 static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
                                  const PgsOptions& pgs) {
-  const size_t bytes = (size_t)(CAP * (CAP + 1) + 4 * CAP) * sizeof(double) + 2 * CAP * sizeof(int);
+  const size_t bytes = (size_t)((CAP * (CAP + 1)) / 2 + 6 * CAP) * sizeof(double) + CAP * sizeof(int);
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(k_pgs_warp<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
@@ -357,12 +373,12 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
   if (e != cudaSuccess) return e;
   // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
   for (int pass = 0; pass <= kPgsRequests; pass++) {
-    k_contact<<<(N + 63) / 64, 64, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
-                                           keep_d, keep_i, ctrl, ans_x, ans_ok);
+    k_contact<<<(int)(((size_t)N * 32 + 127) / 128), 128, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+                                           keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (pass == kPgsRequests) break;
-    // size classes by shared-memory footprint: 6, 4, 3, 2 and 1 resident worlds per SM. The classes touch disjoint worlds,
+    // size classes by shared-memory footprint: 10, 7, 5, 3 and 1 resident worlds per SM. The classes touch disjoint worlds,
     // so they run side by side on helper streams (fork / join on events): the small problems fill the SMs while the few
     // worlds that need all 10000 sweeps finish.
     PgsStreams* ps = pgsStreams();
@@ -379,10 +395,18 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
     if (kmax > 64 && (e = onHelper(1, [&](cudaStream_t hs) { return launchPgsWarp<76>(hs, N, kmax, 64, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
     if (kmax > 76 && (e = onHelper(2, [&](cudaStream_t hs) { return launchPgsWarp<92>(hs, N, kmax, 76, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
     if (kmax > 92 && (e = onHelper(3, [&](cudaStream_t hs) { return launchPgsWarp<116>(hs, N, kmax, 92, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (kmax > 116 && (e = onHelper(4, [&](cudaStream_t hs) { return launchPgsWarp<160>(hs, N, kmax, 116, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 76) + (kmax > 92) + (kmax > 116) + (kmax > 160);
+    if (kmax > 116 && (e = onHelper(4, [&](cudaStream_t hs) { return launchPgsWarp<192>(hs, N, kmax, 116, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 76) + (kmax > 92) + (kmax > 116) + (kmax > 192);
   }
   return cudaSuccess;
+}
+int contactProfileRead(long long* out16) {
+  long long* b = contactProfileBuffer();
+  if (!b) return 0;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out16, b, 16 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(b, 0, 16 * sizeof(long long));
+  return 1;
 }
 void contactKeepSizes(int N, int nd, int cmax, int kmax, size_t* kd, size_t* ki) {
   ContactSnapLayout KL{nd, cmax, kmax};
@@ -396,7 +420,7 @@ cudaError_t contactBackwardLaunch(cudaStream_t s, int N, int nb, int nd, int cma
   ContactBwdLayout BL{nb, nd, kmax};
   Limits lim{lim6, lim6 ? lim6 + nd : nullptr, lim6 ? lim6 + 2 * nd : nullptr, lim6 ? lim6 + 3 * nd : nullptr, lim6 ? lim6 + 4 * nd : nullptr,
              lim6 ? lim6 + 5 * nd : nullptr};
-  const int grid = (N + 63) / 64;
+  const int grid = (int)(((size_t)N * 32 + 63) / 64);
 #define DDB_CB(NBV) k_contact_backward<NBV><<<grid, 64, 0, s>>>(N, layout, KL, BL, snap, keep_d, keep_i, gqn, gqdn, gq, gqd, gtau, work_d, work_i, lcp_d, lcp_i, lim, status)
   if (nb <= 8) DDB_CB(8);
   else if (nb <= 16) DDB_CB(16);

@@ -177,6 +177,11 @@ int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t
 int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims,
                            double* A, double* b, double* lo, double* hi, double* x, int32_t* findex);
 
+/* With DDB_CONTACT_PROFILE=1 in the environment: clock ticks per section of the contact stage summed over worlds since the
+   last call (host array [16]: collision+constraints, assembly, guessSolution, short-circuit, Dantzig, reduce for PGS,
+   post-PGS, commit). DDB_ERR_STATE when profiling is off. */
+int ddb_contact_profile_host(int64_t* ticks_out);
+
 /* Statistics of the last ddb_forward: Gauss-Seidel sweeps the PGS fallback spent per world (host array [N]). */
 int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out);
 

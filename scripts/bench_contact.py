@@ -37,6 +37,11 @@ e1.record(); torch.cuda.synchronize()
 ms_bwd = e0.elapsed_time(e1) / steps
 counts = np.zeros((N, 4), dtype=np.int32)
 world._lib.ddb_contact_debug_host(world._h, counts.ctypes.data_as(C.c_void_p), -1, None, None, None, None, None, None, None, None, None)
+prof = np.zeros(16, dtype=np.int64)
+if world._lib.ddb_contact_profile_host(prof.ctypes.data_as(C.c_void_p)) == 0:
+    names = ["collide+constraints", "assembly", "guess", "short_circuit", "dantzig", "reduce_for_pgs", "post_pgs", "commit"]
+    tot = max(int(prof[:8].sum()), 1)
+    print("contact stage profile (share of thread time):", {k: round(float(v) / tot, 3) for k, v in zip(names, prof[:8])}, file=sys.stderr)
 sw = np.zeros(N, dtype=np.int32)
 world._lib.ddb_contact_pgs_sweeps_host(world._h, sw.ctypes.data_as(C.c_void_p))
 rows = counts[:, 1]
