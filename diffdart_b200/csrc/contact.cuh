@@ -48,10 +48,23 @@ struct ContactLayout {
   __host__ __device__ size_t oBias() const { return oImp() + (size_t)nb * 6; }        // [nb][6]
   __host__ __device__ size_t oDelV() const { return oBias() + (size_t)nb * 6; }       // [nb][6]
   __host__ __device__ size_t oU() const { return oDelV() + (size_t)nb * 6; }          // [nb] + dqd [nd]
-  __host__ __device__ size_t doubles() const { return oU() + (size_t)nb + nd; }
+  __host__ __device__ size_t padDoubles() const { return (size_t)19 * nb + nd; }      // imp, bias, delV [nb][6] each, u [nb], dqd [nd]
+  __host__ __device__ size_t oLanePads() const { return oU() + (size_t)nb + nd; }     // 32 private copies for the impulse tests run side by side
+  __host__ __device__ size_t doubles() const { return oLanePads() + 32 * padDoubles(); }
   // ints: bodyA bodyB dim type group [cmax each], findex keep mapTo [kmax each], misc
   __host__ __device__ size_t oSaved() const { return (size_t)5 * cmax + (size_t)7 * kmax + 8; }  // loop state kept across a deferred PGS solve
   __host__ __device__ size_t ints() const { return oSaved() + 8 + DDB_MAX_BODIES; }
+};
+
+// scratch of one impulse-dynamics pass: constraint impulses, bias impulses, body velocity changes, joint impulses, dqd
+struct ImpulsePad {
+  double* p;
+  int nb;
+  DDB_LCP_DI double* imp(int body) const { return p + (size_t)body * 6; }
+  DDB_LCP_DI double* bias(int body) const { return p + (size_t)(nb + body) * 6; }
+  DDB_LCP_DI double* delV(int body) const { return p + (size_t)(2 * nb + body) * 6; }
+  DDB_LCP_DI double* u() const { return p + (size_t)18 * nb; }
+  DDB_LCP_DI double* dqd() const { return p + (size_t)19 * nb; }
 };
 
 struct ContactWork {
@@ -84,6 +97,8 @@ struct ContactWork {
   DDB_LCP_DI double* imp(int body) const { return d + L.oImp() + (size_t)body * 6; }
   DDB_LCP_DI double* bias(int body) const { return d + L.oBias() + (size_t)body * 6; }
   DDB_LCP_DI double* delV(int body) const { return d + L.oDelV() + (size_t)body * 6; }
+  DDB_LCP_DI ImpulsePad pad0() const { return ImpulsePad{d + L.oImp(), L.nb}; }  // the world's own pad (imp/bias/delV/u/dqd above)
+  DDB_LCP_DI ImpulsePad lanePad(int lane) const { return ImpulsePad{d + L.oLanePads() + (size_t)lane * L.padDoubles(), L.nb}; }
   DDB_LCP_DI double* u() const { return d + L.oU(); }
   DDB_LCP_DI double* dqd() const { return d + L.oU() + L.nb; }
   DDB_LCP_DI int* bodyA() const { return i; }
@@ -119,13 +134,18 @@ struct ContactSnapLayout {
   __host__ __device__ size_t ints() const { return oCounts() + 2; }
 };
 
+DDB_LCP_DI void coopSyncWarp(int coopN) {
+#ifdef __CUDA_ARCH__
+  if (coopN > 1) __syncwarp();
+#endif
+}
 DDB_LCP_DI SV ldSV6(const double* p) { return sv(mk(p[0], p[1], p[2]), mk(p[3], p[4], p[5])); }
 DDB_LCP_DI void stSV6(double* p, SV a) { p[0] = a.w.x; p[1] = a.w.y; p[2] = a.w.z; p[3] = a.v.x; p[4] = a.v.y; p[5] = a.v.z; }
 DDB_LCP_DI double dotSV6(const double* n, const double* v) { return n[0] * v[0] + n[1] * v[1] + n[2] * v[2] + n[3] * v[3] + n[4] * v[4] + n[5] * v[5]; }
 
 // Impulse dynamics: body-frame constraint impulses in cw.imp -> dqd (per dof) and body velocity changes (cw.delV).
 // (Skeleton::updateBiasImpulse + updateVelocityChange; GenericJoint.hpp:2135-2152,2266-2272,2365-2377)
-DDB_LCP_DI void impulsePass(const Snap& sn, const ContactWork& cw, int nb) {
+DDB_LCP_DI void impulsePass(const Snap& sn, const ImpulsePad& cw, int nb) {
   for (int i = 0; i < nb; i++) {
     const double* im = cw.imp(i);
     double* bi = cw.bias(i);
@@ -238,6 +258,10 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
   const int nb = c_topo.nb, nd = c_topo.nd;
   const ContactTopo& ct = c_ctopo;
   ContactStepOut out = {0, 0, 0, 0, 0};
+  int coopLane = 0, coopN = 1;  // one world per warp (lcpStride == 1): independent pieces of work are spread over the lanes
+#ifdef __CUDA_ARCH__
+  if (lcpStride == 1) { coopLane = threadIdx.x & 31; coopN = 32; }
+#endif
   long long tmark = 0;
 #ifdef __CUDA_ARCH__
   if (cw.prof) tmark = clock64();
@@ -439,29 +463,48 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
         if (restitutionVel > 1e-1) { if (restitutionVel > bouncing) { bouncing = restitutionVel; if (bouncing > 1e+2) bouncing = 1e+2; } }
       }
       b[o] += bouncing;
-      for (int k = 0; k < dim; k++) {
-        for (int i = 0; i < nb; i++) for (int z = 0; z < 6; z++) cw.imp(i)[z] = 0.0;
-        if (ra) for (int z = 0; z < 6; z++) cw.imp(a)[z] += cw.NA(c, k)[z];
-        if (rb) for (int z = 0; z < 6; z++) cw.imp(bb)[z] += cw.NB(c, k)[z];
-        for (int z = 0; z < nd; z++) cw.dqd()[z] = 0.0;
-        impulsePass(sn, cw, nb);
+      for (int k = 0; k < dim; k++) cw.keep()[o + k] = c * 4 + k;  // row -> (constraint, direction) for the tests below
+    }
+    // the impulse tests are independent: with one warp per world every lane runs one on its private pad
+    coopSyncWarp(coopN);
+    {
+      const ImpulsePad pad = coopN > 1 ? cw.lanePad(coopLane) : cw.pad0();
+      for (int base = 0; base < n; base += coopN) {
+        const int t = base + coopLane;
+        if (t >= n) continue;
+        const int c = cw.keep()[t] >> 2, k = cw.keep()[t] & 3, o = offs[c];
+        const int a = cw.bodyA()[c], bb = cw.bodyB()[c];
+        const bool ra = ct.shape[a].reactive != 0, rb = ct.shape[bb].reactive != 0;
+        for (int i = 0; i < nb; i++) for (int z = 0; z < 6; z++) pad.imp(i)[z] = 0.0;
+        if (ra) for (int z = 0; z < 6; z++) pad.imp(a)[z] += cw.NA(c, k)[z];
+        if (rb) for (int z = 0; z < 6; z++) pad.imp(bb)[z] += cw.NB(c, k)[z];
+        for (int z = 0; z < nd; z++) pad.dqd()[z] = 0.0;
+        impulsePass(sn, pad, nb);
         double* mcol = cw.massed(rowsTotal + o + k);
-        for (int z = 0; z < nd; z++) mcol[z] = cw.dqd()[z];
+        for (int z = 0; z < nd; z++) mcol[z] = pad.dqd()[z];
         for (int m = c; m < nc; m++) {
           if (cw.groupOf()[m] != g) continue;
           const int am = cw.bodyA()[m], bm = cw.bodyB()[m];
           for (int l = 0; l < cw.dim()[m]; l++) {
             double v = 0.0;
-            if (ct.shape[am].reactive) v += dotSV6(cw.NA(m, l), cw.delV(am));
-            if (ct.shape[bm].reactive) v += dotSV6(cw.NB(m, l), cw.delV(bm));
+            if (ct.shape[am].reactive) v += dotSV6(cw.NA(m, l), pad.delV(am));
+            if (ct.shape[bm].reactive) v += dotSV6(cw.NB(m, l), pad.delV(bm));
             A[(size_t)(o + k) * n + offs[m] + l] = v;
           }
         }
+      }
+      coopSyncWarp(coopN);
+      // the blocks below the diagonal mirror rows computed by other tests
+      for (int base = 0; base < n; base += coopN) {
+        const int t = base + coopLane;
+        if (t >= n) continue;
+        const int c = cw.keep()[t] >> 2, k = cw.keep()[t] & 3, o = offs[c];
         for (int m = 0; m < c; m++) {
           if (cw.groupOf()[m] != g) continue;
           for (int l = 0; l < cw.dim()[m]; l++) A[(size_t)(o + k) * n + offs[m] + l] = A[(size_t)(offs[m] + l) * n + o + k];
         }
       }
+      coopSyncWarp(coopN);
     }
     // ---- squared column norms of A (aColNormGradientBackup) ----
     for (int j = 0; j < n; j++) { double sacc = 0.0; for (int r = 0; r < n; r++) sacc += A[(size_t)r * n + j] * A[(size_t)r * n + j]; cw.colnorm()[j] = sacc; }
@@ -486,11 +529,13 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       if (frictionless) {
         for (int k = 0; k < n; k++) { if (findex[k] == -1) { mapTo[k] = nr; keep[nr++] = k; } else mapTo[k] = -1; }
         v.init(lcpD, lcpI, nr, ct.kmax, lcpStride);
+        coopSync(v);
         for (int a = 0; a < nr; a++) {
-          for (int c2 = 0; c2 < nr; c2++) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]];
+          for (int c2 = v.lane; c2 < nr; c2 += v.nl) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]];
           v.b(a) = b[keep[a]]; v.lo(a) = lo[keep[a]]; v.hi(a) = hi[keep[a]]; v.findex(a) = -1; v.x(a) = x0[keep[a]];
           v.tmp(a) = 1.0;  // column scale (read by the warp-cooperative PGS)
         }
+        coopSync(v);
         return nr;
       }
       nr = n;
@@ -500,26 +545,31 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       for (;;) {
         bool found = false;
         for (int a = 0; a < nr - 1 && !found; a++) {
-          for (int c2 = a + 1; c2 < nr; c2++) {
-            if (v.C(a) != v.C(c2) || hi[keep[a]] != hi[keep[c2]] || lo[keep[a]] != lo[keep[c2]]) continue;
-            if (!(fabs(b[keep[a]] - b[keep[c2]]) < 1e-4)) continue;
-            double sq = 0.0;
-            for (int k = 0; k < nr; k++) {
-              double dl = A[(size_t)keep[k] * n + keep[a]] * v.d(a) - A[(size_t)keep[k] * n + keep[c2]] * v.d(c2);
-              sq += dl * dl;
+          // the first c2 > a whose column duplicates column a; with one warp per world the candidates are tested 32 at a time
+          for (int base = a + 1; base < nr && !found; base += v.nl) {
+            const int c2 = base + v.lane;
+            bool dup = false;
+            if (c2 < nr && v.C(a) == v.C(c2) && hi[keep[a]] == hi[keep[c2]] && lo[keep[a]] == lo[keep[c2]] &&
+                fabs(b[keep[a]] - b[keep[c2]]) < 1e-4) {
+              double sq = 0.0;
+              for (int k = 0; k < nr; k++) {
+                double dl = A[(size_t)keep[k] * n + keep[a]] * v.d(a) - A[(size_t)keep[k] * n + keep[c2]] * v.d(c2);
+                sq += dl * dl;
+              }
+              dup = sq < 1e-4;
             }
-            if (!(sq < 1e-4)) continue;
-            // mergeLCPColumns(a, c2)
+            const int first = coopFirstTrue(v, dup, base);
+            if (first < 0) continue;
+            // mergeLCPColumns(a, first)
             v.d(a) = v.d(a) * 2.0;
             for (int k = 0; k < nr; k++) {
               int f = v.C(k);
-              if (f == c2) v.C(k) = a; else if (f > c2) v.C(k) = f - 1;
+              if (f == first) v.C(k) = a; else if (f > first) v.C(k) = f - 1;
             }
-            for (int k = c2; k < nr - 1; k++) { keep[k] = keep[k + 1]; v.d(k) = v.d(k + 1); v.C(k) = v.C(k + 1); }
-            for (int k = 0; k < n; k++) { if (mapTo[k] == c2) mapTo[k] = a; else if (mapTo[k] > c2) mapTo[k]--; }
+            for (int k = first; k < nr - 1; k++) { keep[k] = keep[k + 1]; v.d(k) = v.d(k + 1); v.C(k) = v.C(k + 1); }
+            for (int k = 0; k < n; k++) { if (mapTo[k] == first) mapTo[k] = a; else if (mapTo[k] > first) mapTo[k]--; }
             nr--;
             found = true;
-            break;
           }
         }
         if (!found) break;
@@ -527,10 +577,12 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       // materialise the reduced problem in the view (scale/fidx are read before their slots are overwritten)
       v.n = nr; v.nskip = dpad(nr);
       for (int a = 0; a < nr; a++) { v.tmp(a) = v.d(a); v.findex(a) = v.C(a); }
+      coopSync(v);
       for (int a = 0; a < nr; a++) {
-        for (int c2 = 0; c2 < nr; c2++) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]] * v.tmp(c2);
+        for (int c2 = v.lane; c2 < nr; c2 += v.nl) v.Araw(a, c2) = A[(size_t)keep[a] * n + keep[c2]] * v.tmp(c2);
         v.b(a) = b[keep[a]]; v.lo(a) = lo[keep[a]]; v.hi(a) = hi[keep[a]]; v.x(a) = x0[keep[a]];
       }
+      coopSync(v);
       return nr;
     };
     auto mapOut = [&]() { for (int k = 0; k < n; k++) x[k] = mapTo[k] >= 0 ? v.x(mapTo[k]) : 0.0; };
@@ -744,7 +796,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     }
   }
   for (int z = 0; z < nd; z++) cw.dqd()[z] = 0.0;
-  if (any) impulsePass(sn, cw, nb);
+  if (any) impulsePass(sn, cw.pad0(), nb);
   for (int z = 0; z < nd; z++) {
     const size_t ix = vidx(layout, N, nd, w, z);
     qd_out[ix] = qd_pre_in[ix] + cw.dqd()[z];

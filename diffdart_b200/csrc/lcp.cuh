@@ -612,6 +612,16 @@ DDB_LCP_DI void coopSync(const LcpView& v) {
   if (v.nl > 1) __syncwarp();
 #endif
 }
+// base + (first lane whose flag is set), -1 when none: the candidates base .. base + nl - 1 are tested side by side
+DDB_LCP_DI int coopFirstTrue(const LcpView& v, bool flag, int base) {
+#ifdef __CUDA_ARCH__
+  if (v.nl > 1) {
+    const unsigned m = __ballot_sync(0xffffffffu, flag);
+    return m ? base + __ffs(m) - 1 : -1;
+  }
+#endif
+  return flag ? base : -1;
+}
 // first index of the largest value over j in [from, n), evaluated by the whole warp (or by the one thread)
 template <class F>
 DDB_LCP_DI int coopArgMaxFirst(const LcpView& v, int from, int n, F val) {
