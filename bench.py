@@ -110,6 +110,76 @@ def cpu_world_steps(n_worlds, threads, reps=1):
     return n_worlds * reps / dt, dt
 
 
+# ---- second workload (reported next to the headline, not instead of it): BASELINE configs[2], contact-rich box stacking ----
+CONTACT_WORLDS = 16384
+CONTACT_WORKLOAD = ("box_stack: 16384 worlds per GPU of 5 FreeJoint boxes 1x1x0.5 stacked on a welded floor (BASELINE configs[2], SURVEY 8(d) C3: "
+                    "1 mm overlap per interface, x,y ~ U(-0.05,0.05), yaw ~ U(-0.1,0.1), qd ~ U(-0.1,0.1), mu = 1, e = 0); step = forwardPass with the "
+                    "contact solve (collision, LCP assembly, short-circuit / Dantzig / PGS chain, classification) + backward through the contact solution")
+
+
+def box_stack_states(N, seed, n=5):
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 6 * n))
+    for i in range(n):
+        q[:, 6 * i + 2] = rng.uniform(-0.1, 0.1, N)
+        q[:, 6 * i + 3] = rng.uniform(-0.05, 0.05, N)
+        q[:, 6 * i + 4] = rng.uniform(-0.05, 0.05, N)
+        q[:, 6 * i + 5] = 0.25 + 0.5 * i - 1e-3 * (i + 1)
+    qd = rng.uniform(-0.1, 0.1, (N, 6 * n))
+    return q, qd, np.zeros((N, 6 * n))
+
+
+def contact_bench(local_rank, rank, steps=4, warmup=3):
+    """Forward + backward of the box-stacking batch through the Python host layer; returns (ms per step, tier histogram, rows)."""
+    import torch
+
+    from diffdart_b200 import skeletons
+    from diffdart_b200.world import BatchedWorld, LossGradient, forwardPass
+
+    N = CONTACT_WORLDS
+    q, qd, tau = box_stack_states(N, 7 + rank)
+    dev = torch.device("cuda", local_rank)
+    world = BatchedWorld(skeletons.create_box_stack(5), N, device=local_rank)
+    cu = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    world.setPositions(cu(q)); world.setVelocities(cu(qd))
+    tq = cu(tau)
+    g = torch.randn(N, q.shape[1], dtype=torch.float64, device=dev)
+    nxt, this = LossGradient(), LossGradient()
+    nxt.lossWrtPosition, nxt.lossWrtVelocity = g, g.clone()
+
+    def step():
+        world.setForces(tq)
+        snap = forwardPass(world)  # the rollout advances: every step sees new contacts and the solver's cached solution
+        snap.backprop(world, this, nxt)
+
+    for _ in range(warmup):  # SURVEY 8(d): warm-up steps populate the LCP cache
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    status = world.last_solver_status.cpu().numpy()
+    tiers = {str(int(k)): int(v) for k, v in zip(*np.unique(status, return_counts=True))}
+    return e0.elapsed_time(e1) / steps, tiers, N
+
+
+def contact_cpu_baseline(n_worlds=6):
+    """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
+    from diffdart_b200 import skeletons
+    from oracle.oracle import OracleWorld
+
+    o = OracleWorld(skeletons.create_box_stack(5))
+    q, qd, tau = box_stack_states(n_worlds, 7)
+    t0 = time.perf_counter()
+    for w in range(n_worlds):
+        o.contact_jacobians(q[w], qd[w], tau[w], mode="reference")
+    dt = time.perf_counter() - t0
+    return n_worlds / dt, dt
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -245,11 +315,15 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    # ---- second workload: contact-rich box stacking (its own handle) ----
+    contact_ms, contact_tiers = float("nan"), {}
+    if not args.no_contact:
+        contact_ms, contact_tiers, _ = contact_bench(local_rank, rank)
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -280,6 +354,18 @@ def run_ours(args):
                               "achieved": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12,
                               "frac": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12 / peak.value},
         }
+        if not args.no_contact:
+            line["contact_rich"] = {"workload": CONTACT_WORKLOAD, "value": world_size * CONTACT_WORLDS / (contact_ms * 1e-3), "unit": UNIT,
+                                    "ms_per_step": contact_ms, "worlds_per_gpu": CONTACT_WORLDS, "scaling": "weak",
+                                    "solver_tier_mask_hist_rank0": contact_tiers,
+                                    "tier_bits": "1 short-circuit through the cached solution, 2 Dantzig, 4 PGS, 8 friction dropped"}
+            if world_size == 1 and not args.no_cpu_baseline:
+                try:
+                    cv, cs = contact_cpu_baseline()
+                    line["contact_rich"]["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "port",
+                                                            "sample": "6 worlds, forwardPass + the reference's Jacobian recipe on one core (%.1f s)" % cs}
+                except Exception as exc:  # the oracle's reference libraries travel prebuilt; report instead of failing the headline
+                    line["contact_rich"]["cpu_baseline"] = {"unavailable": str(exc)[:200]}
         if world_size == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v, secs = cpu_world_steps(N_WORLDS, threads)
@@ -303,6 +389,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-contact", action="store_true", help="skip the second (contact-rich) workload")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 2000:
