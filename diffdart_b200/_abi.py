@@ -146,4 +146,5 @@ EXPORTED_SYMBOLS = [
     "ddb_num_dofs", "ddb_forward", "ddb_backward", "ddb_jacobians", "ddb_inv_mass_matrix", "ddb_snapshot_select",
     "ddb_snapshot_current", "ddb_snapshot_reserve", "ddb_forward_host", "ddb_backward_host", "ddb_jacobians_host",
     "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs", "ddb_contact_capacity", "ddb_contact_debug_host",
+    "ddb_contact_pgs_sweeps_host", "ddb_contact_profile_host",
 ]
