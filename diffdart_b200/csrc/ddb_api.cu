@@ -21,28 +21,50 @@ namespace {
 #ifndef DDB_BLOCK
 #define DDB_BLOCK 64
 #endif
+#ifndef DDB_BLOCK_BWD
+#define DDB_BLOCK_BWD 32  // measured: the forward wants two warps per CTA marching together (instruction cache), the backward CTAs of one warp
+#endif
 #ifndef DDB_MINB
 #define DDB_MINB 1
 #endif
-constexpr int kBlock = DDB_BLOCK;
-constexpr int kMinB = DDB_MINB;
+#ifndef DDB_MINB_FWD
+#define DDB_MINB_FWD DDB_MINB
+#endif
+#ifndef DDB_MINB_BWD
+#define DDB_MINB_BWD DDB_MINB
+#endif
+constexpr int kBlock = DDB_BLOCK, kBlockB = DDB_BLOCK_BWD;
+constexpr int kMinB = DDB_MINB, kMinBF = DDB_MINB_FWD, kMinBB = DDB_MINB_BWD;
 
 struct KernelTable {
-  void (*fwd)(cudaStream_t, int, const double*, const double*, const double*, double*, double*, double*);
-  void (*bwd)(cudaStream_t, int, double*, const double*, const double*, double*, double*, double*, Limits);
+  // forward / backward over the worlds [w0, w1) of the batch
+  void (*fwd)(cudaStream_t, int, int, int, const double*, const double*, const double*, double*, double*, double*);
+  void (*bwd)(cudaStream_t, int, int, int, double*, const double*, const double*, const double*, const double*, double*, double*, double*, Limits);
   void (*jac)(cudaStream_t, int, double*, double*, double*, double*, double*, double*);
   void (*minv)(cudaStream_t, int, double*, double*);
 };
 
 template <int NB, bool CHAIN>
 struct Launch {
-  static int grid(int N) { return (N + kBlock - 1) / kBlock; }
-  static void fwd(cudaStream_t s, int N, const double* q, const double* qd, const double* tau, double* qn, double* qdn, double* snap) {
-    k_forward<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, q, qd, tau, qn, qdn, snap);
+  static int grid(int N, int block = kBlock) { return (N + block - 1) / block; }
+  static void fwd(cudaStream_t s, int N, int w0, int w1, const double* q, const double* qd, const double* tau, double* qn, double* qdn, double* snap) {
+    k_forward<NB, CHAIN, kBlock, kMinBF><<<grid(w1 - w0), kBlock, 0, s>>>(N, w0, w1, q, qd, tau, qn, qdn, snap);
   }
-  static void bwd(cudaStream_t s, int N, double* snap, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
-                  Limits lim) {
-    k_backward<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, gqn, gqdn, gq, gqd, gtau, lim);
+  static void bwd(cudaStream_t s, int N, int w0, int w1, double* snap, const double* gqn, const double* gqdn, const double* gqnAdd,
+                  const double* gqdnAdd, double* gq, double* gqd, double* gtau, Limits lim) {
+    // chains stage their snapshot rows in shared memory (dynamics.cuh, StageGeom): 16 bytes x slots per world
+    const size_t smem = (CHAIN && DDB_BWD_STAGE) ? StageGeom<NB, kBlockB>::kBytes : 0;
+    if (smem) {
+      static bool once[64] = {false};  // per instantiation and device: the attribute belongs to the function in that context
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!once[dev & 63]) {
+        cudaFuncSetAttribute(k_backward<NB, CHAIN, kBlockB, kMinBB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_backward<NB, CHAIN, kBlockB, kMinBB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        once[dev & 63] = true;
+      }
+    }
+    k_backward<NB, CHAIN, kBlockB, kMinBB><<<grid(w1 - w0, kBlockB), kBlockB, smem, s>>>(N, w0, w1, snap, gqn, gqdn, gqnAdd, gqdnAdd, gq, gqd, gtau, lim);
   }
   static void jac(cudaStream_t s, int N, double* snap, double* pp, double* pv, double* vp, double* vv, double* fv) {
     k_jacobians<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, pp, pv, vp, vv, fv);
@@ -105,6 +127,12 @@ struct ddb_handle {
   int* bwdStatus = nullptr;
   int *pgsCtrl = nullptr, *pgsOk = nullptr;  // deferred PGS solves (contact_api.h)
   double* pgsX = nullptr;
+  // lanes: internal streams on which chunks of worlds run side by side (rollouts, host-buffer path)
+  std::vector<cudaStream_t> lanes;
+  std::vector<cudaEvent_t> laneDone;
+  cudaEvent_t forkEv = nullptr;
+  int nLanes = 2;
+  double* gradRun = nullptr;  // 4 x [N*n]: running loss gradient of a rollout's reverse sweep (ping-pong)
   // host-buffer path
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
@@ -157,7 +185,44 @@ int allocKeep(ddb_handle* h, int slot) {
   return DDB_OK;
 }
 
-size_t snapDoubles(const ddb_handle* h) { return snapDoublesPerWorld(h->topo.snapPairs, h->n, h->topo.has_limits != 0) * (size_t)h->N; }
+// ---- lanes ----
+// Worlds are independent, so a batch can run as chunks on separate streams. Inside one kernel that changes nothing; across
+// the kernels of a rollout (or the copies of the host-buffer path) it does: a 65536-world kernel lasts ~30 us, of which the
+// ramp-up and the drain of its last, partly filled wave leave many SMs idle; with chunks on lanes the next kernel of one chunk
+// fills the SMs the other chunk is draining, and host<->device copies of one chunk hide behind the kernels of another.
+int ensureLanes(ddb_handle* h) {
+  if ((int)h->lanes.size() >= h->nLanes && h->forkEv) return DDB_OK;
+  if (!h->forkEv) DDB_CUDA(h, cudaEventCreateWithFlags(&h->forkEv, cudaEventDisableTiming));
+  while ((int)h->lanes.size() < h->nLanes) {
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev = nullptr;
+    DDB_CUDA(h, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    DDB_CUDA(h, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    h->lanes.push_back(st);
+    h->laneDone.push_back(ev);
+  }
+  return DDB_OK;
+}
+// chunk c of K: [w0, w1), boundaries on multiples of 64 worlds (CTA size and snapshot tile)
+void chunkRange(int N, int K, int c, int* w0, int* w1) {
+  const int per = ((N + K - 1) / K + 63) / 64 * 64;
+  *w0 = std::min(N, c * per);
+  *w1 = std::min(N, (c + 1) * per);
+}
+int forkLanes(ddb_handle* h, cudaStream_t s, int K) {
+  DDB_CUDA(h, cudaEventRecord(h->forkEv, s));
+  for (int c = 0; c < K; c++) DDB_CUDA(h, cudaStreamWaitEvent(h->lanes[c], h->forkEv, 0));
+  return DDB_OK;
+}
+int joinLanes(ddb_handle* h, cudaStream_t s, int K) {
+  for (int c = 0; c < K; c++) {
+    DDB_CUDA(h, cudaEventRecord(h->laneDone[c], h->lanes[c]));
+    DDB_CUDA(h, cudaStreamWaitEvent(s, h->laneDone[c], 0));
+  }
+  return DDB_OK;
+}
+
+size_t snapDoubles(const ddb_handle* h) { return snapDoublesPerWorld(h->topo.snapPairs, h->n, h->topo.has_limits != 0) * snapWorldsPadded(h->N); }
 
 }  // namespace
 
@@ -303,6 +368,10 @@ int ddb_destroy(ddb_handle* h) {
   for (double* p : h->keepD) if (p) cudaFree(p);
   for (int* p : h->keepI) if (p) cudaFree(p);
   if (h->hstream) cudaStreamDestroy(h->hstream);
+  for (cudaStream_t l : h->lanes) cudaStreamDestroy(l);
+  for (cudaEvent_t e : h->laneDone) cudaEventDestroy(e);
+  if (h->forkEv) cudaEventDestroy(h->forkEv);
+  if (h->gradRun) cudaFree(h->gradRun);
   delete h;
   return DDB_OK;
 }
@@ -340,7 +409,7 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
   cudaStream_t s = (cudaStream_t)stream;
   int rc = enter(h, s);
   if (rc) return rc;
-  h->k.fwd(s, h->N, q, qd, tau, qn, qdn, h->slots[h->cur]);
+  h->k.fwd(s, h->N, 0, h->N, q, qd, tau, qn, qdn, h->slots[h->cur]);
   DDB_CUDA(h, cudaGetLastError());
   h->launches++;
   if (h->hasContacts) {
@@ -421,7 +490,7 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
     h->launches++;
     return DDB_OK;
   }
-  h->k.bwd(s, h->N, h->slots[h->cur], gqn, gqdn, gq, gqd, gtau, h->lim);
+  h->k.bwd(s, h->N, 0, h->N, h->slots[h->cur], gqn, gqdn, nullptr, nullptr, gq, gqd, gtau, h->lim);
   DDB_CUDA(h, cudaGetLastError());
   h->launches++;
   return DDB_OK;
@@ -477,6 +546,108 @@ int ddb_inv_mass_matrix(ddb_handle* h, void* stream, double* minv) {
   return DDB_OK;
 }
 
+int ddb_set_lanes(ddb_handle* h, int32_t n_lanes) {
+  if (!h || n_lanes < 1 || n_lanes > 16) return fail(h, DDB_ERR_INVALID, "ddb_set_lanes: 1..16 lanes");
+  h->nLanes = n_lanes;
+  return DDB_OK;
+}
+
+__global__ void k_add_inplace(size_t n, double* __restrict__ a, const double* __restrict__ b) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] += b[i];
+}
+
+// T steps from (q0, qd0) under tau[t], every step retained in snapshot slot t (SingleShot::getSnapshots, SingleShot.cpp:719-760).
+int ddb_rollout_forward(ddb_handle* h, void* stream, int32_t T, const double* q0, const double* qd0, const double* tau, double* q_seq,
+                        double* qd_seq) {
+  if (!h || T < 1 || !q0 || !qd0 || !tau || !q_seq || !qd_seq) return fail(h, DDB_ERR_INVALID, "ddb_rollout_forward: bad argument");
+  int rc = ddb_snapshot_reserve(h, T, nullptr);
+  if (rc) return rc;
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t V = (size_t)h->N * h->n;
+  if (h->hasContacts) {
+    // the contact stage works on the whole batch (deferred PGS passes, shared scratch): steps run one after the other on s
+    for (int t = 0; t < T; t++) {
+      h->cur = t;
+      rc = ddb_forward(h, stream, t ? q_seq + (t - 1) * V : q0, t ? qd_seq + (t - 1) * V : qd0, tau + t * V, q_seq + t * V, qd_seq + t * V, nullptr,
+                       nullptr, nullptr, nullptr);
+      if (rc) return rc;
+    }
+    return DDB_OK;
+  }
+  rc = enter(h, s);
+  if (rc) return rc;
+  rc = ensureLanes(h);
+  if (rc) return rc;
+  const int K = h->nLanes;
+  rc = forkLanes(h, s, K);
+  if (rc) return rc;
+  for (int t = 0; t < T; t++)
+    for (int c = 0; c < K; c++) {
+      int w0, w1;
+      chunkRange(h->N, K, c, &w0, &w1);
+      if (w0 >= w1) continue;
+      h->k.fwd(h->lanes[c], h->N, w0, w1, t ? q_seq + (t - 1) * V : q0, t ? qd_seq + (t - 1) * V : qd0, tau + t * V, q_seq + t * V, qd_seq + t * V,
+               h->slots[t]);
+      h->launches++;
+    }
+  DDB_CUDA(h, cudaGetLastError());
+  for (int t = 0; t < T; t++) h->slotValid[t] = 1;
+  h->cur = T - 1;
+  return joinLanes(h, s, K);
+}
+
+// Reverse sweep over the retained steps (SingleShot::backpropGradientWrt, SingleShot.cpp:650-700): g_q_seq[t], g_qd_seq[t] are the
+// loss gradients w.r.t. the state after step t; what the later steps pulled back is added before step t is pulled back.
+int ddb_rollout_backward(ddb_handle* h, void* stream, int32_t T, const double* g_q_seq, const double* g_qd_seq, double* g_q0, double* g_qd0,
+                         double* g_tau) {
+  if (!h || T < 1 || !g_q_seq || !g_qd_seq || !g_q0 || !g_qd0 || !g_tau) return fail(h, DDB_ERR_INVALID, "ddb_rollout_backward: bad argument");
+  if ((int)h->slots.size() < T) return fail(h, DDB_ERR_STATE, "ddb_rollout_backward: fewer retained steps than T");
+  for (int t = 0; t < T; t++)
+    if (!h->slotValid[t]) return fail(h, DDB_ERR_STATE, "ddb_rollout_backward: a step of the rollout has no retained forward pass");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t V = (size_t)h->N * h->n;
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  if (!h->gradRun) DDB_CUDA(h, cudaMalloc(&h->gradRun, 4 * V * sizeof(double)));
+  double* run[2][2] = {{h->gradRun, h->gradRun + V}, {h->gradRun + 2 * V, h->gradRun + 3 * V}};
+  if (h->hasContacts) {
+    for (int t = T - 1; t >= 0; t--) {
+      const int o = t & 1;  // step t writes run[o], reads run[1-o] (written by step t+1)
+      double* oq = t ? run[o][0] : g_q0;
+      double* oqd = t ? run[o][1] : g_qd0;
+      const double *iq = g_q_seq + t * V, *iqd = g_qd_seq + t * V;
+      if (t < T - 1) {
+        // incoming = direct loss on state t + what steps > t pulled back
+        k_add_inplace<<<296, 256, 0, s>>>(V, run[1 - o][0], iq);
+        k_add_inplace<<<296, 256, 0, s>>>(V, run[1 - o][1], iqd);
+        iq = run[1 - o][0]; iqd = run[1 - o][1];
+      }
+      h->cur = t;
+      int rc = ddb_backward(h, stream, iq, iqd, oq, oqd, g_tau + t * V);
+      if (rc) return rc;
+    }
+    return DDB_OK;
+  }
+  int rc = enter(h, s);
+  if (rc) return rc;
+  rc = ensureLanes(h);
+  if (rc) return rc;
+  const int K = h->nLanes;
+  rc = forkLanes(h, s, K);
+  if (rc) return rc;
+  for (int t = T - 1; t >= 0; t--)
+    for (int c = 0; c < K; c++) {
+      int w0, w1;
+      chunkRange(h->N, K, c, &w0, &w1);
+      if (w0 >= w1) continue;
+      const int o = t & 1;
+      h->k.bwd(h->lanes[c], h->N, w0, w1, h->slots[t], g_q_seq + t * V, g_qd_seq + t * V, t < T - 1 ? run[1 - o][0] : nullptr,
+               t < T - 1 ? run[1 - o][1] : nullptr, t ? run[o][0] : g_q0, t ? run[o][1] : g_qd0, g_tau + t * V, h->lim);
+      h->launches++;
+    }
+  DDB_CUDA(h, cudaGetLastError());
+  return joinLanes(h, s, K);
+}
+
 // ---- host-buffer entry points (the e2e path): H2D, kernel, D2H on the handle's own stream ----
 static int ensureStage(ddb_handle* h, size_t doubles) {
   if (h->stageDoubles >= doubles) return DDB_OK;
@@ -488,6 +659,10 @@ static int ensureStage(ddb_handle* h, size_t doubles) {
   return DDB_OK;
 }
 
+// Contact-free handles with world-major vectors run the call as chunks on the lanes: the copy-in of chunk c+1, the kernel of chunk c
+// and the copy-out of chunk c-1 overlap (PCIe is full duplex), so the call costs about max(bytes in, bytes out) / link rate.
+static bool hostChunked(const ddb_handle* h) { return !h->hasContacts && h->topo.layout == DDB_LAYOUT_WORLD_MAJOR && h->N >= 4096; }
+
 int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const double* tau, double* qn, double* qdn) {
   if (!h || !q || !qd || !tau || !qn || !qdn) return fail(h, DDB_ERR_INVALID, "ddb_forward_host: null pointer");
   cudaSetDevice(h->device);
@@ -495,6 +670,35 @@ int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const dou
   int rc = ensureStage(h, 8 * V);
   if (rc) return rc;
   double* d = h->stage;
+  if (hostChunked(h)) {
+    rc = enter(h, h->hstream);
+    if (rc) return rc;
+    rc = ensureLanes(h);
+    if (rc) return rc;
+    const int L = (int)h->lanes.size(), K = 4 * L;  // chunks, dealt round-robin to the lanes
+    rc = forkLanes(h, h->hstream, L);
+    if (rc) return rc;
+    for (int c = 0; c < K; c++) {
+      int w0, w1;
+      chunkRange(h->N, K, c, &w0, &w1);
+      if (w0 >= w1) continue;
+      cudaStream_t st = h->lanes[c % L];
+      const size_t o = (size_t)w0 * h->n, b = (size_t)(w1 - w0) * h->n * sizeof(double);
+      DDB_CUDA(h, cudaMemcpyAsync(d + o, q + o, b, cudaMemcpyHostToDevice, st));
+      DDB_CUDA(h, cudaMemcpyAsync(d + V + o, qd + o, b, cudaMemcpyHostToDevice, st));
+      DDB_CUDA(h, cudaMemcpyAsync(d + 2 * V + o, tau + o, b, cudaMemcpyHostToDevice, st));
+      h->k.fwd(st, h->N, w0, w1, d, d + V, d + 2 * V, d + 3 * V, d + 4 * V, h->slots[h->cur]);
+      h->launches++;
+      DDB_CUDA(h, cudaMemcpyAsync(qn + o, d + 3 * V + o, b, cudaMemcpyDeviceToHost, st));
+      DDB_CUDA(h, cudaMemcpyAsync(qdn + o, d + 4 * V + o, b, cudaMemcpyDeviceToHost, st));
+    }
+    DDB_CUDA(h, cudaGetLastError());
+    h->slotValid[h->cur] = 1;
+    rc = joinLanes(h, h->hstream, L);
+    if (rc) return rc;
+    DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
+    return DDB_OK;
+  }
   DDB_CUDA(h, cudaMemcpyAsync(d, q, B, cudaMemcpyHostToDevice, h->hstream));
   DDB_CUDA(h, cudaMemcpyAsync(d + V, qd, B, cudaMemcpyHostToDevice, h->hstream));
   DDB_CUDA(h, cudaMemcpyAsync(d + 2 * V, tau, B, cudaMemcpyHostToDevice, h->hstream));
@@ -513,6 +717,35 @@ int ddb_backward_host(ddb_handle* h, const double* gqn, const double* gqdn, doub
   int rc = ensureStage(h, 8 * V);
   if (rc) return rc;
   double* d = h->stage;
+  if (hostChunked(h)) {
+    if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward_host: no forward pass retained in the current snapshot slot");
+    rc = enter(h, h->hstream);
+    if (rc) return rc;
+    rc = ensureLanes(h);
+    if (rc) return rc;
+    const int L = (int)h->lanes.size(), K = 4 * L;
+    rc = forkLanes(h, h->hstream, L);
+    if (rc) return rc;
+    for (int c = 0; c < K; c++) {
+      int w0, w1;
+      chunkRange(h->N, K, c, &w0, &w1);
+      if (w0 >= w1) continue;
+      cudaStream_t st = h->lanes[c % L];
+      const size_t o = (size_t)w0 * h->n, b = (size_t)(w1 - w0) * h->n * sizeof(double);
+      DDB_CUDA(h, cudaMemcpyAsync(d + o, gqn + o, b, cudaMemcpyHostToDevice, st));
+      DDB_CUDA(h, cudaMemcpyAsync(d + V + o, gqdn + o, b, cudaMemcpyHostToDevice, st));
+      h->k.bwd(st, h->N, w0, w1, h->slots[h->cur], d, d + V, nullptr, nullptr, d + 2 * V, d + 3 * V, d + 4 * V, h->lim);
+      h->launches++;
+      DDB_CUDA(h, cudaMemcpyAsync(gq + o, d + 2 * V + o, b, cudaMemcpyDeviceToHost, st));
+      DDB_CUDA(h, cudaMemcpyAsync(gqd + o, d + 3 * V + o, b, cudaMemcpyDeviceToHost, st));
+      DDB_CUDA(h, cudaMemcpyAsync(gtau + o, d + 4 * V + o, b, cudaMemcpyDeviceToHost, st));
+    }
+    DDB_CUDA(h, cudaGetLastError());
+    rc = joinLanes(h, h->hstream, L);
+    if (rc) return rc;
+    DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
+    return DDB_OK;
+  }
   DDB_CUDA(h, cudaMemcpyAsync(d, gqn, B, cudaMemcpyHostToDevice, h->hstream));
   DDB_CUDA(h, cudaMemcpyAsync(d + V, gqdn, B, cudaMemcpyHostToDevice, h->hstream));
   rc = ddb_backward(h, h->hstream, d, d + V, d + 2 * V, d + 3 * V, d + 4 * V);

@@ -57,8 +57,8 @@ DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {
 
 // ---------------------------------------------------------------------------------------------
 // Snapshot of one step, written by the forward kernel and read by the backward / Jacobian
-// kernels. 18 double2 per body, pair-major ([pair][world]) so that every access of a warp is
-// one contiguous 512-byte segment:
+// kernels. 18 double2 per body; every access of a warp is one contiguous 512-byte segment
+// (layout of the pairs: struct Snap below):
 //   pairs 0-5  relative transform T_i (R row-major, p)      pairs 12-14 AIS_i = IA_i S_i
 //   pairs 6-8  spatial velocity V_i                         pair  15    (psi_i, qd_i)
 //   pairs 9-11 spatial acceleration A_i                     pairs 16-17 (G_i = R_world^T g, qdd_i)
@@ -70,13 +70,32 @@ DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {
 constexpr int kSnapPairs = 18;
 constexpr int kSnapPairsFree = 59;  // + pairs 56-58: the joint coordinates q (6)
 
+#ifndef DDB_SNAP_TILED
+#define DDB_SNAP_TILED 1
+#endif
 struct Snap {
-  double2* base;  // [nb*18][N]
+  double2* base;
   int N, w;
-  DDB_DI void st(int body, int k, double a, double b) const { base[(size_t)(c_topo.b[body].snapOff + k) * N + w] = make_double2(a, b); }
-  DDB_DI double2 ld(int body, int k) const { return __ldg(base + (size_t)(c_topo.b[body].snapOff + k) * N + w); }
+#if DDB_SNAP_TILED
+  // tile-major: [world / 32][pair][world % 32]. The pairs of 32 consecutive worlds form one contiguous block (46 KB for the
+  // 5-link chain), so a warp streams through one DRAM-page-friendly region instead of touching one 512-byte piece in each
+  // of 90 rows that lie N*16 bytes apart
+  DDB_DI size_t rowStride() const { return 32; }
+  DDB_DI size_t origin() const { return ((size_t)(w >> 5) * c_topo.snapPairs) * 32 + (w & 31); }
+#else
+  // pair-major: [pair][world]
+  DDB_DI size_t rowStride() const { return (size_t)N; }
+  DDB_DI size_t origin() const { return (size_t)w; }
+#endif
+  DDB_DI size_t at(int body, int k) const { return origin() + (size_t)(c_topo.b[body].snapOff + k) * rowStride(); }
+  DDB_DI void st(int body, int k, double a, double b) const { base[at(body, k)] = make_double2(a, b); }
+  DDB_DI double2 ld(int body, int k) const { return __ldg(base + at(body, k)); }
   // plain (coherent) load: for values written earlier by the same thread in the same kernel
-  DDB_DI double2 ldc(int body, int k) const { return base[(size_t)(c_topo.b[body].snapOff + k) * N + w]; }
+  DDB_DI double2 ldc(int body, int k) const { return base[at(body, k)]; }
+  DDB_DI void beginUp(int) const {}
+  DDB_DI void endDown(int) const {}
+  DDB_DI void beginAdj(int) const {}
+  DDB_DI void endAdj(int) const {}
   DDB_DI void stSV(int body, int k, SV x) const {
     st(body, k, x.w.x, x.w.y); st(body, k + 1, x.w.z, x.v.x); st(body, k + 2, x.v.y, x.v.z);
   }
@@ -97,6 +116,138 @@ struct Snap {
   }
 };
 
+// ---------------------------------------------------------------------------------------------
+// Staged snapshot for the chain backward kernel. One world per thread at 255 registers leaves two warps per scheduler,
+// and every sweep of the backward is a chain of dependent snapshot reads: issued as plain loads they stall the warp for
+// an HBM round trip per body. Instead each thread copies its own rows global -> shared with cp.async (LDGSTS: no
+// registers, no scoreboard), far ahead of their use, and the sweeps read shared memory.
+//   phase A (M^-1 solve, up + down): rows T (0-5), AIS (12-14), (psi, qd) (15) of every body, 10 slots per body, all
+//     requested at kernel entry, one commit group per body in the order the up sweep consumes them.
+//   phase B (ID adjoint, leaves -> root): rows 0-11, 15-17 of one body, 15 slots, two buffers; the request for body j-2
+//     is issued when body j is done. The buffers reuse the slots of phase A bodies the down sweep has finished with
+//     (chains of >= 3 bodies), so a thread owns max(10 NB, 30) slots of 16 bytes: 800 B for the 5-link chain,
+//     8 CTAs of 32 worlds per SM.
+// A thread only reads slots it filled itself: cp.async.wait_group orders them, no CTA barrier is needed.
+// ---------------------------------------------------------------------------------------------
+#ifdef DDB_HOST_EMULATION  // the g++ build of these headers used by the CPU tests never takes the staged path
+template <int N> DDB_DI void cpAsyncWait() {}
+DDB_DI void cpAsyncCommit() {}
+DDB_DI void cpAsync16(unsigned, const void*) {}
+DDB_DI unsigned sharedAddr(const void*) { return 0; }
+#else
+template <int N> DDB_DI void cpAsyncWait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+DDB_DI void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+DDB_DI void cpAsync16(unsigned dst, const void* src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory"); }
+DDB_DI unsigned sharedAddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+#endif
+DDB_DI void cpAsyncWaitDyn(int n) {  // n is a compile-time constant after unrolling
+  switch (n) {
+    case 0: cpAsyncWait<0>(); break;
+    case 1: cpAsyncWait<1>(); break;
+    case 2: cpAsyncWait<2>(); break;
+    case 3: cpAsyncWait<3>(); break;
+    case 4: cpAsyncWait<4>(); break;
+    case 5: cpAsyncWait<5>(); break;
+    case 6: cpAsyncWait<6>(); break;
+    default: cpAsyncWait<7>(); break;
+  }
+}
+
+template <int NB, int BLOCK>
+struct StageGeom {
+  static constexpr int kRowsA = 10, kRowsB = 15;
+  static constexpr int kBufBase = NB >= 3 ? 0 : kRowsA * NB;  // short chains: the phase B buffers sit behind phase A
+  static constexpr int kSlots = (kRowsA * NB > kBufBase + 2 * kRowsB) ? kRowsA * NB : kBufBase + 2 * kRowsB;
+  static constexpr size_t kBytes = (size_t)kSlots * BLOCK * sizeof(double2);
+};
+
+template <class D>
+struct SnapReaders {  // T / spatial-vector reads on top of D::ld(body, pair)
+  DDB_DI const D& self() const { return *static_cast<const D*>(this); }
+  DDB_DI SV ldSV(int body, int k) const {
+    double2 a = self().ld(body, k), b = self().ld(body, k + 1), c = self().ld(body, k + 2);
+    return sv(mk(a.x, a.y, b.x), mk(b.y, c.x, c.y));
+  }
+  DDB_DI Xf ldT(int body) const {
+    double2 a = self().ld(body, 0), b = self().ld(body, 1), c = self().ld(body, 2), d = self().ld(body, 3), e = self().ld(body, 4),
+            f = self().ld(body, 5);
+    Xf t;
+    t.R.m[0] = a.x; t.R.m[1] = a.y; t.R.m[2] = b.x; t.R.m[3] = b.y; t.R.m[4] = c.x; t.R.m[5] = c.y;
+    t.R.m[6] = d.x; t.R.m[7] = d.y; t.R.m[8] = e.x; t.p = mk(e.y, f.x, f.y);
+    return t;
+  }
+};
+
+template <int NB, int BLOCK>
+struct StageBase {
+  typedef StageGeom<NB, BLOCK> G;
+  const double2* g;   // this world's column of the snapshot in global memory
+  size_t strideN;     // pairs between consecutive rows
+  double2* sm;        // this thread's column of the CTA's staging area
+  unsigned smAddr;
+  DDB_DI void init(const Snap& sn, double2* smemBase) {
+    g = sn.base + sn.origin();
+    strideN = sn.rowStride();
+    sm = smemBase + threadIdx.x;
+    smAddr = sharedAddr(sm);
+  }
+  DDB_DI void copyRow(int slot, int body, int k) const {
+    const double2* src = g + (size_t)(c_topo.b[body].snapOff + k) * strideN;
+    cpAsync16(smAddr + (unsigned)(slot * BLOCK * (int)sizeof(double2)), src);
+  }
+  DDB_DI static int slotA(int body, int k) { return G::kRowsA * body + (k < 6 ? k : k - 6); }
+  DDB_DI static int bufOf(int body) { return G::kBufBase + ((NB - 1 - body) & 1) * G::kRowsB; }
+  DDB_DI static int slotB(int body, int k) { return bufOf(body) + (k < 12 ? k : k - 3); }
+  DDB_DI void requestA(int body) const {
+#pragma unroll
+    for (int k = 0; k < 6; k++) copyRow(slotA(body, k), body, k);
+#pragma unroll
+    for (int k = 12; k < 16; k++) copyRow(slotA(body, k), body, k);
+    cpAsyncCommit();
+  }
+  DDB_DI void requestB(int body) const {  // body < 0: an empty group keeps the group count uniform
+    if (body >= 0) {
+#pragma unroll
+      for (int k = 0; k < 12; k++) copyRow(slotB(body, k), body, k);
+#pragma unroll
+      for (int k = 15; k < 18; k++) copyRow(slotB(body, k), body, k);
+    }
+    cpAsyncCommit();
+  }
+};
+
+// phase A accessor: handed to solveInvMass
+template <int NB, int BLOCK>
+struct StageA : StageBase<NB, BLOCK>, SnapReaders<StageA<NB, BLOCK>> {
+  typedef StageBase<NB, BLOCK> B;
+  DDB_DI void start() const {
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--) B::requestA(i);
+    if (NB < 3) { B::requestB(NB - 1); B::requestB(NB - 2); }
+  }
+  DDB_DI double2 ld(int body, int k) const { return B::sm[B::slotA(body, k) * BLOCK]; }
+  // groups were committed for bodies NB-1 ... 0: body i has landed when at most i groups are pending
+  DDB_DI void beginUp(int i) const { cpAsyncWaitDyn(NB >= 3 ? i : i + 2); }  // (short chains: + the two phase B groups)
+  // the down sweep is done with bodies 0..i: their slots become the phase B buffers
+  DDB_DI void endDown(int i) const {
+    if (NB >= 3 && i == 1) B::requestB(NB - 1);
+    if (NB >= 3 && i == 2) B::requestB(NB - 2);
+  }
+  DDB_DI void beginAdj(int) const {}
+  DDB_DI void endAdj(int) const {}
+};
+// phase B accessor: handed to idAdjoint
+template <int NB, int BLOCK>
+struct StageB : StageBase<NB, BLOCK>, SnapReaders<StageB<NB, BLOCK>> {
+  typedef StageBase<NB, BLOCK> B;
+  DDB_DI double2 ld(int body, int k) const { return B::sm[B::slotB(body, k) * BLOCK]; }
+  DDB_DI void beginUp(int) const {}
+  DDB_DI void endDown(int) const {}
+  // exactly one younger group (body i-1's, possibly empty) may still be in flight
+  DDB_DI void beginAdj(int) const { cpAsyncWait<1>(); }
+  DDB_DI void endAdj(int i) const { B::requestB(i - 2); }
+};
+
 template <int NB, bool CHAIN>
 struct Tree {
   DDB_DI static int parentOf(int i) { return CHAIN ? i - 1 : c_topo.b[i].parent; }
@@ -104,10 +255,12 @@ struct Tree {
   DDB_DI static bool hasDof(int i) { return CHAIN ? true : c_topo.b[i].type != DDB_JOINT_WELD; }
 };
 
-DDB_DI Xf jointTransform(const DevBody& b, double qi) {
-  double c = 0.0, s = 0.0;
+DDB_DI void jointCS(const DevBody& b, double qi, double& c, double& s) {
+  c = 0.0; s = 0.0;
   if (b.type == DDB_JOINT_REVOLUTE) sincos(qi, &s, &c);
   else if (b.type == DDB_JOINT_PRISMATIC) c = qi;
+}
+DDB_DI Xf jointTransformCS(const DevBody& b, double c, double s) {
   Xf t;
 #pragma unroll
   for (int k = 0; k < 9; k++) t.R.m[k] = fma(s, b.N2[k], fma(c, b.N1[k], b.N0[k]));
@@ -115,6 +268,11 @@ DDB_DI Xf jointTransform(const DevBody& b, double qi) {
   t.p.y = fma(s, b.P2[1], fma(c, b.P1[1], b.P0[1]));
   t.p.z = fma(s, b.P2[2], fma(c, b.P1[2], b.P0[2]));
   return t;
+}
+DDB_DI Xf jointTransform(const DevBody& b, double qi) {
+  double c, s;
+  jointCS(b, qi, c, s);
+  return jointTransformCS(b, c, s);
 }
 
 // ---- FreeJoint pieces (generic instantiation only) ----
@@ -219,13 +377,15 @@ DDB_DI void ld6c(const Snap& sn, int body, int k, double* x) {
   double2 a = sn.ldc(body, k), b = sn.ldc(body, k + 1), c = sn.ldc(body, k + 2);
   x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
-DDB_DI void ld6(const Snap& sn, int body, int k, double* x) {
+template <class SN>
+DDB_DI void ld6(const SN& sn, int body, int k, double* x) {
   double2 a = sn.ld(body, k), b = sn.ld(body, k + 1), c = sn.ld(body, k + 2);
   x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
 }
 DDB_DI void st36(const Snap& sn, int body, int k, const double* m) { for (int i = 0; i < 18; i++) sn.st(body, k + i, m[2 * i], m[2 * i + 1]); }
 DDB_DI void ld36c(const Snap& sn, int body, int k, double* m) { for (int i = 0; i < 18; i++) { double2 a = sn.ldc(body, k + i); m[2 * i] = a.x; m[2 * i + 1] = a.y; } }
-DDB_DI void ld36(const Snap& sn, int body, int k, double* m) { for (int i = 0; i < 18; i++) { double2 a = sn.ld(body, k + i); m[2 * i] = a.x; m[2 * i + 1] = a.y; } }
+template <class SN>
+DDB_DI void ld36(const SN& sn, int body, int k, double* m) { for (int i = 0; i < 18; i++) { double2 a = sn.ld(body, k + i); m[2 * i] = a.x; m[2 * i + 1] = a.y; } }
 DDB_DI SV sv6(const double* x) { return sv(mk(x[0], x[1], x[2]), mk(x[3], x[4], x[5])); }
 
 // ---------------------------------------------------------------------------------------------
@@ -244,12 +404,27 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     V3 G[NB];
     ABI IA[NB];
     double psi[NB], u[NB], qdv[NB];
+    double cth[NB], sth[NB];
   } ws;
   Xf* T = ws.T;
   SV *V = ws.V, *AIS = ws.AIS, *A = ws.A, *bias = ws.bias;
   V3* G = ws.G;
   ABI* IA = ws.IA;
   double *psi = ws.psi, *u = ws.u, *qdv = ws.qdv;
+#ifndef DDB_FWD_KEEP_T
+  // chains: the 12 numbers of T_i are rebuilt from (cos q_i, sin q_i) in sweeps 2 and 3 (24 DFMA with constant-bank
+  // operands each time) instead of occupying 24 registers per body across the whole kernel
+  double *cth = ws.cth, *sth = ws.sth;
+  // (the empty asm makes the value opaque: otherwise the compiler merges the rebuild with the first evaluation and keeps T live)
+#ifdef DDB_HOST_EMULATION
+  auto opaque = [](double x) { return x; };
+#else
+  auto opaque = [](double x) { asm volatile("" : "+d"(x)); return x; };
+#endif
+  auto Tof = [&](int i) -> Xf { return CHAIN ? jointTransformCS(c_topo.b[i], opaque(cth[i]), opaque(sth[i])) : T[i]; };
+#else
+  auto Tof = [&](int i) -> Xf { return T[i]; };
+#endif
   auto down1 = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
@@ -267,16 +442,29 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
       st6(sn, i, 56, q6);
     } else {
       const double qi = d ? qOf(TS::dofOf(i)) : 0.0, qdi = d ? qdOf(TS::dofOf(i)) : 0.0;
+#ifndef DDB_FWD_KEEP_T
+      if (CHAIN) { jointCS(b, qi, cth[i], sth[i]); t = jointTransformCS(b, cth[i], sth[i]); }
+      else t = jointTransform(b, qi);
+#else
       t = jointTransform(b, qi);
+#endif
       qdv[i] = qdi;
       Sq = qdi * b.S;
     }
+#ifndef DDB_FWD_KEEP_T
+    if (!CHAIN) T[i] = t;
+#else
     T[i] = t;
+#endif
     V[i] = (p >= 0) ? AdInvT(t, V[p]) + Sq : Sq;
     V3 gp = (p >= 0) ? G[p] : mk(c_topo.g[0], c_topo.g[1], c_topo.g[2]);
     G[i] = mulT(t.R, gp);
     sn.stT(i, t);
     sn.stSV(i, 6, V[i]);
+  };
+  // rigid-body terms of sweep 2, set right before it (they stay off the register file during sweep 1)
+  auto rigid = [&](int i) {
+    const DevBody& b = c_topo.b[i];
     IA[i] = toABI(b.I);
     // bias = -dad(V, I V) - I [0; R_w^T g]   (BodyNode.cpp:1692-1702)
     SV IV = mul(b.I, V[i]);
@@ -315,7 +503,7 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
         double av[6];
         for (int a = 0; a < 6; a++) { double acc = 0.0; for (int k = 0; k < 6; k++) acc += AISm[a * 6 + k] * pu[k]; av[a] = acc; }
         SV beta = bias[i] + mul(IA[i], eta) + sv6(av);
-        bias[p] = bias[p] + dAdInvT(T[i], beta);
+        bias[p] = bias[p] + dAdInvT(Tof(i), beta);
       }
       return;
     }
@@ -336,16 +524,22 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     if (p >= 0) {
       // beta = bias + IA (eta + S psi u)   (GenericJoint.hpp:2049-2074)
       SV beta = bias[i] + mul(IA[i], eta) + (ps * ui) * ais;
-      bias[p] = bias[p] + dAdInvT(T[i], beta);
+      const Xf Ti = Tof(i);
+      bias[p] = bias[p] + dAdInvT(Ti, beta);
       ABI Pi = IA[i];
       if (TS::hasDof(i)) rank1Downdate(Pi, ais, ps);
-      addTransformedInertia(IA[p], T[i], Pi);
+      addTransformedInertia(IA[p], Ti, Pi);
     }
   };
   auto down2 = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
-    SV Ap = (p >= 0) ? AdInvT(T[i], A[p]) : svzero();
+    const Xf Ti = Tof(i);
+    SV Ap = (p >= 0) ? AdInvT(Ti, A[p]) : svzero();
+#ifdef DDB_FWD_REBUILD_V
+    // chains: V_i is rebuilt along the sweep from (T_i, V_parent) instead of staying live since sweep 1
+    if (CHAIN) V[i] = (p >= 0) ? AdInvT(Ti, V[p]) + qdv[i] * b.S : qdv[i] * b.S;
+#endif
     if (!CHAIN && b.type == DDB_JOINT_FREE) {
       double AISm[36], psi6[36], u6[6], qd6[6], r6[6], acc6[6];
       ld36c(sn, i, 12, AISm); ld36c(sn, i, 30, psi6); ld6c(sn, i, 51, u6); ld6c(sn, i, 48, qd6);
@@ -372,14 +566,24 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
   };
   if (CHAIN) {
 #pragma unroll
+#ifdef DDB_FWD_RIGID_LATE
     for (int i = 0; i < NB; i++) down1(i);
 #pragma unroll
+    for (int i = NB - 1; i >= 0; i--) {
+      if (i == NB - 1) rigid(i);
+      if (i > 0) rigid(i - 1);  // the parent's own terms, set just before its child adds to them
+      up(i);
+    }
+#else
+    for (int i = 0; i < NB; i++) { down1(i); rigid(i); }
+#pragma unroll
     for (int i = NB - 1; i >= 0; i--) up(i);
+#endif
 #pragma unroll
     for (int i = 0; i < NB; i++) down2(i);
   } else {
 #pragma unroll 1
-    for (int i = 0; i < nb; i++) down1(i);
+    for (int i = 0; i < nb; i++) { down1(i); rigid(i); }
 #pragma unroll 1
     for (int i = nb - 1; i >= 0; i--) up(i);
 #pragma unroll 1
@@ -405,8 +609,8 @@ struct BwdScratch {
   V3 pG[NB];
 };
 
-template <int NB, bool CHAIN, class LamF, class MuF>
-DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws, MuF muFree) {
+template <int NB, bool CHAIN, class SN, class LamF, class MuF>
+DDB_DI void solveInvMass(const SN& sn, int nb, LamF lamOf, BwdScratch<NB>& ws, MuF muFree) {
   typedef Tree<NB, CHAIN> TS;
   SV* c = ws.c;
   double* a = ws.a;
@@ -416,6 +620,7 @@ DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws,
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
+    sn.beginUp(i);
     if (!CHAIN && b.type == DDB_JOINT_FREE) {
       // a (6) = lambda - S^T c; the parent receives X^T (c + AIS psi a); a is kept in c[i] (no longer needed as bias)
       double a6[6], sc[6];
@@ -465,6 +670,7 @@ DDB_DI void solveInvMass(const Snap& sn, int nb, LamF lamOf, BwdScratch<NB>& ws,
     }
     mu[i] = m;
     U[i] = Up + m * b.S;
+    sn.endDown(i);
   };
   if (CHAIN) {
 #pragma unroll
@@ -547,8 +753,8 @@ DDB_DI void freeJointPosJacobians(const double* q6, const double* qd6, double dt
 // MODE 0: velocities / accelerations / gravity of the step as retained in the snapshot.
 // MODE 1: the same with dA[i] added to every body acceleration (the joint accelerations of the contact impulses).
 // MODE 2: V = 0, G = 0, A = dA: Phi = mu^T M(q) a, the bilinear mass-matrix form used for d(M^-1 w)/dq terms.
-template <int NB, bool CHAIN, int MODE, class Out, class OutFree>
-DDB_DI void idAdjointEx(const Snap& sn, int nb, BwdScratch<NB>& ws, const SV* dA, Out out, OutFree outFree) {
+template <int NB, bool CHAIN, int MODE, class SN, class Out, class OutFree>
+DDB_DI void idAdjointEx(const SN& sn, int nb, BwdScratch<NB>& ws, const SV* dA, Out out, OutFree outFree) {
   typedef Tree<NB, CHAIN> TS;
   auto accOf = [&](int i) { return MODE == 2 ? dA[i] : (MODE == 1 ? sn.ldSV(i, 9) + dA[i] : sn.ldSV(i, 9)); };
   auto velOf = [&](int i) { return MODE == 2 ? svzero() : sn.ldSV(i, 6); };
@@ -560,6 +766,7 @@ DDB_DI void idAdjointEx(const Snap& sn, int nb, BwdScratch<NB>& ws, const SV* dA
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
     const int p = TS::parentOf(i);
+    sn.beginAdj(i);
     const SV Vi = velOf(i), Ai = accOf(i);
     if (!CHAIN && b.type == DDB_JOINT_FREE) {
       double qd6[6] = {0, 0, 0, 0, 0, 0};
@@ -634,6 +841,7 @@ DDB_DI void idAdjointEx(const Snap& sn, int nb, BwdScratch<NB>& ws, const SV* dA
       pV[p] = pV[p] + dAdInvT(t, Vb);
       pG[p] = pG[p] + mul(t.R, Gb);
     }
+    sn.endAdj(i);
   };
   if (CHAIN) {
 #pragma unroll
@@ -648,9 +856,9 @@ DDB_DI void idAdjointEx(const Snap& sn, int nb, BwdScratch<NB>& ws, const SV* dA
   }
 }
 
-template <int NB, bool CHAIN, class Out, class OutFree>
-DDB_DI void idAdjoint(const Snap& sn, int nb, BwdScratch<NB>& ws, Out out, OutFree outFree) {
-  idAdjointEx<NB, CHAIN, 0>(sn, nb, ws, nullptr, out, outFree);
+template <int NB, bool CHAIN, class SN, class Out, class OutFree>
+DDB_DI void idAdjoint(const SN& sn, int nb, BwdScratch<NB>& ws, Out out, OutFree outFree) {
+  idAdjointEx<NB, CHAIN, 0, SN>(sn, nb, ws, nullptr, out, outFree);
 }
 
 // U_i = J_i mu: body twists under joint rates mu (fills ws.U / ws.mu exactly as solveInvMass leaves them)

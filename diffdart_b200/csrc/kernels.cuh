@@ -8,6 +8,10 @@
 #pragma once
 #include "dynamics.cuh"
 
+#ifndef DDB_BWD_STAGE
+#define DDB_BWD_STAGE 1  // 0: the chain backward reads the snapshot with plain loads (A/B timing only)
+#endif
+
 namespace ddb {
 
 struct Limits {  // device arrays of length n (valid only when c_topo.has_limits)
@@ -16,15 +20,18 @@ struct Limits {  // device arrays of length n (valid only when c_topo.has_limits
 
 // doubles per world in one snapshot slot
 __host__ __device__ inline size_t snapDoublesPerWorld(int snapPairs, int n, bool limits) { return (size_t)2 * snapPairs + (limits ? 3 * n : 0); }
+// worlds are padded to whole tiles of 32 in the snapshot
+__host__ __device__ inline size_t snapWorldsPadded(int N) { return ((size_t)N + 31) / 32 * 32; }
 // the clip section (q, qd, tau as [3n][N]) sits behind the per-body pairs
-DDB_DI double* clipSection(double* snap, int /*nb*/, int N) { return snap + (size_t)2 * c_topo.snapPairs * N; }
+DDB_DI double* clipSection(double* snap, int /*nb*/, int N) { return snap + (size_t)2 * c_topo.snapPairs * snapWorldsPadded(N); }
 
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_forward(int N, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
+k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
           double* __restrict__ qn, double* __restrict__ qdn, double* __restrict__ snap) {
-  const int w = blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= N) return;
+  // worlds [w0, w1) of the N-world batch (the host splits a batch into chunks that run on different streams)
+  const int w = w0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
@@ -99,18 +106,39 @@ DDB_DI double clipGrad(double g, double x, double lo, double hi) {
 
 template <int NB, bool CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
-k_backward(int N, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
+k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
+           const double* __restrict__ gqnAdd, const double* __restrict__ gqdnAdd,
            double* __restrict__ gq, double* __restrict__ gqd, double* __restrict__ gtau, Limits lim) {
-  const int w = blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= N) return;
+  // loss gradient w.r.t. the post-step state = gqn (+ gqnAdd), gqdn (+ gqdnAdd): in a rollout the second term is what the
+  // later steps pulled back (SingleShot.cpp:667-670); NULL otherwise
+  const int w = w0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
+  // chains read the snapshot through the cp.async staging area (dynamics.cuh, StageA / StageB); trees read global memory
+#ifdef DDB_HOST_EMULATION
+  double2* ddb_stage = nullptr;
+#else
+  extern __shared__ double2 ddb_stage[];
+#endif
+  StageA<NB, BLOCK> sa;
+  StageB<NB, BLOCK> sb;
+  constexpr bool STAGED = CHAIN && DDB_BWD_STAGE;
+  if (STAGED) {
+    sa.init(sn, ddb_stage);
+    sb.init(sn, ddb_stage);
+    sa.start();
+  }
   // lambda = dL/dqd'
-  solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return gqdn[vidx(layout, N, n, w, d)]; }, ws,
-                          [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; });
+  auto gqnOf = [&](size_t ix) { return gqnAdd ? gqn[ix] + gqnAdd[ix] : gqn[ix]; };
+  auto gqdnOf = [&](size_t ix) { return gqdnAdd ? gqdn[ix] + gqdnAdd[ix] : gqdn[ix]; };
+  auto lamOf = [&](int d) { return gqdnOf(vidx(layout, N, n, w, d)); };
+  auto muFree = [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; };
+  if (STAGED) solveInvMass<NB, CHAIN>(sa, nb, lamOf, ws, muFree);
+  else solveInvMass<NB, CHAIN>(sn, nb, lamOf, ws, muFree);
   if (CHAIN) {
 #pragma unroll
     for (int i = 0; i < NB; i++) gtau[vidx(layout, N, n, w, i)] = dt * mu[i];
@@ -119,27 +147,30 @@ k_backward(int N, double* __restrict__ snap, const double* __restrict__ gqn, con
     for (int i = 0; i < nb; i++)
       if (c_topo.b[i].ndof == 1) gtau[vidx(layout, N, n, w, c_topo.b[i].dof)] = dt * mu[i];
   }
-  idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
+  auto out1 = [&](int d, double dq, double dqd) {
     size_t ix = vidx(layout, N, n, w, d);
-    double a = gqn[ix], l = gqdn[ix];
+    double a = gqnOf(ix), l = gqdnOf(ix);
     // pos-pos = I, vel-pos = dt I for R^1 joints; pos-vel^T l = -dt dPhi/dq; vel-vel^T l = l - dt dPhi/dqd
     gq[ix] = fma(-dt, dq, a);
     gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
-  }, [&](int body, const double* dq6, const double* dqd6) {
+  };
+  auto out6 = [&](int body, const double* dq6, const double* dqd6) {
     // FreeJoint block: dL/dq = posPos^T g_q' - dt dPhi/dq, dL/dqd = velPos^T g_q' + l - dt dPhi/dqd
     const DevBody& b = c_topo.b[body];
     double q6[6], qd6[6], pp[36], vp[36], a6[6];
     ld6(sn, body, 56, q6); ld6(sn, body, 48, qd6);
     freeJointPosJacobians(q6, qd6, dt, pp, vp);
-    for (int k = 0; k < 6; k++) a6[k] = gqn[vidx(layout, N, n, w, b.dof + k)];
+    for (int k = 0; k < 6; k++) a6[k] = gqnOf(vidx(layout, N, n, w, b.dof + k));
     for (int k = 0; k < 6; k++) {
       double sp = 0.0, sv2 = 0.0;
       for (int r = 0; r < 6; r++) { sp += pp[r * 6 + k] * a6[r]; sv2 += vp[r * 6 + k] * a6[r]; }
       const size_t ix = vidx(layout, N, n, w, b.dof + k);
       gq[ix] = sp - dt * dq6[k];
-      gqd[ix] = sv2 + gqdn[ix] - dt * dqd6[k];
+      gqd[ix] = sv2 + gqdnOf(ix) - dt * dqd6[k];
     }
-  });
+  };
+  if (STAGED) idAdjoint<NB, CHAIN>(sb, nb, ws, out1, out6);
+  else idAdjoint<NB, CHAIN>(sn, nb, ws, out1, out6);
   if (c_topo.has_limits) {
     const double* clip = clipSection(snap, nb, N);
 #pragma unroll 1

@@ -144,6 +144,10 @@ class BatchedWorld:
         self.last_active_set, self.last_solver_status = active, status
         return qn, qdn
 
+    def setLanes(self, n_lanes):
+        """Number of internal streams the rollout and host-buffer entry points spread chunks of worlds over."""
+        _check(self._lib, self._h, self._lib.ddb_set_lanes(self._h, int(n_lanes)), "ddb_set_lanes")
+
     def launch_count(self):
         return int(self._lib.ddb_launch_count(self._h))
 

@@ -196,7 +196,28 @@ int32_t ddb_snapshot_current(const ddb_handle* h);
 /* grow the slot pool to at least n_slots (never shrinks); returns the pool size in *n_out */
 int ddb_snapshot_reserve(ddb_handle* h, int32_t n_slots, int32_t* n_out);
 
-/* Host-buffer entry points: same semantics, host pointers, copies inside. */
+/*
+ * T-step rollouts: the caller of the hot path in the reference's trajectory code.
+ *   ddb_rollout_forward   SingleShot::getSnapshots (dart/trajectory/SingleShot.cpp:719-760): T steps from (q0, qd0) under
+ *                         tau[t]; step t is retained in snapshot slot t (the pool grows as needed) and its post-step state
+ *                         is written to q_seq[t], qd_seq[t].
+ *   ddb_rollout_backward  SingleShot::backpropGradientWrt (SingleShot.cpp:650-700): the reverse sweep over the retained steps.
+ *                         g_q_seq[t], g_qd_seq[t] = loss gradient w.r.t. the state after step t (zeros where the loss does not
+ *                         look); the gradient pulled back by the later steps is added before step t is pulled back. Outputs:
+ *                         dL/dq0, dL/dqd0 and dL/dtau[t] for every step.
+ * All sequences are [T] consecutive batched vectors in the handle's layout. Contact-free handles run the rollout as chunks
+ * of worlds on the handle's lanes (ddb_set_lanes, default 2), with no synchronisation between chunks until the call's end;
+ * handles with a contact stage step the whole batch in order on `stream`.
+ */
+int ddb_rollout_forward(ddb_handle* h, void* stream, int32_t T, const double* q0, const double* qd0,
+                        const double* tau, double* q_seq, double* qd_seq);
+int ddb_rollout_backward(ddb_handle* h, void* stream, int32_t T, const double* g_q_seq,
+                         const double* g_qd_seq, double* g_q0, double* g_qd0, double* g_tau);
+/* number of internal streams (1..16) used by the rollout entry points and the host-buffer path */
+int ddb_set_lanes(ddb_handle* h, int32_t n_lanes);
+
+/* Host-buffer entry points: same semantics, host pointers, copies inside (contact-free handles with world-major vectors
+   pipeline copy-in / kernel / copy-out over chunks of worlds on the lanes). */
 int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const double* tau,
                      double* q_next, double* qd_next);
 int ddb_backward_host(ddb_handle* h, const double* g_q_next, const double* g_qd_next,

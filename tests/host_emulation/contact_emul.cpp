@@ -21,9 +21,9 @@ extern "C" int emul_contact_step(const ddb_topology* topo, const ddb_params* par
   if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
   const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
   caps[0] = cmax; caps[1] = kmax;
-  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
-  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, q, qd, tau, qn, qdn, snap.data());
   if (c_ctopo.n_pairs == 0) { counts[0] = counts[1] = counts[2] = counts[3] = 0; return 0; }
   ContactLayout L{nb, nd, cmax, kmax};
   std::vector<double> wd(L.doubles(), 0.0), ld(lcpScratchDoubles(kmax) * 32, 0.0);
@@ -50,11 +50,11 @@ extern "C" int emul_step_backward(const ddb_topology* topo, const ddb_params* pa
   bool chain;
   if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
   const int N = 1, nd = c_topo.nd;
-  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
-  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, q, qd, tau, qn, qdn, snap.data());
   Limits lim{};
-  k_backward<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), gqn, gqdn, gq, gqd, gtau, lim);
+  k_backward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, snap.data(), gqn, gqdn, nullptr, nullptr, gq, gqd, gtau, lim);
   k_jacobians<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), posPos, posVel, velPos, velVel, forceVel);
   k_inv_mass<DDB_MAX_BODIES, false, 64, 1>(N, snap.data(), minv);
   return 0;
@@ -69,9 +69,9 @@ extern "C" int emul_contact_step_backward(const ddb_topology* topo, const ddb_pa
   if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
   if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
   const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
-  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
-  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, q, qd, tau, qn, qdn, snap.data());
   ContactLayout L{nb, nd, cmax, kmax};
   ContactSnapLayout KL{nd, cmax, kmax};
   ContactBwdLayout BL{nb, nd, kmax};
@@ -98,9 +98,9 @@ extern "C" int emul_mass_bilinear_grad(const ddb_topology* topo, const ddb_param
   bool chain;
   if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
   const int N = 1, nb = c_topo.nb, nd = c_topo.nd;
-  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0), zero(nd, 0.0), qn(nd), qdn(nd);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0), zero(nd, 0.0), qn(nd), qdn(nd);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
-  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, zero.data(), zero.data(), qn.data(), qdn.data(), snap.data());
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, q, zero.data(), zero.data(), qn.data(), qdn.data(), snap.data());
   Snap sn{reinterpret_cast<double2*>(snap.data()), N, 0};
   ContactBwdLocals<DDB_MAX_BODIES> loc;
   twistsFromRates<DDB_MAX_BODIES>(sn, nb, [&](int d) { return mu_a[d]; }, loc.ws.U, loc.ws.mu);
@@ -132,9 +132,9 @@ extern "C" int emul_contact_step_deferred(const ddb_topology* topo, const ddb_pa
   if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
   if (foldContactTopology(topo, params, c_ctopo, err) != DDB_OK) return 2;
   const int N = 1, nb = c_topo.nb, nd = c_topo.nd, cmax = c_ctopo.cmax, kmax = c_ctopo.kmax;
-  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * N + 8, 0.0);
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0);
   blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
-  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, q, qd, tau, qn, qdn, snap.data());
+  k_forward<DDB_MAX_BODIES, false, 64, 1>(N, 0, N, q, qd, tau, qn, qdn, snap.data());
   if (c_ctopo.n_pairs == 0) { counts[0] = counts[1] = counts[2] = counts[3] = 0; *passes_out = 0; return 0; }
   ContactLayout L{nb, nd, cmax, kmax};
   std::vector<double> wd(L.doubles(), 0.0), ld(lcpScratchDoubles(kmax) * 32, 0.0);

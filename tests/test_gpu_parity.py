@@ -204,14 +204,21 @@ def test_error_paths():
     assert lib.ddb_snapshot_select(h, 3) == 1
     assert lib.ddb_forward(h, None, None, g.data_ptr(), g.data_ptr(), g.data_ptr(), g.data_ptr(), None, None, None, None) == 1
     lib.ddb_destroy(h)
-    # the backward pass through contacts is not built yet: refused with a message, never approximated
-    topo, params, keep = skeletons.create_box_stack(2).to_ctypes()
+    # restitution > 0 (the bounce approximation, BackpropSnapshot.cpp:1141-1234) is not restated: the backward through such
+    # a world is refused with a message, never approximated
+    bouncy = skeletons.create_box_stack(2)
+    for sk in bouncy.skeletons:
+        for b in sk.bodies:
+            b.setRestitutionCoeff(0.5)
+    topo, params, keep = bouncy.to_ctypes()
     h = _abi._vp()
     assert lib.ddb_create(C.byref(topo), C.byref(params), 8, 0, C.byref(h)) == 0
     g6 = torch.zeros(8, 12, dtype=torch.float64, device="cuda")
     assert lib.ddb_forward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.clone().data_ptr(), g6.clone().data_ptr(), None, None, None, None) == 0
     assert lib.ddb_backward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr()) == 4
-    assert b"not implemented" in lib.ddb_last_error(h)
+    assert b"restitution" in lib.ddb_last_error(h)
+    # rollouts: the reverse sweep needs the forward sweep
+    assert lib.ddb_rollout_backward(h, None, 2, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr()) == 4
     lib.ddb_destroy(h)
 
 

@@ -1,0 +1,128 @@
+"""GPU: the T-step rollout entry points (ddb_rollout_forward / ddb_rollout_backward, the shape of SingleShot::getSnapshots and
+SingleShot::backpropGradientWrt, dart/trajectory/SingleShot.cpp:650-760) and the chunk-pipelined host-buffer path.
+
+Worlds are independent and every chunk runs the same kernels on the same numbers, so splitting a batch over lanes must not
+change a single bit; against the CPU oracle the bars are those of test_gpu_parity.py."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from diffdart_b200 import _abi, skeletons
+from diffdart_b200.rollout import dart_rollout
+from diffdart_b200.world import BatchedWorld, LossGradient, forwardPass
+from oracle import oracle as orc
+from util import random_inputs, ref_equals, max_ref_err
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device="cuda")
+
+
+def stepwise(desc, q0, qd0, taus, gp, gv):
+    """The same rollout through forwardPass / BackpropSnapshot.backprop, one call per step."""
+    T, N = taus.shape[0], q0.shape[0]
+    world = BatchedWorld(desc, N, n_snapshot_slots=T)
+    world.setPositions(cuda(q0)); world.setVelocities(cuda(qd0))
+    snaps, poses, vels = [], [], []
+    for t in range(T):
+        world.setForces(cuda(taus[t]))
+        snaps.append(forwardPass(world))
+        poses.append(world.getPositions().clone()); vels.append(world.getVelocities().clone())
+    run_q = torch.zeros_like(poses[0]); run_qd = torch.zeros_like(poses[0])
+    gtau = [None] * T
+    for t in reversed(range(T)):
+        nxt, this = LossGradient(), LossGradient()
+        nxt.lossWrtPosition, nxt.lossWrtVelocity = cuda(gp[t]) + run_q, cuda(gv[t]) + run_qd
+        snaps[t].backprop(world, this, nxt)
+        run_q, run_qd, gtau[t] = this.lossWrtPosition, this.lossWrtVelocity, this.lossWrtTorque
+    return torch.stack(poses), torch.stack(vels), run_q, run_qd, torch.stack(gtau)
+
+
+def rollout(desc, q0, qd0, taus, gp, gv, lanes):
+    N = q0.shape[0]
+    world = BatchedWorld(desc, N)
+    world.setLanes(lanes)
+    a, b, c = cuda(q0).requires_grad_(), cuda(qd0).requires_grad_(), cuda(taus).requires_grad_()
+    poses, vels = dart_rollout(world, a, b, c)
+    ((poses * cuda(gp)).sum() + (vels * cuda(gv)).sum()).backward()
+    return poses.detach(), vels.detach(), a.grad, b.grad, c.grad
+
+
+@pytest.mark.parametrize("N,lanes", [(64, 1), (1000, 3), (4096, 2), (5000, 4)])
+def test_rollout_equals_stepwise_bitwise(N, lanes):
+    desc = skeletons.create_multiarm_robot(5)
+    T, n = 6, 5
+    q0, qd0, _ = random_inputs(n, N, 5)
+    rng = np.random.default_rng(6)
+    taus, gp, gv = rng.uniform(-1, 1, (T, N, n)), rng.normal(size=(T, N, n)), rng.normal(size=(T, N, n))
+    ref = stepwise(desc, q0, qd0, taus, gp, gv)
+    got = rollout(desc, q0, qd0, taus, gp, gv, lanes)
+    for name, r, g in zip(("poses", "vels", "dL/dq0", "dL/dqd0", "dL/dtau"), ref, got):
+        # the running gradient is added inside the backward kernel (a + b, the same sum the stepwise path forms with torch)
+        assert torch.equal(r, g), (name, float((r - g).abs().max()))
+
+
+def test_rollout_against_oracle():
+    desc = skeletons.create_multiarm_robot(3)
+    N, n, T = 48, 3, 10
+    q0, qd0, _ = random_inputs(n, N, 31)
+    rng = np.random.default_rng(32)
+    taus, gp, gv = rng.uniform(-1, 1, (T, N, n)), rng.normal(size=(T, N, n)), rng.normal(size=(T, N, n))
+    poses, vels, gq0, gqd0, gtau = rollout(desc, q0, qd0, taus, gp, gv, 2)
+    o = orc.OracleWorld(desc)
+    qs, qds = [q0], [qd0]
+    for t in range(T):
+        a, b = o.step(qs[-1], qds[-1], taus[t])
+        qs.append(a); qds.append(b)
+    assert ref_equals(poses.cpu().numpy(), np.stack(qs[1:]), 1e-11)
+    assert ref_equals(vels.cpu().numpy(), np.stack(qds[1:]), 1e-11)
+    gq, gqd = np.zeros_like(q0), np.zeros_like(q0)
+    for t in reversed(range(T)):
+        _, _, gq, gqd, gt = o.step_backprop(qs[t], qds[t], taus[t], gp[t] + gq, gv[t] + gqd, mode="exact", with_step=False)
+        assert ref_equals(gtau[t].cpu().numpy(), gt, 1e-9), (t, max_ref_err(gtau[t].cpu().numpy(), gt))
+    assert ref_equals(gq0.cpu().numpy(), gq, 1e-9), max_ref_err(gq0.cpu().numpy(), gq)
+    assert ref_equals(gqd0.cpu().numpy(), gqd, 1e-9), max_ref_err(gqd0.cpu().numpy(), gqd)
+
+
+def test_rollout_with_contacts_equals_stepwise():
+    """Handles with a contact stage run the rollout step by step on the caller's stream: the same launches as the stepwise path."""
+    desc = skeletons.create_box_stack(2)
+    N, T, n = 32, 4, 12
+    rng = np.random.default_rng(3)
+    q0 = np.zeros((N, n)); qd0 = rng.uniform(-0.1, 0.1, (N, n))
+    for i in range(2):
+        q0[:, 6 * i + 3] = rng.uniform(-0.05, 0.05, N); q0[:, 6 * i + 4] = rng.uniform(-0.05, 0.05, N)
+        q0[:, 6 * i + 5] = 0.25 + 0.5 * i - 1e-3 * (i + 1)
+    taus = np.zeros((T, N, n)); gp, gv = rng.normal(size=(T, N, n)), rng.normal(size=(T, N, n))
+    ref = stepwise(desc, q0, qd0, taus, gp, gv)
+    got = rollout(desc, q0, qd0, taus, gp, gv, 2)
+    for name, r, g in zip(("poses", "vels", "dL/dq0", "dL/dqd0", "dL/dtau"), ref, got):
+        assert torch.allclose(r, g, rtol=0, atol=1e-12), (name, float((r - g).abs().max()))
+
+
+def test_host_path_chunked_equals_device_path():
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(5)
+    N, n = 10000, 5  # >= 4096 worlds, world-major: the host entry points pipeline chunks over the lanes
+    q, qd, tau = random_inputs(n, N, 9)
+    g = np.random.default_rng(10).normal(size=(2, N, n))
+    topo, params, keep = desc.to_ctypes()
+    h = _abi._vp()
+    assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
+    hin = [torch.tensor(a, dtype=torch.float64).pin_memory() for a in (q, qd, tau, g[0], g[1])]
+    hout = [torch.empty(N, n, dtype=torch.float64).pin_memory() for _ in range(5)]
+    assert lib.ddb_forward_host(h, *[t.data_ptr() for t in hin[:3]], hout[0].data_ptr(), hout[1].data_ptr()) == 0, lib.ddb_last_error(h)
+    assert lib.ddb_backward_host(h, hin[3].data_ptr(), hin[4].data_ptr(), *[t.data_ptr() for t in hout[2:]]) == 0, lib.ddb_last_error(h)
+    din = [t.cuda() for t in hin]
+    dout = [torch.empty(N, n, dtype=torch.float64, device="cuda") for _ in range(5)]
+    assert lib.ddb_forward(h, None, *[t.data_ptr() for t in din[:3]], dout[0].data_ptr(), dout[1].data_ptr(), None, None, None, None) == 0
+    assert lib.ddb_backward(h, None, din[3].data_ptr(), din[4].data_ptr(), *[t.data_ptr() for t in dout[2:]]) == 0
+    torch.cuda.synchronize()
+    for a, b in zip(hout, dout):
+        assert torch.equal(a, b.cpu())
+    assert lib.ddb_launch_count(h) > 4  # the host path really ran as several chunk launches
+    lib.ddb_destroy(h)
