@@ -5,7 +5,10 @@
   python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU path on the host cores
 
 Workload (BASELINE.json configs[1]): 65536 independent 5-link pendulums per GPU (no contact), one
-"step" = ddb_forward + ddb_backward over the whole batch (dart_layer forward + backward semantics).
+"step" = one forward step + its analytic backward over the whole batch. The K timed steps run as the library's
+T-step rollout with backprop (ddb_rollout_forward + ddb_rollout_backward, T = 8: the call pattern of the reference's
+trajectory code, SingleShot.cpp:650-760), K/8 rollouts back to back; the same step issued as separate
+ddb_forward + ddb_backward calls (dart_layer forward + backward semantics) is timed next to it ("single_step").
 Weak scaling: every rank owns 65536 worlds; there is no inter-GPU traffic inside a step.
 One JSON line is printed by rank 0 (see the contract in the task description).
 """
@@ -27,7 +30,8 @@ METRIC = "world-steps/sec incl. analytic backprop"
 UNIT = "world-steps/s"
 N_WORLDS = 65536
 N_DOFS = 5
-WORKLOAD = "pendulum5: 65536 five-link revolute pendulums per GPU, no contact (BASELINE configs[1]); step = forward + analytic backward VJP"
+WORKLOAD = ("pendulum5: 65536 five-link revolute pendulums per GPU, no contact (BASELINE configs[1]); step = forward step + analytic backward VJP, "
+            "run as 8-step rollouts with backprop through ddb_rollout_forward / ddb_rollout_backward")
 # Algorithmic HBM bytes per world, SURVEY.md §8(d): forward reads q,qd,tau (3n) and writes q',qd' (2n) = 40n B;
 # backward reads dL/dq',dL/dqd' (2n) + the pre-step state (3n) and writes dL/dq,dL/dqd,dL/dtau (3n) = 64n B.
 # (The design additionally moves a 288 B/body snapshot each way on purpose — DESIGN.md §4 — which shows up in
@@ -255,8 +259,30 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    # ---- the rollout: T = SETS steps forward (one snapshot slot per step), then the reverse sweep ----
+    T = SETS
+    rng = np.random.default_rng(5 + rank)
+    taus = mk(rng.uniform(-1, 1, (T, N, n)))
+    gpos, gvel = mk(rng.normal(size=(T, N, n))), mk(rng.normal(size=(T, N, n)))
+    poses, vels, gtaus = torch.empty_like(taus), torch.empty_like(taus), torch.empty_like(taus)
+    q0d, qd0d = mk(q), mk(qd)
+    gq0, gqd0 = torch.empty_like(q0d), torch.empty_like(q0d)
+    lib.ddb_set_lanes(h, args.lanes)
+
+    def rollout(t_steps):
+        r1 = lib.ddb_rollout_forward(h, sp, t_steps, q0d.data_ptr(), qd0d.data_ptr(), taus.data_ptr(), poses.data_ptr(), vels.data_ptr())
+        r2 = lib.ddb_rollout_backward(h, sp, t_steps, gpos.data_ptr(), gvel.data_ptr(), gq0.data_ptr(), gqd0.data_ptr(), gtaus.data_ptr())
+        if r1 or r2:
+            raise RuntimeError(lib.ddb_last_error(h).decode())
+
+    def run_steps(k):
+        while k > 0:
+            rollout(min(T, k))
+            k -= T
+
     sampler = ClockSampler(local_rank)
-    for s in range(max(args.warmup, 3)):
+    run_steps(max(args.warmup, 3))
+    for s in range(SETS):
         step(s)
     barrier()
     # ---- timed region: exactly K steps, device-resident inputs ----
@@ -265,12 +291,20 @@ def run_ours(args):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     barrier()
     ev[0].record(stream)
-    for s in range(args.steps):
-        step(s)
+    run_steps(args.steps)
     ev[1].record(stream)
     barrier()
     elapsed_ms = ev[0].elapsed_time(ev[1])
     launches = int(lib.ddb_launch_count(h) - launches0)
+    # ---- the same K steps as separate ddb_forward + ddb_backward calls on one stream (dart_layer's two calls) ----
+    barrier()
+    ev2 = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev2[0].record(stream)
+    for s in range(args.steps):
+        step(s)
+    ev2[1].record(stream)
+    barrier()
+    single_ms = ev2[0].elapsed_time(ev2[1])
     # keep the GPU under the same load a little longer if the timed region was too short to sample clocks
     t_end = time.time() + (0.3 if elapsed_ms < 300 else 0.0)
     s = 0
@@ -320,10 +354,10 @@ def run_ours(args):
     if not args.no_contact:
         contact_ms, contact_tiers, _ = contact_bench(local_rank, rank)
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -339,14 +373,16 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "worlds_per_gpu": N, "n_dofs": n, "dt": 1e-3,
-                       "cache": "8 rotating input/output/snapshot sets (960 MB >> 126 MB L2): every step reads cold inputs"},
+            "config": {"workload": WORKLOAD, "worlds_per_gpu": N, "n_dofs": n, "dt": 1e-3, "rollout_steps": T, "lanes": args.lanes,
+                       "cache": "every rollout writes and re-reads 8 snapshot slots + 8 steps of inputs/outputs (790 MB >> 126 MB L2): steps read cold data"},
             "clocks": sampler.result(),
             "e2e": {"value": world_size * N * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 5 * N * n * 8,
                     "d2h_bytes_per_step": 5 * N * n * 8, "steps": e2e_steps,
                     "path": "ddb_forward_host + ddb_backward_host with pinned host buffers"},
             "gpu_launches": launches,
-            "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms},
+            "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms, "note": "whole-batch launches timed alone on one stream, rotating cold sets"},
+            "single_step": {"value": world_size * N * args.steps / (single_ms * 1e-3), "unit": UNIT, "ms_per_step": single_ms / args.steps,
+                            "path": "ddb_forward + ddb_backward per step on one stream, 8 rotating cold sets"},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": dom[4], "peak_source": peak_src,
                          "note": "FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md §4"},
@@ -368,9 +404,11 @@ def run_ours(args):
                     line["contact_rich"]["cpu_baseline"] = {"unavailable": str(exc)[:200]}
         if world_size == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            v, secs = cpu_world_steps(N_WORLDS, threads)
+            v1, s1 = cpu_world_steps(N_WORLDS, threads)
+            reps = int(min(200, max(1, round(12.0 / max(s1, 1e-3)))))  # about 12 s of CPU work
+            v, secs = cpu_world_steps(N_WORLDS, threads, reps=reps)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                    "sample": "one pass over the same 65536-world batch (%.1f s); CPU restatement of the reference arithmetic incl. its finite-difference Jacobian recipes" % secs}
+                                    "sample": "%d passes over the same 65536-world batch (%.1f s); CPU restatement of the reference arithmetic incl. its finite-difference Jacobian recipes (reference not buildable here: no Eigen)" % (reps, secs)}
         print(json.dumps(line))
     lib.ddb_destroy(h)
     if world_size > 1:
@@ -390,6 +428,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-contact", action="store_true", help="skip the second (contact-rich) workload")
+    ap.add_argument("--lanes", type=int, default=2, help="internal streams the rollout spreads chunks of worlds over")
     args = ap.parse_args()
     if args.impl == "reference":
         if args.steps == 2000:

@@ -660,8 +660,47 @@ static int ensureStage(ddb_handle* h, size_t doubles) {
 }
 
 // Contact-free handles with world-major vectors run the call as chunks on the lanes: the copy-in of chunk c+1, the kernel of chunk c
-// and the copy-out of chunk c-1 overlap (PCIe is full duplex), so the call costs about max(bytes in, bytes out) / link rate.
+// and the copy-out of chunk c-1 overlap (PCIe is full duplex). Measured on B200 / PCIe 5 (65536 five-link worlds, 13 MB each way per
+// forward + backward): 1 chunk 0.62 ms, 2 chunks 0.53 ms, 4 chunks 0.57-0.63 ms, 8 chunks 0.75 ms - every extra copy costs ~5 us of DMA
+// set-up, also when the pipeline is replayed from a CUDA graph (tried: no gain), and letting the kernels read / write the pinned
+// host buffers themselves is 3x slower (40-byte strides over PCIe). Hence two chunks (DDB_HOST_CHUNKS overrides).
 static bool hostChunked(const ddb_handle* h) { return !h->hasContacts && h->topo.layout == DDB_LAYOUT_WORLD_MAJOR && h->N >= 4096; }
+static int envInt(const char* name, int dflt) { const char* e = getenv(name); return e ? std::max(1, atoi(e)) : dflt; }
+
+// kind 0: forward (in: q, qd, tau; out: qn, qdn), kind 1: backward (in: gqn, gqdn; out: gq, gqd, gtau); ptr = the five host pointers in that order
+static int enqueueHostChunks(ddb_handle* h, int kind, const void* const* ptr, int K) {
+  const size_t V = (size_t)h->N * h->n;
+  double* d = h->stage;
+  const int L = std::min((int)h->lanes.size(), K), nin = kind == 0 ? 3 : 2;
+  int rc = forkLanes(h, h->hstream, L);
+  if (rc) return rc;
+  for (int c = 0; c < K; c++) {
+    int w0, w1;
+    chunkRange(h->N, K, c, &w0, &w1);
+    if (w0 >= w1) continue;
+    cudaStream_t st = h->lanes[c % L];
+    const size_t o = (size_t)w0 * h->n, b = (size_t)(w1 - w0) * h->n * sizeof(double);
+    for (int a = 0; a < nin; a++) DDB_CUDA(h, cudaMemcpyAsync(d + a * V + o, (const double*)ptr[a] + o, b, cudaMemcpyHostToDevice, st));
+    if (kind == 0) h->k.fwd(st, h->N, w0, w1, d, d + V, d + 2 * V, d + 3 * V, d + 4 * V, h->slots[h->cur]);
+    else h->k.bwd(st, h->N, w0, w1, h->slots[h->cur], d, d + V, nullptr, nullptr, d + 2 * V, d + 3 * V, d + 4 * V, h->lim);
+    for (int a = nin; a < 5; a++) DDB_CUDA(h, cudaMemcpyAsync((double*)ptr[a] + o, d + a * V + o, b, cudaMemcpyDeviceToHost, st));
+  }
+  DDB_CUDA(h, cudaGetLastError());
+  return joinLanes(h, h->hstream, L);
+}
+
+static int runHostChunked(ddb_handle* h, int kind, const void* const* ptr) {
+  int rc = enter(h, h->hstream);
+  if (rc) return rc;
+  rc = ensureLanes(h);
+  if (rc) return rc;
+  static const int K = envInt("DDB_HOST_CHUNKS", 2);
+  rc = enqueueHostChunks(h, kind, ptr, K);
+  if (rc) return rc;
+  for (int c = 0; c < K; c++) { int w0, w1; chunkRange(h->N, K, c, &w0, &w1); h->launches += w1 > w0; }
+  DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
+  return DDB_OK;
+}
 
 int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const double* tau, double* qn, double* qdn) {
   if (!h || !q || !qd || !tau || !qn || !qdn) return fail(h, DDB_ERR_INVALID, "ddb_forward_host: null pointer");
@@ -671,32 +710,10 @@ int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const dou
   if (rc) return rc;
   double* d = h->stage;
   if (hostChunked(h)) {
-    rc = enter(h, h->hstream);
+    const void* ptr[5] = {q, qd, tau, qn, qdn};
+    rc = runHostChunked(h, 0, ptr);
     if (rc) return rc;
-    rc = ensureLanes(h);
-    if (rc) return rc;
-    const int L = (int)h->lanes.size(), K = 4 * L;  // chunks, dealt round-robin to the lanes
-    rc = forkLanes(h, h->hstream, L);
-    if (rc) return rc;
-    for (int c = 0; c < K; c++) {
-      int w0, w1;
-      chunkRange(h->N, K, c, &w0, &w1);
-      if (w0 >= w1) continue;
-      cudaStream_t st = h->lanes[c % L];
-      const size_t o = (size_t)w0 * h->n, b = (size_t)(w1 - w0) * h->n * sizeof(double);
-      DDB_CUDA(h, cudaMemcpyAsync(d + o, q + o, b, cudaMemcpyHostToDevice, st));
-      DDB_CUDA(h, cudaMemcpyAsync(d + V + o, qd + o, b, cudaMemcpyHostToDevice, st));
-      DDB_CUDA(h, cudaMemcpyAsync(d + 2 * V + o, tau + o, b, cudaMemcpyHostToDevice, st));
-      h->k.fwd(st, h->N, w0, w1, d, d + V, d + 2 * V, d + 3 * V, d + 4 * V, h->slots[h->cur]);
-      h->launches++;
-      DDB_CUDA(h, cudaMemcpyAsync(qn + o, d + 3 * V + o, b, cudaMemcpyDeviceToHost, st));
-      DDB_CUDA(h, cudaMemcpyAsync(qdn + o, d + 4 * V + o, b, cudaMemcpyDeviceToHost, st));
-    }
-    DDB_CUDA(h, cudaGetLastError());
     h->slotValid[h->cur] = 1;
-    rc = joinLanes(h, h->hstream, L);
-    if (rc) return rc;
-    DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
     return DDB_OK;
   }
   DDB_CUDA(h, cudaMemcpyAsync(d, q, B, cudaMemcpyHostToDevice, h->hstream));
@@ -719,32 +736,8 @@ int ddb_backward_host(ddb_handle* h, const double* gqn, const double* gqdn, doub
   double* d = h->stage;
   if (hostChunked(h)) {
     if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward_host: no forward pass retained in the current snapshot slot");
-    rc = enter(h, h->hstream);
-    if (rc) return rc;
-    rc = ensureLanes(h);
-    if (rc) return rc;
-    const int L = (int)h->lanes.size(), K = 4 * L;
-    rc = forkLanes(h, h->hstream, L);
-    if (rc) return rc;
-    for (int c = 0; c < K; c++) {
-      int w0, w1;
-      chunkRange(h->N, K, c, &w0, &w1);
-      if (w0 >= w1) continue;
-      cudaStream_t st = h->lanes[c % L];
-      const size_t o = (size_t)w0 * h->n, b = (size_t)(w1 - w0) * h->n * sizeof(double);
-      DDB_CUDA(h, cudaMemcpyAsync(d + o, gqn + o, b, cudaMemcpyHostToDevice, st));
-      DDB_CUDA(h, cudaMemcpyAsync(d + V + o, gqdn + o, b, cudaMemcpyHostToDevice, st));
-      h->k.bwd(st, h->N, w0, w1, h->slots[h->cur], d, d + V, nullptr, nullptr, d + 2 * V, d + 3 * V, d + 4 * V, h->lim);
-      h->launches++;
-      DDB_CUDA(h, cudaMemcpyAsync(gq + o, d + 2 * V + o, b, cudaMemcpyDeviceToHost, st));
-      DDB_CUDA(h, cudaMemcpyAsync(gqd + o, d + 3 * V + o, b, cudaMemcpyDeviceToHost, st));
-      DDB_CUDA(h, cudaMemcpyAsync(gtau + o, d + 4 * V + o, b, cudaMemcpyDeviceToHost, st));
-    }
-    DDB_CUDA(h, cudaGetLastError());
-    rc = joinLanes(h, h->hstream, L);
-    if (rc) return rc;
-    DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
-    return DDB_OK;
+    const void* ptr[5] = {gqn, gqdn, gq, gqd, gtau};
+    return runHostChunked(h, 1, ptr);
   }
   DDB_CUDA(h, cudaMemcpyAsync(d, gqn, B, cudaMemcpyHostToDevice, h->hstream));
   DDB_CUDA(h, cudaMemcpyAsync(d + V, gqdn, B, cudaMemcpyHostToDevice, h->hstream));
