@@ -38,12 +38,12 @@ WORKLOAD = ("pendulum5: 65536 five-link revolute pendulums per GPU, no contact (
 # roofline.traffic, not in the algorithmic bytes.)
 FWD_BYTES = 40 * N_DOFS
 BWD_BYTES = 64 * N_DOFS
-# DRAM traffic per launch from the round-1 `ncu --set full` capture (profiles/r01_ncu_full_summary.csv), bytes
-FWD_TRAFFIC = 7.96e6 + 72.4e6
-BWD_TRAFFIC = 93.4e6 + 3.63e6
+# DRAM traffic per whole-batch launch from the `ncu --set full` captures (profiles/r01b_ncu_full_summary.csv), bytes
+FWD_TRAFFIC = 8.03e6 + 71.99e6
+BWD_TRAFFIC = 99.73e6 + 6.46e6
 # FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
-FWD_FLOPS = 4639
-BWD_FLOPS = 4242
+FWD_FLOPS = 4933
+BWD_FLOPS = 4245
 
 
 def inputs(N, seed=1234):
@@ -170,7 +170,7 @@ def contact_bench(local_rank, rank, steps=4, warmup=3):
     return e0.elapsed_time(e1) / steps, tiers, N
 
 
-def contact_cpu_baseline(n_worlds=6):
+def contact_cpu_baseline(n_worlds=1024):
     """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
     from diffdart_b200 import skeletons
     from oracle.oracle import OracleWorld
@@ -387,8 +387,10 @@ def run_ours(args):
                          "traffic": dom[4], "peak_source": peak_src,
                          "note": "FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md §4"},
             "roofline_fp64": {"peak": peak.value, "unit": "TFLOP/s", "peak_source": "ddb_measure_fp64_peak (DFMA micro-benchmark, this run)",
-                              "achieved": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12,
-                              "frac": None if dom[3] is None else dom[3] * N / (dom[1] * 1e-3) / 1e12 / peak.value},
+                              "kernel": dom[0], "achieved": dom[3] * N / (dom[1] * 1e-3) / 1e12, "frac": dom[3] * N / (dom[1] * 1e-3) / 1e12 / peak.value,
+                              "whole_step_achieved": (FWD_FLOPS + BWD_FLOPS) * N * args.steps / (elapsed_ms * 1e-3) / 1e12,
+                              "whole_step_frac": (FWD_FLOPS + BWD_FLOPS) * N * args.steps / (elapsed_ms * 1e-3) / 1e12 / peak.value,
+                              "note": "flops per world counted from SASS (profiles/r01_flops.md); whole_step = the timed rollout (chunks of both kernels overlap on the lanes)"},
         }
         if not args.no_contact:
             line["contact_rich"] = {"workload": CONTACT_WORKLOAD, "value": world_size * CONTACT_WORLDS / (contact_ms * 1e-3), "unit": UNIT,
@@ -399,7 +401,7 @@ def run_ours(args):
                 try:
                     cv, cs = contact_cpu_baseline()
                     line["contact_rich"]["cpu_baseline"] = {"value": cv, "unit": UNIT, "cores": 1, "kind": "port",
-                                                            "sample": "6 worlds, forwardPass + the reference's Jacobian recipe on one core (%.1f s)" % cs}
+                                                            "sample": "1024 worlds, forwardPass + the reference's Jacobian recipe on one core (%.1f s)" % cs}
                 except Exception as exc:  # the oracle's reference libraries travel prebuilt; report instead of failing the headline
                     line["contact_rich"]["cpu_baseline"] = {"unavailable": str(exc)[:200]}
         if world_size == 1 and not args.no_cpu_baseline:

@@ -60,8 +60,8 @@ DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {
 // kernels. 18 double2 per body; every access of a warp is one contiguous 512-byte segment
 // (layout of the pairs: struct Snap below):
 //   pairs 0-5  relative transform T_i (R row-major, p)      pairs 12-14 AIS_i = IA_i S_i
-//   pairs 6-8  spatial velocity V_i                         pair  15    (psi_i, qd_i)
-//   pairs 9-11 spatial acceleration A_i                     pairs 16-17 (G_i = R_world^T g, qdd_i)
+//   pairs 6-8  spatial velocity V_i                         pair  15    (psi_i, qdd_i)           written by sweep 3
+//   pairs 9-11 spatial acceleration A_i                     pairs 16-17 (G_i = R_world^T g, qd_i) written by sweep 1
 // Keeping these instead of recomputing them moves work from the FP64 pipe (the binding unit)
 // to L2/HBM, which the path barely uses otherwise.
 // ---------------------------------------------------------------------------------------------
@@ -76,6 +76,10 @@ constexpr int kSnapPairsFree = 59;  // + pairs 56-58: the joint coordinates q (6
 struct Snap {
   double2* base;
   int N, w;
+  // chains of 1-DOF joints: body i owns pairs [18 i, 18 i + 18), known at compile time, which (with the tile-major layout) turns
+  // every snapshot address into one base register + an immediate; 0 = look the offset up in the topology
+  int chainPairs = 0;
+  DDB_DI int offOf(int body) const { return chainPairs ? body * chainPairs : c_topo.b[body].snapOff; }
 #if DDB_SNAP_TILED
   // tile-major: [world / 32][pair][world % 32]. The pairs of 32 consecutive worlds form one contiguous block (46 KB for the
   // 5-link chain), so a warp streams through one DRAM-page-friendly region instead of touching one 512-byte piece in each
@@ -87,7 +91,7 @@ struct Snap {
   DDB_DI size_t rowStride() const { return (size_t)N; }
   DDB_DI size_t origin() const { return (size_t)w; }
 #endif
-  DDB_DI size_t at(int body, int k) const { return origin() + (size_t)(c_topo.b[body].snapOff + k) * rowStride(); }
+  DDB_DI size_t at(int body, int k) const { return origin() + (size_t)(offOf(body) + k) * rowStride(); }
   DDB_DI void st(int body, int k, double a, double b) const { base[at(body, k)] = make_double2(a, b); }
   DDB_DI double2 ld(int body, int k) const { return __ldg(base + at(body, k)); }
   // plain (coherent) load: for values written earlier by the same thread in the same kernel
@@ -185,14 +189,16 @@ struct StageBase {
   size_t strideN;     // pairs between consecutive rows
   double2* sm;        // this thread's column of the CTA's staging area
   unsigned smAddr;
+  int chainPairs;
   DDB_DI void init(const Snap& sn, double2* smemBase) {
+    chainPairs = sn.chainPairs;
     g = sn.base + sn.origin();
     strideN = sn.rowStride();
     sm = smemBase + threadIdx.x;
     smAddr = sharedAddr(sm);
   }
   DDB_DI void copyRow(int slot, int body, int k) const {
-    const double2* src = g + (size_t)(c_topo.b[body].snapOff + k) * strideN;
+    const double2* src = g + (size_t)(chainPairs * body + k) * strideN;  // (staging is used by chains only)
     cpAsync16(smAddr + (unsigned)(slot * BLOCK * (int)sizeof(double2)), src);
   }
   DDB_DI static int slotA(int body, int k) { return G::kRowsA * body + (k < 6 ? k : k - 6); }
@@ -400,14 +406,14 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
   typedef Tree<NB, CHAIN> TS;
   struct {  // one object, see BwdScratch
     Xf T[NB];
-    SV V[NB], AIS[NB], A[NB], bias[NB];
+    SV V[NB], AIS[NB], A[NB], bias[NB], eta[NB];
     V3 G[NB];
     ABI IA[NB];
     double psi[NB], u[NB], qdv[NB];
     double cth[NB], sth[NB];
   } ws;
   Xf* T = ws.T;
-  SV *V = ws.V, *AIS = ws.AIS, *A = ws.A, *bias = ws.bias;
+  SV *V = ws.V, *AIS = ws.AIS, *A = ws.A, *bias = ws.bias, *eta = ws.eta;
   V3* G = ws.G;
   ABI* IA = ws.IA;
   double *psi = ws.psi, *u = ws.u, *qdv = ws.qdv;
@@ -461,6 +467,9 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     G[i] = mulT(t.R, gp);
     sn.stT(i, t);
     sn.stSV(i, 6, V[i]);
+    // G_i and qd_i leave the register file here (sweeps 2 and 3 do not need them)
+    if (isFree) { sn.st(i, 54, G[i].x, G[i].y); sn.st(i, 55, G[i].z, 0.0); }
+    else { sn.st(i, 16, G[i].x, G[i].y); sn.st(i, 17, G[i].z, qdv[i]); }
   };
   // rigid-body terms of sweep 2, set right before it (they stay off the register file during sweep 1)
   auto rigid = [&](int i) {
@@ -470,6 +479,8 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     SV IV = mul(b.I, V[i]);
     SV fg = b.gravity ? mul(b.I, sv(mk(0, 0, 0), G[i])) : svzero();
     bias[i] = -dad(V[i], IV) - fg;
+    // partial acceleration ad(V, S qd) (GenericJoint.hpp:1740-1750, dS = 0): all that sweeps 2 and 3 need of V_i
+    eta[i] = ad(V[i], qdv[i] * b.S);
   };
   auto up = [&](int i) {
     const DevBody& b = c_topo.b[i];
@@ -507,23 +518,22 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
       }
       return;
     }
-    SV eta = ad(V[i], qdv[i] * b.S);  // partial acceleration (GenericJoint.hpp:1740-1750, dS = 0)
+    const SV etai = eta[i];
     SV ais = svzero();
     double ps = 0.0, ui = 0.0;
     if (TS::hasDof(i)) {
       ais = mul(IA[i], b.S);
       ps = 1.0 / dot(b.S, ais);
       // total force u = tau - S^T (IA eta + bias)   (GenericJoint.hpp:2208-2229 with d = k = 0)
-      ui = tauOf(TS::dofOf(i)) - dot(b.S, mul(IA[i], eta) + bias[i]);
+      ui = tauOf(TS::dofOf(i)) - dot(b.S, mul(IA[i], etai) + bias[i]);
     }
     AIS[i] = ais;
     psi[i] = ps;
     u[i] = ui;
     sn.stSV(i, 12, ais);
-    sn.st(i, 15, ps, qdv[i]);
     if (p >= 0) {
       // beta = bias + IA (eta + S psi u)   (GenericJoint.hpp:2049-2074)
-      SV beta = bias[i] + mul(IA[i], eta) + (ps * ui) * ais;
+      SV beta = bias[i] + mul(IA[i], etai) + (ps * ui) * ais;
       const Xf Ti = Tof(i);
       bias[p] = bias[p] + dAdInvT(Ti, beta);
       ABI Pi = IA[i];
@@ -536,10 +546,6 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
     const int p = TS::parentOf(i);
     const Xf Ti = Tof(i);
     SV Ap = (p >= 0) ? AdInvT(Ti, A[p]) : svzero();
-#ifdef DDB_FWD_REBUILD_V
-    // chains: V_i is rebuilt along the sweep from (T_i, V_parent) instead of staying live since sweep 1
-    if (CHAIN) V[i] = (p >= 0) ? AdInvT(Ti, V[p]) + qdv[i] * b.S : qdv[i] * b.S;
-#endif
     if (!CHAIN && b.type == DDB_JOINT_FREE) {
       double AISm[36], psi6[36], u6[6], qd6[6], r6[6], acc6[6];
       ld36c(sn, i, 12, AISm); ld36c(sn, i, 30, psi6); ld6c(sn, i, 51, u6); ld6c(sn, i, 48, qd6);
@@ -549,8 +555,6 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
       A[i] = Ap + mulS6(b, acc6) + ad(V[i], mulS6(b, qd6));
       sn.stSV(i, 9, A[i]);
       st6(sn, i, 51, acc6);
-      sn.st(i, 54, G[i].x, G[i].y);
-      sn.st(i, 55, G[i].z, 0.0);
       return;
     }
     double acc = 0.0;
@@ -559,10 +563,9 @@ DDB_DI void forwardDynamics(const Snap& sn, int nb, QF qOf, QDF qdOf, TauF tauOf
       acc = psi[i] * (u[i] - dot(AIS[i], Ap));
       store(TS::dofOf(i), acc);
     }
-    A[i] = Ap + acc * b.S + ad(V[i], qdv[i] * b.S);
+    A[i] = Ap + acc * b.S + eta[i];
     sn.stSV(i, 9, A[i]);
-    sn.st(i, 16, G[i].x, G[i].y);
-    sn.st(i, 17, G[i].z, acc);
+    sn.st(i, 15, psi[i], acc);
   };
   if (CHAIN) {
 #pragma unroll
@@ -811,10 +814,10 @@ DDB_DI void idAdjointEx(const SN& sn, int nb, BwdScratch<NB>& ws, const SV* dA, 
       }
       return;
     }
-    const double qdi = MODE == 2 ? 0.0 : sn.ld(i, 15).y;
     const double2 g0 = sn.ld(i, 16), g1 = sn.ld(i, 17);
+    const double qdi = MODE == 2 ? 0.0 : g1.y;
     const V3 Gi = MODE == 2 ? mk(0, 0, 0) : mk(g0.x, g0.y, g1.x);
-    const double qddi = g1.y;
+    const double qddi = sn.ld(i, 15).y;
     const SV Ui = U[i];
     SV IV = mul(b.I, Vi);
     SV Aeff = Ai;

@@ -34,7 +34,7 @@ k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __r
   if (w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
   double* clip = clipSection(snap, nb, N);
   if (CHAIN) {
     double ql[NB], qdl[NB], tl[NB], acc[NB];
@@ -115,7 +115,7 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
   if (w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   // chains read the snapshot through the cp.async staging area (dynamics.cuh, StageA / StageB); trees read global memory
@@ -193,7 +193,7 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
@@ -255,7 +255,7 @@ k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;

@@ -86,6 +86,17 @@ e1.record()
 torch.cuda.synchronize()
 out["graph_step_us"] = e0.elapsed_time(e1) / (R * SETS) * 1e3
 out["ws_per_s_graph"] = N / (out["graph_step_us"] * 1e-6)
+# forward + the five materialised Jacobians (BM_Cartpole_Jacobians semantics, unittests/benchmarks/bench_Jacobians.cpp:131-139)
+J = [torch.empty(N, n, n, dtype=torch.float64, device=dev) for _ in range(5)]
+def jac(s):
+    lib.ddb_snapshot_select(h, s % SETS)
+    assert lib.ddb_jacobians(h, sp, *[t.data_ptr() for t in J]) == 0
+out["jacobians_us"] = timeit(jac, max(8, args.reps // 4))
+Minv = torch.empty(N, n, n, dtype=torch.float64, device=dev)
+def minv(s):
+    lib.ddb_snapshot_select(h, s % SETS)
+    assert lib.ddb_inv_mass_matrix(h, sp, Minv.data_ptr()) == 0
+out["inv_mass_us"] = timeit(minv, max(8, args.reps // 4))
 # T-step rollout with backprop through the rollout entry points, chunks of worlds on 1..4 lanes
 T = SETS
 taus = torch.tensor(rng.uniform(-1, 1, (T, N, n)), device=dev)
