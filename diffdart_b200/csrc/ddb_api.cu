@@ -158,6 +158,8 @@ int cudaFail(ddb_handle* h, cudaError_t e, const char* what) {
 int bindTopology(ddb_handle* h, cudaStream_t s) {
   std::lock_guard<std::mutex> lock(g_mu);
   if (g_owner[h->device] == h) return DDB_OK;
+  // another handle's kernels (on any stream or lane) may still be reading the slot: switching owners drains the device first
+  if (g_owner[h->device] != nullptr) DDB_CUDA(h, cudaDeviceSynchronize());
   DDB_CUDA(h, cudaMemcpyToSymbolAsync(c_topo, &h->topo, sizeof(DevTopo), 0, cudaMemcpyHostToDevice, s));
   if (h->hasContacts) DDB_CUDA(h, contactBindTopology(&h->topo, &h->ctopo, s));
   // the host copy lives in the handle (pageable): make sure the copy has been staged before anyone frees it

@@ -66,6 +66,30 @@ def test_rollout_equals_stepwise_bitwise(N, lanes):
         assert torch.equal(r, g), (name, float((r - g).abs().max()))
 
 
+def test_rollout_dof_major_layout():
+    """The same rollout through the raw ABI with DOF-major vectors x[dof*N + world] (every step of a sequence is one such block)."""
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(4)
+    N, n, T = 300, 4, 5
+    q0, qd0, _ = random_inputs(n, N, 41)
+    rng = np.random.default_rng(42)
+    taus, gp, gv = rng.uniform(-1, 1, (T, N, n)), rng.normal(size=(T, N, n)), rng.normal(size=(T, N, n))
+    ref = rollout(desc, q0, qd0, taus, gp, gv, 2)
+    topo, params, keep = desc.to_ctypes(_abi.LAYOUT_DOF_MAJOR)
+    h = _abi._vp()
+    assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
+    tr = lambda a: cuda(np.swapaxes(a, -1, -2))  # [.., N, n] -> [.., n, N]
+    dq0, dqd0, dt, dgp, dgv = tr(q0), tr(qd0), tr(taus), tr(gp), tr(gv)
+    poses, vels, gtau = torch.empty_like(dt), torch.empty_like(dt), torch.empty_like(dt)
+    gq0, gqd0 = torch.empty_like(dq0), torch.empty_like(dq0)
+    assert lib.ddb_rollout_forward(h, None, T, dq0.data_ptr(), dqd0.data_ptr(), dt.data_ptr(), poses.data_ptr(), vels.data_ptr()) == 0
+    assert lib.ddb_rollout_backward(h, None, T, dgp.data_ptr(), dgv.data_ptr(), gq0.data_ptr(), gqd0.data_ptr(), gtau.data_ptr()) == 0
+    torch.cuda.synchronize()
+    for name, r, g in zip(("poses", "vels", "dL/dq0", "dL/dqd0", "dL/dtau"), ref, (poses, vels, gq0, gqd0, gtau)):
+        assert torch.equal(r, g.transpose(-1, -2)), name
+    lib.ddb_destroy(h)
+
+
 def test_rollout_against_oracle():
     desc = skeletons.create_multiarm_robot(3)
     N, n, T = 48, 3, 10
