@@ -38,9 +38,10 @@ WORKLOAD = ("pendulum5: 65536 five-link revolute pendulums per GPU, no contact (
 # roofline.traffic, not in the algorithmic bytes.)
 FWD_BYTES = 40 * N_DOFS
 BWD_BYTES = 64 * N_DOFS
-# DRAM traffic per whole-batch launch from the `ncu --set full` captures (profiles/r01b_ncu_full_summary.csv), bytes
-FWD_TRAFFIC = 8.03e6 + 71.99e6
-BWD_TRAFFIC = 99.73e6 + 6.46e6
+# DRAM traffic per whole-batch launch from the `ncu --set full` captures of the committed build (profiles/r01d_ncu_full_summary.csv),
+# bytes: dram__bytes_read.sum + dram__bytes_write.sum. (The forward leaves part of its 94 MB snapshot dirty in L2 when it ends.)
+FWD_TRAFFIC = 7.95e6 + 44.88e6
+BWD_TRAFFIC = 99.70e6 + 4.12e6
 # FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
 FWD_FLOPS = 4933
 BWD_FLOPS = 4245

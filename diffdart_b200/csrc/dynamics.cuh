@@ -157,11 +157,19 @@ DDB_DI void cpAsyncWaitDyn(int n) {  // n is a compile-time constant after unrol
   }
 }
 
+#ifndef DDB_STAGE_AHEAD
+#define DDB_STAGE_AHEAD 3
+#endif
+#ifndef DDB_STAGE_NBUF
+#define DDB_STAGE_NBUF 2
+#endif
 template <int NB, int BLOCK>
 struct StageGeom {
-  static constexpr int kRowsA = 10, kRowsB = 15;
-  static constexpr int kBufBase = NB >= 3 ? 0 : kRowsA * NB;  // short chains: the phase B buffers sit behind phase A
-  static constexpr int kSlots = (kRowsA * NB > kBufBase + 2 * kRowsB) ? kRowsA * NB : kBufBase + 2 * kRowsB;
+  static constexpr int kRowsA = 10, kRowsB = 15, kBufs = DDB_STAGE_NBUF;
+  // the phase B buffers reuse phase A slots when the chain is long enough for the down sweep to free them in time
+  static constexpr bool kAlias = kRowsA * NB >= kBufs * kRowsB && NB >= 3;
+  static constexpr int kBufBase = kAlias ? 0 : kRowsA * NB;
+  static constexpr int kSlots = (kRowsA * NB > kBufBase + kBufs * kRowsB) ? kRowsA * NB : kBufBase + kBufs * kRowsB;
   static constexpr size_t kBytes = (size_t)kSlots * BLOCK * sizeof(double2);
 };
 
@@ -202,7 +210,7 @@ struct StageBase {
     cpAsync16(smAddr + (unsigned)(slot * BLOCK * (int)sizeof(double2)), src);
   }
   DDB_DI static int slotA(int body, int k) { return G::kRowsA * body + (k < 6 ? k : k - 6); }
-  DDB_DI static int bufOf(int body) { return G::kBufBase + ((NB - 1 - body) & 1) * G::kRowsB; }
+  DDB_DI static int bufOf(int body) { return G::kBufBase + ((NB - 1 - body) % G::kBufs) * G::kRowsB; }
   DDB_DI static int slotB(int body, int k) { return bufOf(body) + (k < 12 ? k : k - 3); }
   DDB_DI void requestA(int body) const {
 #pragma unroll
@@ -226,18 +234,34 @@ struct StageBase {
 template <int NB, int BLOCK>
 struct StageA : StageBase<NB, BLOCK>, SnapReaders<StageA<NB, BLOCK>> {
   typedef StageBase<NB, BLOCK> B;
+  typedef StageGeom<NB, BLOCK> G;
+  // Phase A rows are requested kAhead bodies ahead of the up sweep, not all at entry: with every warp of the first wave asking
+  // for all of its rows at once (30 MB across the chip) the rows of the first body queue behind everybody's later rows.
+  static constexpr int kAhead = DDB_STAGE_AHEAD;
+  DDB_DI void requestAOrEmpty(int body) const { if (body >= 0) B::requestA(body); else cpAsyncCommit(); }
   DDB_DI void start() const {
+    if (!G::kAlias) {
 #pragma unroll
-    for (int i = NB - 1; i >= 0; i--) B::requestA(i);
-    if (NB < 3) { B::requestB(NB - 1); B::requestB(NB - 2); }
+      for (int b = 0; b < G::kBufs; b++) B::requestB(NB - 1 - b);
+    }
+#pragma unroll
+    for (int a = 0; a < kAhead; a++) requestAOrEmpty(NB - 1 - a);
   }
   DDB_DI double2 ld(int body, int k) const { return B::sm[B::slotA(body, k) * BLOCK]; }
-  // groups were committed for bodies NB-1 ... 0: body i has landed when at most i groups are pending
-  DDB_DI void beginUp(int i) const { cpAsyncWaitDyn(NB >= 3 ? i : i + 2); }  // (short chains: + the two phase B groups)
-  // the down sweep is done with bodies 0..i: their slots become the phase B buffers
+  // when body i is needed, exactly kAhead - 1 younger groups (bodies i-1 ..., possibly empty) have been committed
+  DDB_DI void beginUp(int i) const {
+    cpAsyncWait<kAhead - 1>();
+    requestAOrEmpty(i - kAhead);
+  }
+  // the down sweep is done with bodies 0..i: buffer b (slots [15 b, 15 b + 15)) is free once 10 (i + 1) >= 15 (b + 1)
   DDB_DI void endDown(int i) const {
-    if (NB >= 3 && i == 1) B::requestB(NB - 1);
-    if (NB >= 3 && i == 2) B::requestB(NB - 2);
+    if (G::kAlias) {
+#pragma unroll
+      for (int b = 0; b < G::kBufs; b++) {
+        const int need = (G::kRowsB * (b + 1) + G::kRowsA - 1) / G::kRowsA - 1;  // first i that frees buffer b
+        if (i == need) B::requestB(NB - 1 - b);
+      }
+    }
   }
   DDB_DI void beginAdj(int) const {}
   DDB_DI void endAdj(int) const {}
@@ -249,9 +273,9 @@ struct StageB : StageBase<NB, BLOCK>, SnapReaders<StageB<NB, BLOCK>> {
   DDB_DI double2 ld(int body, int k) const { return B::sm[B::slotB(body, k) * BLOCK]; }
   DDB_DI void beginUp(int) const {}
   DDB_DI void endDown(int) const {}
-  // exactly one younger group (body i-1's, possibly empty) may still be in flight
-  DDB_DI void beginAdj(int) const { cpAsyncWait<1>(); }
-  DDB_DI void endAdj(int i) const { B::requestB(i - 2); }
+  // kBufs - 1 younger groups (bodies i-1 ..., possibly empty) may still be in flight
+  DDB_DI void beginAdj(int) const { cpAsyncWait<StageGeom<NB, BLOCK>::kBufs - 1>(); }
+  DDB_DI void endAdj(int i) const { B::requestB(i - StageGeom<NB, BLOCK>::kBufs); }
 };
 
 template <int NB, bool CHAIN>

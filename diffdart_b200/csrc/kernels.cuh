@@ -127,6 +127,17 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
   StageA<NB, BLOCK> sa;
   StageB<NB, BLOCK> sb;
   constexpr bool STAGED = CHAIN && DDB_BWD_STAGE;
+  // the loss gradients are the first thing the up sweep consumes and the last thing the adjoint sweep adds: chains ask for them
+  // before the staging copies instead of at the point of use
+  double lamv[NB], gqv[NB];
+  if (CHAIN) {
+#pragma unroll
+    for (int d = 0; d < NB; d++) {
+      const size_t ix = vidx(layout, N, n, w, d);
+      lamv[d] = gqdnAdd ? gqdn[ix] + gqdnAdd[ix] : gqdn[ix];
+      gqv[d] = gqnAdd ? gqn[ix] + gqnAdd[ix] : gqn[ix];
+    }
+  }
   if (STAGED) {
     sa.init(sn, ddb_stage);
     sb.init(sn, ddb_stage);
@@ -135,7 +146,7 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
   // lambda = dL/dqd'
   auto gqnOf = [&](size_t ix) { return gqnAdd ? gqn[ix] + gqnAdd[ix] : gqn[ix]; };
   auto gqdnOf = [&](size_t ix) { return gqdnAdd ? gqdn[ix] + gqdnAdd[ix] : gqdn[ix]; };
-  auto lamOf = [&](int d) { return gqdnOf(vidx(layout, N, n, w, d)); };
+  auto lamOf = [&](int d) { return CHAIN ? lamv[d < NB ? d : 0] : gqdnOf(vidx(layout, N, n, w, d)); };
   auto muFree = [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; };
   if (STAGED) solveInvMass<NB, CHAIN>(sa, nb, lamOf, ws, muFree);
   else solveInvMass<NB, CHAIN>(sn, nb, lamOf, ws, muFree);
@@ -149,7 +160,7 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
   }
   auto out1 = [&](int d, double dq, double dqd) {
     size_t ix = vidx(layout, N, n, w, d);
-    double a = gqnOf(ix), l = gqdnOf(ix);
+    double a = CHAIN ? gqv[d < NB ? d : 0] : gqnOf(ix), l = CHAIN ? lamv[d < NB ? d : 0] : gqdnOf(ix);
     // pos-pos = I, vel-pos = dt I for R^1 joints; pos-vel^T l = -dt dPhi/dq; vel-vel^T l = l - dt dPhi/dqd
     gq[ix] = fma(-dt, dq, a);
     gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
