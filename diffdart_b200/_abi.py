@@ -126,6 +126,8 @@ def load_library():
     lib.ddb_lcp_solve.restype = C.c_int
     lib.ddb_lcp_valid.argtypes = [C.c_int32, _vp, C.c_int32, C.c_int32] + [_vp] * 7 + [C.c_int32, _vp]
     lib.ddb_lcp_valid.restype = C.c_int
+    lib.ddb_lemke_solve.argtypes = [C.c_int32, _vp, C.c_int32, C.c_int32] + [_vp] * 6
+    lib.ddb_lemke_solve.restype = C.c_int
     lib.ddb_contact_capacity.argtypes = [_vp, _ip, _ip]
     lib.ddb_contact_capacity.restype = C.c_int
     lib.ddb_contact_debug_host.argtypes = [_vp, _vp, C.c_int32] + [_vp] * 9
@@ -152,5 +154,5 @@ EXPORTED_SYMBOLS = [
     "ddb_num_dofs", "ddb_forward", "ddb_backward", "ddb_jacobians", "ddb_inv_mass_matrix", "ddb_snapshot_select",
     "ddb_snapshot_current", "ddb_snapshot_reserve", "ddb_forward_host", "ddb_backward_host", "ddb_jacobians_host",
     "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs", "ddb_contact_capacity", "ddb_contact_debug_host",
-    "ddb_contact_pgs_sweeps_host", "ddb_contact_profile_host", "ddb_rollout_forward", "ddb_rollout_backward", "ddb_set_lanes",
+    "ddb_contact_pgs_sweeps_host", "ddb_contact_profile_host", "ddb_rollout_forward", "ddb_rollout_backward", "ddb_set_lanes", "ddb_lemke_solve",
 ]

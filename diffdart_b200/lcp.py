@@ -47,3 +47,23 @@ def is_lcp_solution_valid(A, x, b, lo, hi, findex, ignore_friction_indices=False
     if rc:
         raise RuntimeError("ddb_lcp_valid failed: %s" % _abi.ERRORS.get(rc, rc))
     return out.bool()
+
+
+def lemke_solve(M, q, n_rows=None):
+    """dart::lcpsolver::Lemke for a batch of standard LCPs w = M z + q >= 0, z >= 0, z.w = 0 (Lemke.cpp:61-337).
+    M [P, n, n], q [P, n] float64 CUDA tensors (n_rows [P] int32: size of each problem, default n). Returns (z [P, n], err [P] int32,
+    pivots [P] int32); err as the reference: 0 solved, 1 iteration limit, 2 ray termination, 3 validation failed, 4 no pivot."""
+    import torch
+
+    lib = _abi.load_library()
+    M, q = M.contiguous(), q.contiguous()
+    P, n = q.shape
+    z = torch.empty_like(q)
+    err = torch.empty(P, dtype=torch.int32, device=q.device)
+    piv = torch.empty(P, dtype=torch.int32, device=q.device)
+    rc = lib.ddb_lemke_solve(q.device.index or 0, torch.cuda.current_stream(q.device).cuda_stream, P, n,
+                             None if n_rows is None else n_rows.contiguous().data_ptr(), M.data_ptr(), q.data_ptr(), z.data_ptr(),
+                             err.data_ptr(), piv.data_ptr())
+    if rc != 0:
+        raise RuntimeError("ddb_lemke_solve failed: %s" % _abi.ERRORS.get(rc, rc))
+    return z, err, piv

@@ -242,6 +242,18 @@ int ddb_lcp_solve(int32_t device, void* cuda_stream, int32_t n_problems, int32_t
                   const double* A_dev, const double* b_dev, const double* lo_dev, const double* hi_dev,
                   const int32_t* findex_dev, int32_t solver, int32_t early_termination,
                   double* x_inout_dev, int32_t* ok_out_dev);
+/*
+ * Batched Lemke solver for standard LCPs  w = M z + q >= 0, z >= 0, z.w = 0 : replaces
+ * int dart::lcpsolver::Lemke(const MatrixXd& M, const VectorXd& q, VectorXd* z) (dart/lcpsolver/Lemke.hpp:44-46, Lemke.cpp:61-337)
+ * for n_problems independent problems (complementary pivoting with the artificial variable, the reference's tolerances 1e-5 / 1e-8,
+ * 1000 pivots at most, final validate() with threshold 1e-4). M is [n_problems][n_max][n_max] row-major (only the leading
+ * n_rows[i] x n_rows[i] block is read; n_rows may be NULL = n_max everywhere, n_max <= 128); q, z_out are [n_problems][n_max];
+ * err_out[i] = the reference's return code (0 solved, 1 iteration limit, 2 ray termination, 3 validation failed, 4 no pivot; z = 0
+ * unless 0 or 3); pivots_out[i] = pivots taken (may be NULL). Not on the step path (only ODELCPSolver calls it).
+ */
+int ddb_lemke_solve(int32_t device, void* cuda_stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows_dev,
+                    const double* M_dev, const double* q_dev, double* z_out_dev, int32_t* err_out_dev, int32_t* pivots_out_dev);
+
 /* LCPUtils::isLCPSolutionValid (dart/constraint/LCPUtils.cpp:12-81, tolerance 1e-5) per problem. */
 int ddb_lcp_valid(int32_t device, void* cuda_stream, int32_t n_problems, int32_t n_max, const int32_t* n_rows_dev,
                   const double* A_dev, const double* x_dev, const double* b_dev, const double* lo_dev, const double* hi_dev,
