@@ -171,6 +171,63 @@ def contact_bench(local_rank, rank, steps=4, warmup=3):
     return e0.elapsed_time(e1) / steps, tiers, N
 
 
+ATLAS_WORLDS = 4096
+ATLAS_WORKLOAD = ("atlas: 4096 worlds per GPU of the Atlas humanoid (27 revolute joints + FreeJoint root = 33 DOFs, 35 bodies, box feet) standing on the ground "
+                  "box (BASELINE configs[4], SURVEY 8(d) C5: pose of test_AtlasGradients.cpp:222-223 + U(-0.01,0.01), qd ~ U(-0.1,0.1), tau = 0); step = "
+                  "forwardPass with the contact solve + backward through the contact solution; at N > 1 the gradient w.r.t. a parameter shared by all "
+                  "worlds (here: a torque bias, 33 doubles) is summed over the local worlds and all-reduced over NCCL once per backward")
+
+
+def atlas_bench(local_rank, rank, world_size, steps=5, warmup=2):
+    """Config 5 when the reference's URDFs are present in baseline/_ref/atlas (tests/contact_scenes.py says how to put them there)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from contact_scenes import atlas_available, atlas_on_ground, atlas_on_ground_states
+    from diffdart_b200.sharding import allreduce_shared_gradient
+    from diffdart_b200.world import BatchedWorld, LossGradient, forwardPass
+
+    if not atlas_available():
+        return None
+    N = ATLAS_WORLDS
+    q, qd, tau = atlas_on_ground_states(N, 13 + rank)
+    dev = torch.device("cuda", local_rank)
+    world = BatchedWorld(atlas_on_ground(), N, device=local_rank)
+    cu = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    world.setPositions(cu(q)); world.setVelocities(cu(qd))
+    tq = cu(tau)
+    g = torch.randn(N, q.shape[1], dtype=torch.float64, device=dev)
+    nxt, this = LossGradient(), LossGradient()
+    nxt.lossWrtPosition, nxt.lossWrtVelocity = g, g.clone()
+    shared = None
+
+    def step():
+        nonlocal shared
+        world.setForces(tq)
+        snap = forwardPass(world)
+        snap.backprop(world, this, nxt)
+        shared = allreduce_shared_gradient(this.lossWrtTorque)  # d loss / d (torque bias shared by all worlds)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    e0.record()
+    for _ in range(20):
+        allreduce_shared_gradient(this.lossWrtTorque)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    status = world.last_solver_status.cpu().numpy()
+    return {"ms_per_step": ms, "allreduce_us": e0.elapsed_time(e1) / 20 * 1e3, "finite": bool(torch.isfinite(shared).all()),
+            "tiers": {str(int(k)): int(v) for k, v in zip(*np.unique(status, return_counts=True))}}
+
+
 def contact_cpu_baseline(n_worlds=1024):
     """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
     from diffdart_b200 import skeletons
@@ -354,11 +411,18 @@ def run_ours(args):
     contact_ms, contact_tiers = float("nan"), {}
     if not args.no_contact:
         contact_ms, contact_tiers, _ = contact_bench(local_rank, rank)
+    atlas = None
+    if not args.no_contact:
+        try:
+            atlas = atlas_bench(local_rank, rank, world_size)
+        except Exception as exc:  # optional workload: report, never fail the headline
+            atlas = {"error": str(exc)[:200]}
+    atlas_ms = atlas["ms_per_step"] if atlas and "ms_per_step" in atlas else float("nan")
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -405,6 +469,13 @@ def run_ours(args):
                                                             "sample": "1024 worlds, forwardPass + the reference's Jacobian recipe on one core (%.1f s)" % cs}
                 except Exception as exc:  # the oracle's reference libraries travel prebuilt; report instead of failing the headline
                     line["contact_rich"]["cpu_baseline"] = {"unavailable": str(exc)[:200]}
+        if atlas is not None:
+            if "ms_per_step" in atlas:
+                line["atlas_contact"] = {"workload": ATLAS_WORKLOAD, "value": world_size * ATLAS_WORLDS / (atlas_ms * 1e-3), "unit": UNIT, "ms_per_step": atlas_ms,
+                                         "worlds_per_gpu": ATLAS_WORLDS, "scaling": "weak", "shared_gradient_allreduce_us_rank0": atlas["allreduce_us"],
+                                         "solver_tier_mask_hist_rank0": atlas["tiers"], "finite": atlas["finite"]}
+            else:
+                line["atlas_contact"] = atlas
         if world_size == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v1, s1 = cpu_world_steps(N_WORLDS, threads)

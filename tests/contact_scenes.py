@@ -203,3 +203,42 @@ SCENES = {
     "pendulum_on_floor": (pendulum_on_floor, pendulum_on_floor_states),
     "sphere_pendulum_on_floor": (sphere_pendulum_on_floor, sphere_pendulum_on_floor_states),
 }
+
+
+# ---- BASELINE configs[4]: Atlas with box feet on the ground box ----
+# The model files are the reference's own data (data/sdf/atlas/atlas_v3_box_colliders.urdf, ground.urdf). They are not part of
+# this repo: the scene exists when they have been copied to baseline/_ref/atlas/ (git-ignored; it travels to the GPU box):
+#   mkdir -p baseline/_ref/atlas && cp /root/reference/data/sdf/atlas/{atlas_v3_box_colliders,ground}.urdf baseline/_ref/atlas/
+import math
+import os
+
+ATLAS_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "atlas")
+
+
+def atlas_available():
+    return all(os.path.exists(os.path.join(ATLAS_DIR, f)) for f in ("atlas_v3_box_colliders.urdf", "ground.urdf"))
+
+
+def atlas_on_ground():
+    from diffdart_b200.urdf_loader import load_urdf
+
+    atlas, _ = load_urdf(os.path.join(ATLAS_DIR, "atlas_v3_box_colliders.urdf"))
+    ground, _ = load_urdf(os.path.join(ATLAS_DIR, "ground.urdf"))
+    return skeletons.WorldDescription().addSkeleton(atlas).addSkeleton(ground).setGravity([0.0, -9.81, 0.0])
+
+
+def atlas_on_ground_states(N, seed):
+    """Pose of unittests/unit/test_AtlasGradients.cpp:222-223 (root rotated by -pi/2 about x, lowered by 0.01) + U(-0.01, 0.01),
+    qd ~ U(-0.1, 0.1), tau = 0."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 33))
+    q[:, 0] = -0.5 * math.pi
+    q[:, 4] = -0.01
+    q += rng.uniform(-0.01, 0.01, (N, 33))
+    return q, rng.uniform(-0.1, 0.1, (N, 33)), np.zeros((N, 33))
+
+
+# scenes only the GPU tests run (the host emulation of a 35-body world is slow)
+GPU_SCENES = dict(SCENES)
+if atlas_available():
+    GPU_SCENES["atlas_on_ground"] = (atlas_on_ground, atlas_on_ground_states)

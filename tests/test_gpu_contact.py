@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 import torch
 
-from contact_scenes import SCENES
+from contact_scenes import GPU_SCENES as SCENES  # + Atlas on the ground when baseline/_ref/atlas holds the reference's URDFs
 from diffdart_b200 import _abi
 from diffdart_b200.world import BatchedWorld, forwardPass
 from oracle.oracle import OracleWorld
@@ -143,7 +143,7 @@ def test_contact_backward_matches_oracle(scene):
     from diffdart_b200.world import LossGradient
     make, states = SCENES[scene]
     desc = make()
-    N = 16 if scene == "box_stack" else 48
+    N = 16 if scene == "box_stack" else (12 if scene == "atlas_on_ground" else 48)
     q, qd, tau = states(N, 21)
     n = q.shape[1]
     world = BatchedWorld(desc, N)
