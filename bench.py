@@ -387,6 +387,28 @@ def run_ours(args):
     torch.cuda.synchronize(dev)
     fwd_ms = float(np.mean([e3[0].elapsed_time(e3[1]) for e3 in kev]))
     bwd_ms = float(np.mean([e3[1].elapsed_time(e3[2]) for e3 in kev]))
+    # ---- second column of SURVEY 8(d): forward + the five materialised Jacobians (BM_Cartpole_Jacobians semantics) ----
+    jac = [torch.empty(N, n, n, dtype=torch.float64, device=dev) for _ in range(5)]
+    jac_steps = max(3, min(args.steps, 40))
+
+    def jac_step(i):
+        (a, b, c, d, e), (o0, o1, o2, o3, o4) = sets[i % SETS]
+        lib.ddb_snapshot_select(h, i % SETS)
+        r1 = lib.ddb_forward(h, sp, a.data_ptr(), b.data_ptr(), c.data_ptr(), o0.data_ptr(), o1.data_ptr(), None, None, None, None)
+        r2 = lib.ddb_jacobians(h, sp, *[t.data_ptr() for t in jac])
+        if r1 or r2:
+            raise RuntimeError(lib.ddb_last_error(h).decode())
+
+    for i in range(3):
+        jac_step(i)
+    barrier()
+    jev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    jev[0].record(stream)
+    for i in range(jac_steps):
+        jac_step(i)
+    jev[1].record(stream)
+    barrier()
+    jac_ms = jev[0].elapsed_time(jev[1]) / jac_steps
     # ---- e2e: host buffers through the C ABI's host entry points, copies inside the timed region ----
     hin = [torch.tensor(a, dtype=torch.float64).pin_memory() for a in (q, qd, tau, g[0], g[1])]
     hout = [torch.empty(N, n, dtype=torch.float64).pin_memory() for _ in range(5)]
@@ -419,10 +441,10 @@ def run_ours(args):
             atlas = {"error": str(exc)[:200]}
     atlas_ms = atlas["ms_per_step"] if atlas and "ms_per_step" in atlas else float("nan")
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -448,6 +470,9 @@ def run_ours(args):
             "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms, "note": "whole-batch launches timed alone on one stream, rotating cold sets"},
             "single_step": {"value": world_size * N * args.steps / (single_ms * 1e-3), "unit": UNIT, "ms_per_step": single_ms / args.steps,
                             "path": "ddb_forward + ddb_backward per step on one stream, 8 rotating cold sets"},
+            "forward_plus_jacobians": {"value": world_size * N / (jac_ms * 1e-3), "unit": "world-steps/s", "ms_per_step": jac_ms,
+                                       "path": "ddb_forward + ddb_jacobians (pos-pos, pos-vel, vel-pos, vel-vel, force-vel as [N, n, n]) per step: the shape of "
+                                               "BM_Cartpole_Jacobians (unittests/benchmarks/bench_Jacobians.cpp:131-139) on config 2"},
             "roofline": {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": dom[4], "peak_source": peak_src,
                          "note": "FP64-pipe bound, not HBM bound: see roofline_fp64 and DESIGN.md §4"},
