@@ -80,12 +80,11 @@ template <bool FIRST>
 __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, const double* __restrict__ sc, int blk0, int r, int cnt, int lane,
                                               int fiLocal, double hi_r, double diag, double f_r, double& acc, double& hi_e, double& lo_e,
                                               double& x_new) {
-  // S[r][blk0 + jj]: below the diagonal (jj < lane) it sits in this lane's packed row, above it in row blk0 + jj
-  auto elem = [&](int jj) {
-    const int j = blk0 + jj;
-    const int idx = jj <= lane ? (r * (r + 1)) / 2 + j : (j * (j + 1)) / 2 + r;
-    return S[idx] * sc[j] * f_r;
-  };
+  // S[r][blk0 + jj] is only used by the lanes below the diagonal (jj < lane), where it sits in this lane's packed row: one base
+  // pointer per block instead of index arithmetic per step (the other lanes read a neighbouring entry of the shared array and drop it)
+  const double* __restrict__ rowS = S + (r * (r + 1)) / 2 + blk0;
+  const double* __restrict__ scb = sc + blk0;
+  auto elem = [&](int jj) { return rowS[jj] * scb[jj] * f_r; };
   double a_next = elem(0);
 #pragma unroll 8
   for (int jj = 0; jj < cnt; jj++) {

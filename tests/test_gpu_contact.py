@@ -65,7 +65,10 @@ def test_contact_step_matches_oracle(scene):
     for w in range(N):
         r = o.step_contacts(q[w], qd[w], tau[w])
         assert list(counts[w]) == [len(r["contacts"]), len(r["x"]), r["n_groups"], r["tier_mask"]], w
-        assert np.allclose(qdn[w], r["qd_next"], rtol=1e-9, atol=1e-11), w
+        # worlds solved by PGS (tier bits 4 / 8) agree to the north-star tolerance for contact-rich solves: the GPU's Gauss-Seidel sums
+        # a row in another order than the scalar solver, and its stopping rule is relative (1e-8)
+        tol = (1e-6, 1e-8) if r["tier_mask"] & 12 else (1e-9, 1e-11)
+        assert np.allclose(qdn[w], r["qd_next"], rtol=tol[0], atol=tol[1]), w
         assert np.allclose(qn[w], r["q_next"], rtol=0, atol=1e-14), w
         if w % 37 == 0 and len(r["x"]):
             _, contacts, x = contact_debug(world, w)
