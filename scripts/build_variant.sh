@@ -8,5 +8,5 @@ NAME=$1; shift
 mkdir -p $HERE/diffdart_b200/lib/variants /tmp/ddbvar
 nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC -Xptxas -v --expt-relaxed-constexpr -diag-suppress 549 \
   --split-compile 0 $@ -c -o /tmp/ddbvar/ddb_api_$NAME.o $HERE/diffdart_b200/csrc/ddb_api.cu 2> $HERE/diffdart_b200/lib/variants/ptxas_$NAME.log
-nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $HERE/diffdart_b200/lib/variants/libddb_$NAME.so /tmp/ddbvar/ddb_api_$NAME.o $HERE/diffdart_b200/lib/lcp_api.o
+nvcc -gencode arch=compute_100a,code=sm_100a -shared -o $HERE/diffdart_b200/lib/variants/libddb_$NAME.so /tmp/ddbvar/ddb_api_$NAME.o $HERE/diffdart_b200/lib/lcp_api.o $HERE/diffdart_b200/lib/lemke_api.o
 grep -A3 "k_forwardILi5ELb1\|k_backwardILi5ELb1" $HERE/diffdart_b200/lib/variants/ptxas_$NAME.log | grep "spill\|Used" 
