@@ -139,9 +139,15 @@ class WorldDescription:
         self.gravity = np.array([0.0, 0.0, -9.81])
         self.time_step = 1e-3
         self.contact_clipping_depth = 0.03
+        self.max_contacts = 0  # 0 = the library default (64 contacts, 192 LCP rows per world); sizes the contact scratch and the per-slot record
 
     def setGravity(self, g):
         self.gravity = np.asarray(g, dtype=np.float64)
+        return self
+
+    def setMaxContacts(self, n):
+        """Capacity of the contact stage per world (ddb_params.reserved[0]); worlds that exceed it report bit 8 in their status."""
+        self.max_contacts = int(n)
         return self
 
     def setTimeStep(self, dt):
@@ -208,6 +214,7 @@ class WorldDescription:
         params.contact_clipping_depth = self.contact_clipping_depth
         params.layout = layout
         params.n_snapshot_slots = n_snapshot_slots
+        params.reserved[0] = self.max_contacts
         return topo, params, (bodies, lims)
 
 

@@ -238,7 +238,39 @@ def atlas_on_ground_states(N, seed):
     return q, rng.uniform(-0.1, 0.1, (N, 33)), np.zeros((N, 33))
 
 
+# ---- BASELINE configs[3]: a half-cheetah-style URDF walker on the ground (tests/fixtures/walker.urdf, written for this repo) ----
+WALKER_URDF = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "walker.urdf")
+
+
+def walker_on_ground(max_contacts=16):
+    from diffdart_b200.urdf_loader import load_urdf
+
+    walker, _ = load_urdf(WALKER_URDF)
+    w = skeletons.WorldDescription().addSkeleton(walker).setMaxContacts(max_contacts)
+    _floor(w)
+    return w
+
+
+def walker_on_ground_states(N, seed):
+    """Standing pose with both feet 0-4 mm inside the floor (foot boxes reach 0.06 m below the ankles: back leg 0.59 + 0.06, front leg
+    0.48 + 0.06, so the torso is pitched to level them), small joint noise, qd ~ U(-0.3, 0.3), joint torques ~ U(-5, 5) on the legs."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 9))
+    pitch = np.arcsin((0.65 - 0.54) / 1.0)          # front hip lower than the back hip
+    q[:, 2] = pitch + rng.uniform(-0.002, 0.002, N)
+    q[:, 1] = 0.595 - rng.uniform(5e-4, 4e-3, N)     # ankles at 0.06 - depth: the foot boxes dip 0.5-4 mm into the floor
+    q[:, 0] = rng.uniform(-0.5, 0.5, N)
+    q[:, 3:] = rng.uniform(-0.01, 0.01, (N, 6))
+    q[:, 3:6] -= q[:, 2:3] * np.array([1.0, 0.0, 0.0])   # legs hang vertically: hip angle cancels the pitch
+    q[:, 6:9] -= q[:, 2:3] * np.array([1.0, 0.0, 0.0])
+    qd = rng.uniform(-0.3, 0.3, (N, 9))
+    tau = np.zeros((N, 9))
+    tau[:, 3:] = rng.uniform(-5, 5, (N, 6))
+    return q, qd, tau
+
+
 # scenes only the GPU tests run (the host emulation of a 35-body world is slow)
 GPU_SCENES = dict(SCENES)
+GPU_SCENES["walker_on_ground"] = (walker_on_ground, walker_on_ground_states)
 if atlas_available():
     GPU_SCENES["atlas_on_ground"] = (atlas_on_ground, atlas_on_ground_states)
