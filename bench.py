@@ -228,6 +228,44 @@ def atlas_bench(local_rank, rank, world_size, steps=5, warmup=2):
             "tiers": {str(int(k)): int(v) for k, v in zip(*np.unique(status, return_counts=True))}}
 
 
+WALKER_WORLDS, WALKER_STEPS = 32768, 20
+WALKER_WORKLOAD = ("walker: 32768 worlds per GPU of a half-cheetah-style URDF walker (9 DOFs, box feet; tests/fixtures/walker.urdf) on the ground (BASELINE "
+                   "configs[3] style), one 20-step trajectory rollout with backprop through the contact solutions via dart_rollout (loss = |q_T|^2 + |qd_T|^2); "
+                   "scripts/walker_rollout_bench.py runs the 100-step version")
+
+
+def walker_bench(local_rank, rank):
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from contact_scenes import walker_on_ground, walker_on_ground_states
+    from diffdart_b200.rollout import dart_rollout
+    from diffdart_b200.world import BatchedWorld
+
+    N, T = WALKER_WORLDS, WALKER_STEPS
+    dev = torch.device("cuda", local_rank)
+    q, qd, tau = walker_on_ground_states(N, 11 + rank)
+    world = BatchedWorld(walker_on_ground(), N, device=local_rank)
+    cu = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    q0, qd0 = cu(q).requires_grad_(), cu(qd).requires_grad_()
+    taus = cu(np.broadcast_to(tau, (T, N, 9)).copy()).requires_grad_()
+
+    def run():
+        for t in (q0, qd0, taus):
+            t.grad = None
+        poses, vels = dart_rollout(world, q0, qd0, taus)
+        ((poses[-1] ** 2).sum() + (vels[-1] ** 2).sum()).backward()
+
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    return {"ms_per_rollout": e0.elapsed_time(e1), "finite": bool(torch.isfinite(taus.grad).all() and torch.isfinite(q0.grad).all())}
+
+
 def contact_cpu_baseline(n_worlds=1024):
     """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
     from diffdart_b200 import skeletons
@@ -440,11 +478,18 @@ def run_ours(args):
         except Exception as exc:  # optional workload: report, never fail the headline
             atlas = {"error": str(exc)[:200]}
     atlas_ms = atlas["ms_per_step"] if atlas and "ms_per_step" in atlas else float("nan")
+    walker = None
+    if not args.no_contact:
+        try:
+            walker = walker_bench(local_rank, rank)
+        except Exception as exc:  # optional workload: report, never fail the headline
+            walker = {"error": str(exc)[:200]}
+    walker_ms = walker["ms_per_rollout"] if walker and "ms_per_rollout" in walker else float("nan")
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -501,6 +546,13 @@ def run_ours(args):
                                          "solver_tier_mask_hist_rank0": atlas["tiers"], "finite": atlas["finite"]}
             else:
                 line["atlas_contact"] = atlas
+        if walker is not None:
+            if "ms_per_rollout" in walker:
+                line["walker_rollout"] = {"workload": WALKER_WORKLOAD, "value": world_size * WALKER_WORLDS * WALKER_STEPS / (walker_ms * 1e-3), "unit": UNIT,
+                                          "ms_per_rollout": walker_ms, "worlds_per_gpu": WALKER_WORLDS, "rollout_steps": WALKER_STEPS, "scaling": "weak",
+                                          "finite": walker["finite"]}
+            else:
+                line["walker_rollout"] = walker
         if world_size == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v1, s1 = cpu_world_steps(N_WORLDS, threads)
