@@ -285,7 +285,9 @@ def run_reference(args):
     if rank != 0:
         return 0
     threads = os.cpu_count() or 1
-    sample = 16384  # worlds per step (bounded sample of the 65536-world batch)
+    # worlds per step: a bounded sample of the 65536-world batch, sized so that K steps stay within 3e6 .. 8e6 world-steps (tens of seconds on 16 threads)
+    # (not below 4096 worlds: smaller steps are dominated by starting the thread pool, which would understate the CPU arm)
+    sample = int(min(16384, max(4096, (200 * 16384 // max(args.steps, 1)) // 256 * 256)))
     for _ in range(max(args.warmup, 0)):
         cpu_world_steps(2048, threads)
     t0 = time.perf_counter()
@@ -582,8 +584,6 @@ def main():
     ap.add_argument("--lanes", type=int, default=2, help="internal streams the rollout spreads chunks of worlds over")
     args = ap.parse_args()
     if args.impl == "reference":
-        if args.steps == 2000:
-            args.steps, args.warmup = 5, 1
         return run_reference(args)
     return run_ours(args)
 
