@@ -130,6 +130,10 @@ def load_library():
     lib.ddb_lemke_solve.restype = C.c_int
     lib.ddb_contact_capacity.argtypes = [_vp, _ip, _ip]
     lib.ddb_contact_capacity.restype = C.c_int
+    lib.ddb_lcp_cache_get.argtypes = [_vp, _vp, _vp, _vp]
+    lib.ddb_lcp_cache_get.restype = C.c_int
+    lib.ddb_lcp_cache_set.argtypes = [_vp, _vp, _vp, _vp]
+    lib.ddb_lcp_cache_set.restype = C.c_int
     lib.ddb_contact_debug_host.argtypes = [_vp, _vp, C.c_int32] + [_vp] * 9
     lib.ddb_contact_debug_host.restype = C.c_int
     lib.ddb_collide_pairs.argtypes = [C.c_int32, _vp, C.c_int32] + [_vp] * 8
@@ -155,4 +159,5 @@ EXPORTED_SYMBOLS = [
     "ddb_snapshot_current", "ddb_snapshot_reserve", "ddb_forward_host", "ddb_backward_host", "ddb_jacobians_host",
     "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs", "ddb_contact_capacity", "ddb_contact_debug_host",
     "ddb_contact_pgs_sweeps_host", "ddb_contact_profile_host", "ddb_rollout_forward", "ddb_rollout_backward", "ddb_set_lanes", "ddb_lemke_solve",
+    "ddb_lcp_cache_get", "ddb_lcp_cache_set",
 ]

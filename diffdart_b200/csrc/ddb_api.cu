@@ -95,8 +95,11 @@ KernelTable pickTable(int nb, bool chain) {
   return Launch<DDB_MAX_BODIES, false>::table();
 }
 
-// per-device owner of the __constant__ topology slot
-std::mutex g_mu;
+// The __constant__ topology slot of a device has one owner (handle) at a time. Every entry point that launches kernels holds
+// the device's mutex from the bind to its last launch (ApiScope), so host threads driving different handles on one GPU cannot
+// swap the topology between another thread's bind and its kernels. Recursive: the rollout entry points call ddb_forward /
+// ddb_backward.
+std::recursive_mutex g_devMu[64];
 const void* g_owner[64] = {nullptr};
 
 }  // namespace
@@ -137,6 +140,9 @@ struct ddb_handle {
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
   size_t stageDoubles = 0;
+  // the upload of this handle's topology into constant memory: the stream it was ordered on and an event behind it
+  cudaEvent_t topoReady = nullptr;
+  cudaStream_t topoStream = nullptr;
 };
 
 namespace {
@@ -154,15 +160,27 @@ int cudaFail(ddb_handle* h, cudaError_t e, const char* what) {
     if (e__ != cudaSuccess) return cudaFail(h, e__, #call); \
   } while (0)
 
-// make this handle's topology the one in constant memory (stream-ordered)
+struct ApiScope {
+  std::unique_lock<std::recursive_mutex> lk;
+  explicit ApiScope(const ddb_handle* h) : lk(g_devMu[h->device & 63]) {}
+};
+
+// make this handle's topology the one in constant memory (stream-ordered); the caller holds the device's ApiScope
 int bindTopology(ddb_handle* h, cudaStream_t s) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  if (g_owner[h->device] == h) return DDB_OK;
+  if (g_owner[h->device] == h) {
+    // the upload was ordered on another stream: this stream's kernels must not overtake it
+    if (s != h->topoStream) DDB_CUDA(h, cudaStreamWaitEvent(s, h->topoReady, 0));
+    return DDB_OK;
+  }
   // another handle's kernels (on any stream or lane) may still be reading the slot: switching owners drains the device first
   if (g_owner[h->device] != nullptr) DDB_CUDA(h, cudaDeviceSynchronize());
+  g_owner[h->device] = nullptr;
+  if (!h->topoReady) DDB_CUDA(h, cudaEventCreateWithFlags(&h->topoReady, cudaEventDisableTiming));
+  // (the host copy lives in the handle, pageable: the runtime stages it before the call returns)
   DDB_CUDA(h, cudaMemcpyToSymbolAsync(c_topo, &h->topo, sizeof(DevTopo), 0, cudaMemcpyHostToDevice, s));
   if (h->hasContacts) DDB_CUDA(h, contactBindTopology(&h->topo, &h->ctopo, s));
-  // the host copy lives in the handle (pageable): make sure the copy has been staged before anyone frees it
+  DDB_CUDA(h, cudaEventRecord(h->topoReady, s));
+  h->topoStream = s;
   g_owner[h->device] = h;
   return DDB_OK;
 }
@@ -355,12 +373,11 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
 
 int ddb_destroy(ddb_handle* h) {
   if (!h) return DDB_OK;
-  {
-    std::lock_guard<std::mutex> lock(g_mu);
-    if (g_owner[h->device] == h) g_owner[h->device] = nullptr;
-  }
+  ApiScope scope(h);
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
+  if (g_owner[h->device] == h) g_owner[h->device] = nullptr;
+  if (h->topoReady) cudaEventDestroy(h->topoReady);
   for (double* s : h->slots) if (s) cudaFree(s);
   if (h->lim_dev) cudaFree(h->lim_dev);
   if (h->stage) cudaFree(h->stage);
@@ -409,6 +426,7 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
                 double* lcp_cache_inout, int32_t* n_rows_inout, int32_t* active_set_out, int32_t* status_out) {
   if (!h || !q || !qd || !tau || !qn || !qdn) return fail(h, DDB_ERR_INVALID, "ddb_forward: null pointer");
   cudaStream_t s = (cudaStream_t)stream;
+  ApiScope scope(h);
   int rc = enter(h, s);
   if (rc) return rc;
   h->k.fwd(s, h->N, 0, h->N, q, qd, tau, qn, qdn, h->slots[h->cur]);
@@ -427,6 +445,27 @@ int ddb_forward(ddb_handle* h, void* stream, const double* q, const double* qd, 
       DDB_CUDA(h, cudaMemcpy2DAsync(status_out, sizeof(int), h->ccounts + 3, 4 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToDevice, s));
   }
   h->slotValid[h->cur] = 1;
+  return DDB_OK;
+}
+
+// World::getCachedLCPSolution / setCachedLCPSolution (BoxedLcpConstraintSolver.cpp:174-186) for every world: the solution the
+// handle carries from step to step when ddb_forward is given no cache of the caller's. [N][max_rows] doubles and [N] row counts.
+int ddb_lcp_cache_get(ddb_handle* h, void* stream, double* cache_out, int32_t* n_rows_out) {
+  if (!h || !cache_out || !n_rows_out) return fail(h, DDB_ERR_INVALID, "ddb_lcp_cache_get: null pointer");
+  if (!h->hasContacts) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  DDB_CUDA(h, cudaMemcpyAsync(cache_out, h->lcp_cache, (size_t)h->N * h->kmax * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(h, cudaMemcpyAsync(n_rows_out, h->n_cache, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return DDB_OK;
+}
+int ddb_lcp_cache_set(ddb_handle* h, void* stream, const double* cache, const int32_t* n_rows) {
+  if (!h || !cache || !n_rows) return fail(h, DDB_ERR_INVALID, "ddb_lcp_cache_set: null pointer");
+  if (!h->hasContacts) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");
+  cudaStream_t s = (cudaStream_t)stream;
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  DDB_CUDA(h, cudaMemcpyAsync(h->lcp_cache, cache, (size_t)h->N * h->kmax * sizeof(double), cudaMemcpyDeviceToDevice, s));
+  DDB_CUDA(h, cudaMemcpyAsync(h->n_cache, n_rows, (size_t)h->N * sizeof(int), cudaMemcpyDeviceToDevice, s));
   return DDB_OK;
 }
 
@@ -482,6 +521,7 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");
   cudaStream_t s = (cudaStream_t)stream;
+  ApiScope scope(h);
   int rc = enter(h, s);
   if (rc) return rc;
   if (h->hasContacts) {
@@ -502,6 +542,7 @@ int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* v
   if (!h) return DDB_ERR_INVALID;
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_jacobians: no forward pass retained in the current snapshot slot");
   cudaStream_t s = (cudaStream_t)stream;
+  ApiScope scope(h);
   int rc = enter(h, s);
   if (rc) return rc;
   if (h->hasContacts) {
@@ -540,6 +581,7 @@ int ddb_inv_mass_matrix(ddb_handle* h, void* stream, double* minv) {
   if (!h || !minv) return fail(h, DDB_ERR_INVALID, "ddb_inv_mass_matrix: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_inv_mass_matrix: no forward pass retained in the current snapshot slot");
   cudaStream_t s = (cudaStream_t)stream;
+  ApiScope scope(h);
   int rc = enter(h, s);
   if (rc) return rc;
   h->k.minv(s, h->N, h->slots[h->cur], minv);
@@ -562,6 +604,7 @@ __global__ void k_add_inplace(size_t n, double* __restrict__ a, const double* __
 int ddb_rollout_forward(ddb_handle* h, void* stream, int32_t T, const double* q0, const double* qd0, const double* tau, double* q_seq,
                         double* qd_seq) {
   if (!h || T < 1 || !q0 || !qd0 || !tau || !q_seq || !qd_seq) return fail(h, DDB_ERR_INVALID, "ddb_rollout_forward: bad argument");
+  ApiScope scope(h);
   int rc = ddb_snapshot_reserve(h, T, nullptr);
   if (rc) return rc;
   cudaStream_t s = (cudaStream_t)stream;
@@ -603,6 +646,7 @@ int ddb_rollout_forward(ddb_handle* h, void* stream, int32_t T, const double* q0
 int ddb_rollout_backward(ddb_handle* h, void* stream, int32_t T, const double* g_q_seq, const double* g_qd_seq, double* g_q0, double* g_qd0,
                          double* g_tau) {
   if (!h || T < 1 || !g_q_seq || !g_qd_seq || !g_q0 || !g_qd0 || !g_tau) return fail(h, DDB_ERR_INVALID, "ddb_rollout_backward: bad argument");
+  ApiScope scope(h);
   if ((int)h->slots.size() < T) return fail(h, DDB_ERR_STATE, "ddb_rollout_backward: fewer retained steps than T");
   for (int t = 0; t < T; t++)
     if (!h->slotValid[t]) return fail(h, DDB_ERR_STATE, "ddb_rollout_backward: a step of the rollout has no retained forward pass");
@@ -692,13 +736,16 @@ static int enqueueHostChunks(ddb_handle* h, int kind, const void* const* ptr, in
 }
 
 static int runHostChunked(ddb_handle* h, int kind, const void* const* ptr) {
-  int rc = enter(h, h->hstream);
-  if (rc) return rc;
-  rc = ensureLanes(h);
-  if (rc) return rc;
   static const int K = envInt("DDB_HOST_CHUNKS", 2);
-  rc = enqueueHostChunks(h, kind, ptr, K);
-  if (rc) return rc;
+  {
+    ApiScope scope(h);  // released before the host waits for the device
+    int rc = enter(h, h->hstream);
+    if (rc) return rc;
+    rc = ensureLanes(h);
+    if (rc) return rc;
+    rc = enqueueHostChunks(h, kind, ptr, K);
+    if (rc) return rc;
+  }
   for (int c = 0; c < K; c++) { int w0, w1; chunkRange(h->N, K, c, &w0, &w1); h->launches += w1 > w0; }
   DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
   return DDB_OK;

@@ -148,7 +148,10 @@ inline int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out
 }
 
 
-// shapes, reactive flags (skeleton has DOFs), collidable pairs in collision-object order, capacities
+// shapes, reactive flags, collidable pairs in collision-object order, capacities.
+// BodyNode::isReactive (BodyNode.cpp:1999-2018) is per body: the skeleton is mobile and the body depends on at least one
+// generalized coordinate, i.e. the body itself or one of its ancestors hangs on a joint with DOFs. A welded root link of a
+// fixed-base robot (world -> fixed -> base) is not reactive although its skeleton moves.
 inline int foldContactTopology(const ddb_topology* topo, const ddb_params* params, ContactTopo& ct, std::string& err) {
   const int nb = topo->n_bodies;
     std::memset(&ct, 0, sizeof(ct));
@@ -158,12 +161,15 @@ inline int foldContactTopology(const ddb_topology* topo, const ddb_params* param
     for (int i = 0; i < nb; i++) nskel = std::max(nskel, topo->bodies[i].skeleton + 1);
     if (nskel > DDB_MAX_BODIES) { err = "too many skeletons"; return DDB_ERR_INVALID; }
     ct.nskel = nskel;
-    std::vector<char> skelHasDof(nskel, 0);
-    for (int i = 0; i < nb; i++) if (topo->bodies[i].joint_type != DDB_JOINT_WELD) skelHasDof[topo->bodies[i].skeleton] = 1;
+    std::vector<char> dependsOnDof(nb, 0);  // bodies are listed parent-before-child (checked by foldTopology)
+    for (int i = 0; i < nb; i++) {
+      const int p = topo->bodies[i].parent;
+      dependsOnDof[i] = topo->bodies[i].joint_type != DDB_JOINT_WELD || (p >= 0 && p < i && dependsOnDof[p]);
+    }
     for (int i = 0; i < nb; i++) {
       const ddb_body& sb = topo->bodies[i];
       ShapeDesc& sd = ct.shape[i];
-      sd.shape = sb.shape_type; sd.skel = sb.skeleton; sd.reactive = skelHasDof[sb.skeleton];
+      sd.shape = sb.shape_type; sd.skel = sb.skeleton; sd.reactive = dependsOnDof[i];
       sd.friction = sb.friction; sd.restitution = sb.restitution;
       for (int k = 0; k < 3; k++) { sd.size[k] = sb.shape_size[k]; sd.offP[k] = sb.shape_offset.p[k]; }
       for (int k = 0; k < 9; k++) sd.offR[k] = sb.shape_offset.r[k];

@@ -268,7 +268,8 @@ k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL,
   const int st = contactBackwardWorld<NB>(sn, KL, keep_d + (size_t)w * KL.doubles(), keep_i + (size_t)w * KL.ints(), bw, ld, li, gqn, gqdn, gq,
                                           gqd, gtau, layout, N, w, 1);
   if (status) status[w] = st;
-  if (c_topo.has_limits) {
+  // clipLossGradientsToBounds belongs to backprop() only (BackpropSnapshot.cpp:374-428); the Jacobian getters pass no limits
+  if (c_topo.has_limits && lim.pos_lo) {
     const int n = c_topo.nd;
     const double* clip = clipSection(snap, c_topo.nb, N);
     for (int d = 0; d < n; d++) {
@@ -313,26 +314,31 @@ void contactScratchSizes(int N, int nb, int nd, int cmax, int kmax, size_t* wd, 
   *li = warps * lcpScratchInts(kmax) * 32;     // interleaved layout of k_lcp_solve's callers valid too)
 }
 // DDB_CONTACT_PROFILE=1: clock64 ticks summed over worlds per section of the contact stage (see ContactWork::mark)
-static long long* contactProfileBuffer() {
-  static long long* buf = nullptr;
-  static bool init = false;
-  if (!init) {
-    init = true;
+static long long* contactProfileBuffer() {  // one buffer per device (the current one)
+  static long long* buf[64] = {nullptr};
+  static bool init[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  if (!init[dev]) {
+    init[dev] = true;
     const char* e = getenv("DDB_CONTACT_PROFILE");
-    if (e && e[0] == '1' && cudaMalloc(&buf, 16 * sizeof(long long)) == cudaSuccess) cudaMemset(buf, 0, 16 * sizeof(long long));
-    else buf = nullptr;
+    if (e && e[0] == '1' && cudaMalloc(&buf[dev], 16 * sizeof(long long)) == cudaSuccess) cudaMemset(buf[dev], 0, 16 * sizeof(long long));
+    else buf[dev] = nullptr;
   }
-  return buf;
+  return buf[dev];
 }
 template <int CAP>
 static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
                                  const PgsOptions& pgs) {
   const size_t bytes = (size_t)((CAP * (CAP + 1)) / 2 + 6 * CAP) * sizeof(double) + CAP * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(k_pgs_warp<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  static bool configured[64] = {false};  // per instantiation and device: the attribute belongs to the function in that context
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (!configured[dev & 63]) {
+    e = cudaFuncSetAttribute(k_pgs_warp<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return e;
-    configured = true;
+    configured[dev & 63] = true;
   }
   k_pgs_warp<CAP><<<N, 32, bytes, s>>>(N, kmax, nLow, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
   return cudaGetLastError();

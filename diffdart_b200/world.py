@@ -125,7 +125,7 @@ class BatchedWorld:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- raw batched calls ----
-    def step_raw(self, q, qd, tau, slot):
+    def step_raw(self, q, qd, tau, slot, idempotent=False):
         qn, qdn = torch.empty_like(q), torch.empty_like(q)
         rc = self._lib.ddb_snapshot_select(self._h, slot)
         _check(self._lib, self._h, rc, "ddb_snapshot_select")
@@ -137,8 +137,17 @@ class BatchedWorld:
             # the active set (ConstraintMapping per LCP row) and the solver tier are returned per world
             active = torch.empty(self.N, km.value, dtype=torch.int32, device=self.device)
             status = torch.empty(self.N, dtype=torch.int32, device=self.device)
+        cache = nrows = None
+        if idempotent and km.value > 0:
+            # forwardPass(world, idempotent=True) restores the solver's cached solution (RestorableSnapshot.cpp:23,32): the step
+            # works on a scratch copy of the cache, which is dropped, so the handle's own cache stays as it was
+            cache = torch.empty(self.N, km.value, dtype=torch.float64, device=self.device)
+            nrows = torch.empty(self.N, dtype=torch.int32, device=self.device)
+            rc = self._lib.ddb_lcp_cache_get(self._h, self._stream(), cache.data_ptr(), nrows.data_ptr())
+            _check(self._lib, self._h, rc, "ddb_lcp_cache_get")
         rc = self._lib.ddb_forward(self._h, self._stream(), q.data_ptr(), qd.data_ptr(), tau.data_ptr(), qn.data_ptr(),
-                                   qdn.data_ptr(), None, None, None if active is None else active.data_ptr(),
+                                   qdn.data_ptr(), None if cache is None else cache.data_ptr(),
+                                   None if nrows is None else nrows.data_ptr(), None if active is None else active.data_ptr(),
                                    None if status is None else status.data_ptr())
         _check(self._lib, self._h, rc, "ddb_forward")
         self.last_active_set, self.last_solver_status = active, status
@@ -249,10 +258,11 @@ class BackpropSnapshot:
 
 def forwardPass(world, idempotent=False):
     """dart.neural.forwardPass: take one step of every world, return the snapshot.
-    idempotent=True leaves the world's state untouched (NeuralUtils.cpp:29-33,61-62)."""
+    idempotent=True leaves the world untouched: positions, velocities, forces and the constraint solver's cached LCP solution
+    (NeuralUtils.cpp:29-33,61-62 through RestorableSnapshot.cpp:18-33)."""
     q, qd, tau = world._q, world._qd, world._tau
     slot = world._acquire_slot()
-    qn, qdn = world.step_raw(q, qd, tau, slot)
+    qn, qdn = world.step_raw(q, qd, tau, slot, idempotent=idempotent)
     snap = BackpropSnapshot(world, slot, (q, qd, tau), (qn, qdn))
     if not idempotent:
         world._q, world._qd = qn, qdn

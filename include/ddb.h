@@ -20,6 +20,8 @@
  *  - Every function returns 0 on success, a DDB_ERR_* code otherwise;
  *    ddb_last_error() returns a human-readable host string.
  *  - There is no CPU fallback: without a CUDA device ddb_create fails.
+ *  - Threading: a handle is not thread-safe (neither is a World); different handles may be driven from different
+ *    host threads, also on one device: entry points that launch kernels serialise per device while they enqueue work.
  */
 #ifndef DDB_H_
 #define DDB_H_
@@ -174,6 +176,14 @@ int ddb_jacobians(ddb_handle* h, void* cuda_stream,
  * -3 ILLEGAL, -4 IRRELEVANT = no such row, >= 0 UPPER_BOUND pointing at its normal row).
  */
 int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t* max_rows);
+/*
+ * Replaces World::getCachedLCPSolution / setCachedLCPSolution (BoxedLcpConstraintSolver.cpp:174-186; saved and restored by
+ * RestorableSnapshot.cpp:23,32 for forwardPass(world, idempotent=true), NeuralUtils.cpp:29-33,61-62) for every world: the
+ * solver's cached solution the handle carries from step to step when ddb_forward is given no cache of the caller's.
+ * cache [N][max_rows] doubles, n_rows [N] (device pointers, copies ordered on `stream`).
+ */
+int ddb_lcp_cache_get(ddb_handle* h, void* cuda_stream, double* cache_out_dev, int32_t* n_rows_out_dev);
+int ddb_lcp_cache_set(ddb_handle* h, void* cuda_stream, const double* cache_dev, const int32_t* n_rows_dev);
 int ddb_contact_debug_host(ddb_handle* h, int32_t* counts, int32_t world, double* contacts, int32_t* bodies, int32_t* dims,
                            double* A, double* b, double* lo, double* hi, double* x, int32_t* findex);
 

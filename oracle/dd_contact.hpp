@@ -103,6 +103,13 @@ inline int sphereSphere(double r0, const double* c0, double r1, const double* c1
   return 1;
 }
 
+// BodyNode::isReactive (BodyNode.cpp:1999-2018): the skeleton is mobile and the body has dependent generalized
+// coordinates, i.e. the body or one of its ancestors hangs on a joint with DOFs (per body, not per skeleton)
+inline bool isReactive(const Model& M, int body) {
+  for (int i = body; i >= 0; i = M.b[i].parent) if (M.b[i].ndof > 0) return true;
+  return false;
+}
+
 // all-pairs narrow phase in collision-object order (one shape per body, flattened body order)
 inline std::vector<Contact> collideWorld(const Model& M, const Dyn<double>& d) {
   std::vector<Contact> total;
@@ -112,6 +119,9 @@ inline std::vector<Contact> collideWorld(const Model& M, const Dyn<double>& d) {
     for (size_t b = a + 1; b < obj.size(); b++) {
       const int i = obj[a], j = obj[b];
       if (M.b[i].skel == M.b[j].skel) continue;  // self-collision checking is off by default (CollisionFilter.cpp:137-140)
+      // a pair of two non-reactive bodies never yields an active constraint (ContactConstraint.cpp:342); it is left out of the
+      // contact list here as in the CUDA pair table, so the reported contact counts agree
+      if (!isReactive(M, i) && !isReactive(M, j)) continue;
       double T1[12], T2[12];
       poseOf(d.b[i].W, M.b[i].shapeOffset, T1);
       poseOf(d.b[j].W, M.b[j].shapeOffset, T2);
@@ -157,10 +167,6 @@ struct Constraint {  // ContactConstraint
   Contact contact;
 };
 
-inline bool isReactive(const Model& M, int body) {  // skeleton is mobile and has DOFs
-  for (int i = 0; i < M.nb; i++) if (M.b[i].skel == M.b[body].skel && M.b[i].ndof > 0) return true;
-  return false;
-}
 
 inline void tangentBasis(const Vec3<double>& n, Vec3<double>& t1, Vec3<double>& t2) {  // ContactConstraint.cpp:716-746, first direction = z
   Vec3<double> t = cross(v3<double>(0, 0, 1), n);

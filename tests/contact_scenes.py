@@ -193,7 +193,33 @@ def sphere_pendulum_on_floor_states(N, seed):
     return q, qd, tau
 
 
+def fixed_base_arm_on_floor():
+    """A fixed-base arm as DartLoader builds it from a URDF (world -> fixed -> base): the welded base box sits 2 mm inside the floor.
+    BodyNode::isReactive is per body (BodyNode.cpp:1999-2018): the base depends on no generalized coordinate, so its contacts with the
+    floor never become constraints, while the tip box of the two revolute links does touch the floor and does."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    s = skeletons.Skeleton("arm")
+    base = s.createWeldJointAndBodyNodePair(None).setTransformFromParentBodyNode(p=[0, 0, 0.098])
+    base.setBoxShape([0.3, 0.3, 0.2])
+    a = s.createRevoluteJointAndBodyNodePair(base).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, 1.402])
+    a.setLocalCOM([0, 0, -0.4])
+    b = s.createRevoluteJointAndBodyNodePair(a).setAxis([0, 1, 0]).setTransformFromParentBodyNode(p=[0, 0, -0.8])
+    b.setLocalCOM([0, 0, -0.3]).setBoxShape([0.2, 0.2, 0.2], p=[0, 0, -0.6])
+    w.addSkeleton(s)
+    return w
+
+
+def fixed_base_arm_on_floor_states(N, seed):
+    rng = np.random.default_rng(seed)
+    q = rng.uniform(-0.02, 0.02, (N, 2))   # as pendulum_on_floor: the tip box dips into the floor (bodies of one skeleton do not collide)
+    qd = rng.uniform(-0.5, 0.5, (N, 2))
+    tau = rng.uniform(-1, 1, (N, 2))
+    return q, qd, tau
+
+
 SCENES = {
+    "fixed_base_arm_on_floor": (fixed_base_arm_on_floor, fixed_base_arm_on_floor_states),
     "box_stack": (box_stack, box_stack_states),
     "free_box_on_floor": (free_box_on_floor, free_box_on_floor_states),
     "box_on_pedestal": (box_on_pedestal, box_on_pedestal_states),

@@ -198,9 +198,10 @@ def test_contact_backward_matches_oracle(scene):
     assert clamping > 0
 
 
-@pytest.mark.parametrize("scene", ["free_box_on_floor", "pendulum_on_floor", "two_box_stack"])
+@pytest.mark.parametrize("scene", ["free_box_on_floor", "pendulum_on_floor", "two_box_stack", "fixed_base_arm_on_floor", "walker_on_ground"])
 def test_contact_jacobians_match_oracle(scene):
-    """BackpropSnapshot::get{PosPos,PosVel,VelPos,VelVel,ForceVel}Jacobian with contacts (ddb_jacobians)."""
+    """BackpropSnapshot::get{PosPos,PosVel,VelPos,VelVel,ForceVel}Jacobian with contacts (ddb_jacobians). walker_on_ground carries
+    finite joint limits: the getters do not clip (only backprop() does, BackpropSnapshot.cpp:374-428) and must not touch the limits."""
     make, states = SCENES[scene]
     desc = make()
     N = 12
@@ -219,6 +220,38 @@ def test_contact_jacobians_match_oracle(scene):
         Jn = o.contact_jacobians(q[w], qd[w], tau[w], mode="reference", x_override=xs[w][:k], mapping_override=active[w, :k], q_noise=4e-16)
         for name in ("posPos", "posVel", "velPos", "velVel", "forceVel"):
             assert rel(Jg[name][w], J[name]) < 1e-8 + 20.0 * rel(Jn[name], J[name]), (scene, w, name)
+
+
+@pytest.mark.parametrize("scene", ["two_box_stack", "walker_on_ground"])
+def test_idempotent_forward_pass_leaves_the_cached_lcp_solution(scene):
+    """forwardPass(world, idempotent=True) restores the constraint solver's cached solution (RestorableSnapshot.cpp:23,32 via
+    NeuralUtils.cpp:29-33,61-62): with an idempotent call in between, the following steps are bit-identical to those without it."""
+    make, states = SCENES[scene]
+    desc = make()
+    N = 64
+    q, qd, tau = states(N, 17)
+
+    def run(with_idempotent):
+        world = BatchedWorld(desc, N)
+        world.setPositions(cuda(q)); world.setVelocities(cuda(qd))
+        out = []
+        for t in range(3):
+            world.setForces(cuda(tau))
+            if with_idempotent and t == 1:
+                q0, qd0 = world.getPositions().clone(), world.getVelocities().clone()
+                # a different state, so that the idempotent step's own solution differs from the cached one
+                world.setVelocities(world.getVelocities() * 0.5)
+                snap = forwardPass(world, idempotent=True)
+                assert torch.equal(world.getPositions(), q0) and torch.equal(world.getExternalForces(), cuda(tau))
+                assert not torch.equal(snap.getPostStepVelocity(), world.getVelocities())
+                world.setVelocities(qd0)
+            forwardPass(world)
+            out.append((world.getPositions().clone(), world.getVelocities().clone(), world.last_active_set.clone(), world.last_solver_status.clone()))
+        return out
+
+    for a, b in zip(run(False), run(True)):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
 
 
 def test_dart_layer_autograd_through_contacts():
