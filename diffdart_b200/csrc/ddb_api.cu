@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cstdint>
 #include <algorithm>
 #include <mutex>
 #include <string>
@@ -42,6 +43,9 @@ struct KernelTable {
   void (*bwd)(cudaStream_t, int, int, int, double*, const double*, const double*, const double*, const double*, double*, double*, double*, Limits);
   void (*jac)(cudaStream_t, int, double*, double*, double*, double*, double*, double*);
   void (*minv)(cudaStream_t, int, double*, double*);
+  // chains only (else NULL): the same kernels with their vectors in pinned host memory (HOSTIO, kernels.cuh)
+  void (*fwdHost)(cudaStream_t, int, int, int, const double*, const double*, const double*, double*, double*, double*);
+  void (*bwdHost)(cudaStream_t, int, int, int, double*, const double*, const double*, double*, double*, double*, Limits);
 };
 
 template <int NB, bool CHAIN>
@@ -53,7 +57,7 @@ struct Launch {
   static void bwd(cudaStream_t s, int N, int w0, int w1, double* snap, const double* gqn, const double* gqdn, const double* gqnAdd,
                   const double* gqdnAdd, double* gq, double* gqd, double* gtau, Limits lim) {
     // chains stage their snapshot rows in shared memory (dynamics.cuh, StageGeom): 16 bytes x slots per world
-    const size_t smem = (CHAIN && DDB_BWD_STAGE) ? StageGeom<NB, kBlockB>::kBytes : 0;
+    const size_t smem = (CHAIN && DDB_BWD_STAGE) ? ChainStageGeom<NB, kBlockB>::kBytes : 0;
     if (smem) {
       static bool once[64] = {false};  // per instantiation and device: the attribute belongs to the function in that context
       int dev = 0;
@@ -72,7 +76,32 @@ struct Launch {
   static void minv(cudaStream_t s, int N, double* snap, double* out) {
     k_inv_mass<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, out);
   }
-  static KernelTable table() { return KernelTable{fwd, bwd, jac, minv}; }
+  // per instantiation and device: the attribute belongs to the function in that context
+  template <class K>
+  static void allowShared(K kernel, size_t smem, bool* once) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (smem > 48 * 1024 && !once[dev & 63]) {
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      once[dev & 63] = true;
+    }
+  }
+  static void fwdHost(cudaStream_t s, int N, int w0, int w1, const double* q, const double* qd, const double* tau, double* qn, double* qdn, double* snap) {
+    const size_t smem = (size_t)3 * kBlock * NB * sizeof(double);
+    k_forward<NB, CHAIN, kBlock, kMinBF, true><<<grid(w1 - w0), kBlock, smem, s>>>(N, w0, w1, q, qd, tau, qn, qdn, snap);
+  }
+  static void bwdHost(cudaStream_t s, int N, int w0, int w1, double* snap, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
+                      Limits lim) {
+    const size_t smem = (DDB_BWD_STAGE ? ChainStageGeom<NB, kBlockB>::kBytes : 0) + (size_t)3 * kBlockB * NB * sizeof(double);
+    static bool once[64] = {false};
+    allowShared(k_backward<NB, CHAIN, kBlockB, kMinBB, true>, smem, once);
+    k_backward<NB, CHAIN, kBlockB, kMinBB, true><<<grid(w1 - w0, kBlockB), kBlockB, smem, s>>>(N, w0, w1, snap, gqn, gqdn, nullptr, nullptr, gq, gqd, gtau, lim);
+  }
+  static KernelTable table() {
+    KernelTable t{fwd, bwd, jac, minv, nullptr, nullptr};
+    if (CHAIN) { t.fwdHost = fwdHost; t.bwdHost = bwdHost; }
+    return t;
+  }
 };
 
 KernelTable pickTable(int nb, bool chain) {
@@ -327,6 +356,8 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
   // DDB_FORCE_GENERIC=1 routes chains through the generic tree kernels (used by the tests to cover both)
   const char* fg = getenv("DDB_FORCE_GENERIC");
   if (fg && fg[0] == '1') h->chain = false;
+  if (h->chain && h->nb > 8) h->chain = false;  // chain kernels exist for up to 8 links
+  if (h->chain) canonicalizeChain(topo, h->topo);  // chain kernels work in canonical joint frames (chain.cuh)
   h->k = pickTable(h->nb, h->chain);
   DDB_CUDA(h, cudaSetDevice(device));
   int slots = params->n_snapshot_slots < 1 ? 1 : params->n_snapshot_slots;
@@ -711,6 +742,7 @@ static int ensureStage(ddb_handle* h, size_t doubles) {
 // set-up, also when the pipeline is replayed from a CUDA graph (tried: no gain), and letting the kernels read / write the pinned
 // host buffers themselves is 3x slower (40-byte strides over PCIe). Hence two chunks (DDB_HOST_CHUNKS overrides).
 static bool hostChunked(const ddb_handle* h) { return !h->hasContacts && h->topo.layout == DDB_LAYOUT_WORLD_MAJOR && h->N >= 4096; }
+static bool hostZeroCopy(const ddb_handle* h) { return !h->hasContacts && h->topo.layout == DDB_LAYOUT_WORLD_MAJOR && h->k.fwdHost != nullptr; }
 static int envInt(const char* name, int dflt) { const char* e = getenv(name); return e ? std::max(1, atoi(e)) : dflt; }
 
 // kind 0: forward (in: q, qd, tau; out: qn, qdn), kind 1: backward (in: gqn, gqdn; out: gq, gqd, gtau); ptr = the five host pointers in that order
@@ -733,6 +765,41 @@ static int enqueueHostChunks(ddb_handle* h, int kind, const void* const* ptr, in
   }
   DDB_CUDA(h, cudaGetLastError());
   return joinLanes(h, h->hstream, L);
+}
+
+// Pinned (page-locked, mapped) host memory can be addressed by the kernels themselves; returns the device-side aliases of the five
+// vectors, or false when one of them is ordinary pageable memory (then the copy path below is taken).
+static bool mappedHostPointers(const void* const* ptr, const void** dev) {
+  for (int i = 0; i < 5; i++) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr[i]) != cudaSuccess) { cudaGetLastError(); return false; }
+    if (a.type != cudaMemoryTypeHost || !a.devicePointer) return false;
+    if ((reinterpret_cast<uintptr_t>(a.devicePointer) & 15) != 0) return false;  // 16-byte vector accesses
+    dev[i] = a.devicePointer;
+  }
+  return true;
+}
+// DDB_HOST_ZEROCOPY=0 forces the cudaMemcpyAsync pipeline (A/B timing)
+static bool zeroCopyEnabled() { const char* e = getenv("DDB_HOST_ZEROCOPY"); return !(e && e[0] == '0'); }
+
+// One launch of the HOSTIO kernel over the whole batch: see kernels.cuh. Measured on B200 / PCIe 5 against the two-chunk copy pipeline
+// in bench.py's e2e leg.
+static int runHostZeroCopy(ddb_handle* h, int kind, const void* const* dev) {
+  {
+    ApiScope scope(h);
+    int rc = enter(h, h->hstream);
+    if (rc) return rc;
+    if (kind == 0)
+      h->k.fwdHost(h->hstream, h->N, 0, h->N, (const double*)dev[0], (const double*)dev[1], (const double*)dev[2], (double*)dev[3], (double*)dev[4],
+                   h->slots[h->cur]);
+    else
+      h->k.bwdHost(h->hstream, h->N, 0, h->N, h->slots[h->cur], (const double*)dev[0], (const double*)dev[1], (double*)dev[2], (double*)dev[3],
+                   (double*)dev[4], h->lim);
+    DDB_CUDA(h, cudaGetLastError());
+    h->launches++;
+  }
+  DDB_CUDA(h, cudaStreamSynchronize(h->hstream));
+  return DDB_OK;
 }
 
 static int runHostChunked(ddb_handle* h, int kind, const void* const* ptr) {
@@ -758,9 +825,11 @@ int ddb_forward_host(ddb_handle* h, const double* q, const double* qd, const dou
   int rc = ensureStage(h, 8 * V);
   if (rc) return rc;
   double* d = h->stage;
-  if (hostChunked(h)) {
-    const void* ptr[5] = {q, qd, tau, qn, qdn};
-    rc = runHostChunked(h, 0, ptr);
+  const void* ptr[5] = {q, qd, tau, qn, qdn};
+  const void* dev[5];
+  const bool zc = hostZeroCopy(h) && zeroCopyEnabled() && mappedHostPointers(ptr, dev);
+  if (zc || hostChunked(h)) {
+    rc = zc ? runHostZeroCopy(h, 0, dev) : runHostChunked(h, 0, ptr);
     if (rc) return rc;
     h->slotValid[h->cur] = 1;
     return DDB_OK;
@@ -783,10 +852,12 @@ int ddb_backward_host(ddb_handle* h, const double* gqn, const double* gqdn, doub
   int rc = ensureStage(h, 8 * V);
   if (rc) return rc;
   double* d = h->stage;
-  if (hostChunked(h)) {
+  const void* ptr[5] = {gqn, gqdn, gq, gqd, gtau};
+  const void* dev[5];
+  const bool zc = hostZeroCopy(h) && zeroCopyEnabled() && mappedHostPointers(ptr, dev);
+  if (zc || hostChunked(h)) {
     if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward_host: no forward pass retained in the current snapshot slot");
-    const void* ptr[5] = {gqn, gqdn, gq, gqd, gtau};
-    return runHostChunked(h, 1, ptr);
+    return zc ? runHostZeroCopy(h, 1, dev) : runHostChunked(h, 1, ptr);
   }
   DDB_CUDA(h, cudaMemcpyAsync(d, gqn, B, cudaMemcpyHostToDevice, h->hstream));
   DDB_CUDA(h, cudaMemcpyAsync(d + V, gqdn, B, cudaMemcpyHostToDevice, h->hstream));

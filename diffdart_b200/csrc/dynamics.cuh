@@ -47,8 +47,16 @@ struct DevTopo {
   DevBody b[DDB_MAX_BODIES];
 };
 
-// single translation unit: the topology of the handle that launched last lives here
+// the topology of the handle that launched last lives here (one copy per translation unit).
+// DDB_SPEC_TOPO names a file holding one topology as an aggregate initializer: kernels of that translation unit are then
+// specialised for it (the compiler folds the constants and everything that follows from their zeros and ones).
+#ifdef DDB_SPEC_TOPO
+__device__ const DevTopo c_topo =
+#include DDB_SPEC_TOPO
+;
+#else
 __constant__ DevTopo c_topo;
+#endif
 
 // batched vector element (world w, dof d)
 DDB_DI size_t vidx(int layout, int N, int n, int w, int d) {

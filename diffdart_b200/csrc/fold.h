@@ -148,6 +148,80 @@ inline int foldTopology(const ddb_topology* t, const ddb_params* p, DevTopo& out
 }
 
 
+// Serial chains of 1-DOF joints are run in canonical joint frames (chain.cuh): body frame i' sits at joint i with the joint axis
+// as its z axis. Rewrites the DevBody entries of a topology foldTopology has accepted as a chain:
+//   N0, P0 <- F_i = X_p^-1 T_parentBodyToJoint,i (A_i, 0)   with X_i = T_childBodyToJoint,i (A_i, 0), A_i e_z = axis_i
+//   I      <- the rigid-body inertia about the new origin, in the new axes
+//   S      <- (e_z; 0) / (0; e_z)  (kept for reference; the chain kernels pick components instead of multiplying by S)
+struct HXf { HM3 R; double p[3]; };
+inline HXf hxmul(const HXf& A, const HXf& B) {
+  HXf r; r.R = mmul(A.R, B.R); mvec(A.R, B.p, r.p);
+  for (int k = 0; k < 3; k++) r.p[k] += A.p[k];
+  return r;
+}
+inline HXf hxinv(const HXf& A) {
+  HXf r;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) r.R.m[3 * i + j] = A.R.m[3 * j + i];
+  mvec(r.R, A.p, r.p);
+  for (int k = 0; k < 3; k++) r.p[k] = -r.p[k];
+  return r;
+}
+// shortest rotation taking e_z to the unit vector a (exact 0 / +-1 entries for axis-aligned a)
+inline HM3 rotZTo(const double* a) {
+  HM3 R = {{1, 0, 0, 0, 1, 0, 0, 0, 1}};
+  const double c = a[2];
+  if (c > 1.0 - 1e-15) return R;
+  if (c < -1.0 + 1e-15) { R.m[4] = -1; R.m[8] = -1; return R; }  // half a turn about x
+  const double v[3] = {-a[1], a[0], 0.0};  // e_z x a
+  const HM3 K = {{0, -v[2], v[1], v[2], 0, -v[0], -v[1], v[0], 0}};
+  const HM3 K2 = mmul(K, K);
+  for (int k = 0; k < 9; k++) R.m[k] += K.m[k] + K2.m[k] / (1.0 + c);
+  return R;
+}
+inline void canonicalizeChain(const ddb_topology* t, DevTopo& out) {
+  std::vector<HXf> X(t->n_bodies);
+  out.snapPairs = 0;
+  for (int i = 0; i < t->n_bodies; i++) {
+    const ddb_body& s = t->bodies[i];
+    DevBody& b = out.b[i];
+    double a[3] = {s.axis[0], s.axis[1], s.axis[2]};
+    const double an = std::sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+    for (int k = 0; k < 3; k++) a[k] /= an;
+    HXf A, Tp, Tc;
+    A.R = rotZTo(a); A.p[0] = A.p[1] = A.p[2] = 0.0;
+    std::memcpy(Tp.R.m, s.parent_to_joint.r, sizeof(Tp.R.m)); std::memcpy(Tp.p, s.parent_to_joint.p, sizeof(Tp.p));
+    std::memcpy(Tc.R.m, s.child_to_joint.r, sizeof(Tc.R.m)); std::memcpy(Tc.p, s.child_to_joint.p, sizeof(Tc.p));
+    X[i] = hxmul(Tc, A);
+    HXf F = hxmul(Tp, A);
+    if (i > 0) F = hxmul(hxinv(X[i - 1]), F);
+    std::memset(b.N0, 0, sizeof(b.N0)); std::memset(b.N1, 0, sizeof(b.N1)); std::memset(b.N2, 0, sizeof(b.N2));
+    std::memset(b.P1, 0, sizeof(b.P1)); std::memset(b.P2, 0, sizeof(b.P2));
+    std::memcpy(b.N0, F.R.m, sizeof(b.N0));
+    std::memcpy(b.P0, F.p, sizeof(b.P0));
+    const bool rev = s.joint_type == DDB_JOINT_REVOLUTE;
+    b.S.w = V3{0, 0, rev ? 1.0 : 0.0};
+    b.S.v = V3{0, 0, rev ? 0.0 : 1.0};
+    // inertia: centre of mass and moment (about the centre of mass) expressed in the new frame, then Inertia::computeSpatialTensor
+    const HXf Xi = hxinv(X[i]);
+    double c[3];
+    mvec(Xi.R, s.com, c);
+    for (int k = 0; k < 3; k++) c[k] += Xi.p[k];
+    const HM3 Ic = {{s.moment[0], s.moment[3], s.moment[4], s.moment[3], s.moment[1], s.moment[5], s.moment[4], s.moment[5], s.moment[2]}};
+    const HM3 In = mmul(mmul(Xi.R, Ic), hxinv(Xi).R);
+    const double m = s.mass;
+    b.I.m = m;
+    b.I.h = V3{m * c[0], m * c[1], m * c[2]};
+    b.I.J[0] = In.m[0] + m * (c[1] * c[1] + c[2] * c[2]);
+    b.I.J[1] = In.m[4] + m * (c[0] * c[0] + c[2] * c[2]);
+    b.I.J[2] = In.m[8] + m * (c[0] * c[0] + c[1] * c[1]);
+    b.I.J[3] = In.m[1] - m * c[0] * c[1];
+    b.I.J[4] = In.m[2] - m * c[0] * c[2];
+    b.I.J[5] = In.m[5] - m * c[1] * c[2];
+    b.snapOff = out.snapPairs;
+    out.snapPairs += kChainPairs;
+  }
+}
+
 // shapes, reactive flags, collidable pairs in collision-object order, capacities.
 // BodyNode::isReactive (BodyNode.cpp:1999-2018) is per body: the skeleton is mobile and the body depends on at least one
 // generalized coordinate, i.e. the body itself or one of its ancestors hangs on a joint with DOFs. A welded root link of a

@@ -7,9 +7,14 @@
 // q, qd, tau are appended only when joint limits are finite (clipLossGradientsToBounds needs them).
 #pragma once
 #include "dynamics.cuh"
+#include "chain.cuh"
 
 #ifndef DDB_BWD_STAGE
+#ifdef DDB_HOST_EMULATION
+#define DDB_BWD_STAGE 0  // (no cp.async on the host)
+#else
 #define DDB_BWD_STAGE 1  // 0: the chain backward reads the snapshot with plain loads (A/B timing only)
+#endif
 #endif
 
 namespace ddb {
@@ -25,27 +30,84 @@ __host__ __device__ inline size_t snapWorldsPadded(int N) { return ((size_t)N + 
 // the clip section (q, qd, tau as [3n][N]) sits behind the per-body pairs
 DDB_DI double* clipSection(double* snap, int /*nb*/, int N) { return snap + (size_t)2 * c_topo.snapPairs * snapWorldsPadded(N); }
 
-template <int NB, bool CHAIN, int BLOCK, int MINB>
+// ---- host-buffer variants (HOSTIO) of the chain kernels: the e2e path of a binding that holds its state in host memory ----
+// q, qd, tau, ... then point into PINNED HOST memory (mapped into the device's address space). A CTA moves the rows of its
+// worlds (world-major: BLOCK * NB consecutive doubles per vector) between host memory and shared memory with coalesced
+// 16-byte accesses, so PCIe sees full-width bursts; threads take their own values from shared memory. The copy engines are
+// not involved: reads of later CTAs, arithmetic and result writes of earlier CTAs overlap on the full-duplex link without
+// chunking the call, and there is no per-copy set-up cost (5 copies x chunks, ~5 us each, on the cudaMemcpyAsync path).
+DDB_DI void ioCopyIn(double* __restrict__ dst, const double* __restrict__ src, int cnt, int tid, int nthreads) {
+  // src is 16-byte aligned: CTA boundaries are multiples of 32 worlds
+  const int pairs = cnt >> 1;
+  for (int i = tid; i < pairs; i += nthreads) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(src)[i];
+  if ((cnt & 1) && tid == 0) dst[cnt - 1] = src[cnt - 1];
+}
+DDB_DI void ioCopyOut(double* __restrict__ dst, const double* __restrict__ src, int cnt, int tid, int nthreads) {
+  const int pairs = cnt >> 1;
+  for (int i = tid; i < pairs; i += nthreads) reinterpret_cast<double2*>(dst)[i] = reinterpret_cast<const double2*>(src)[i];
+  if ((cnt & 1) && tid == 0) dst[cnt - 1] = src[cnt - 1];
+}
+#ifdef DDB_HOST_EMULATION
+DDB_DI void ctaSync() {}
+DDB_DI double* ioShared() { return nullptr; }
+#else
+DDB_DI void ctaSync() { __syncthreads(); }
+DDB_DI double* ioShared() { extern __shared__ double2 ddb_io_shared[]; return reinterpret_cast<double*>(ddb_io_shared); }
+#endif
+
+template <int NB, bool CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
           double* __restrict__ qn, double* __restrict__ qdn, double* __restrict__ snap) {
   // worlds [w0, w1) of the N-world batch (the host splits a batch into chunks that run on different streams)
   const int w = w0 + blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= w1) return;
+  if (!HOSTIO && w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kChainPairs : 0};
   double* clip = clipSection(snap, nb, N);
-  if (CHAIN) {
+  if constexpr (CHAIN) {
     double ql[NB], qdl[NB], tl[NB], acc[NB];
+    double* io = nullptr;
+    const int wb = w0 + blockIdx.x * BLOCK;                // first world of this CTA
+    const int cnt = ((wb + BLOCK < w1 ? wb + BLOCK : w1) - wb) * NB;       // doubles per vector of this CTA
+    if (HOSTIO) {  // (world-major vectors)
+      io = ioShared();
+      ioCopyIn(io, q + (size_t)wb * NB, cnt, threadIdx.x, BLOCK);
+      ioCopyIn(io + BLOCK * NB, qd + (size_t)wb * NB, cnt, threadIdx.x, BLOCK);
+      ioCopyIn(io + 2 * BLOCK * NB, tau + (size_t)wb * NB, cnt, threadIdx.x, BLOCK);
+      ctaSync();
+      const int t = w < w1 ? threadIdx.x : 0;  // threads past the end shadow world wb (results dropped)
 #pragma unroll
-    for (int d = 0; d < NB; d++) {
-      size_t ix = vidx(layout, N, n, w, d);
-      ql[d] = q[ix]; qdl[d] = qd[ix]; tl[d] = tau[ix];
+      for (int d = 0; d < NB; d++) { ql[d] = io[t * NB + d]; qdl[d] = io[(BLOCK + t) * NB + d]; tl[d] = io[(2 * BLOCK + t) * NB + d]; }
+      ctaSync();
+      if (w >= w1) sn.w = wb;
+    } else {
+#pragma unroll
+      for (int d = 0; d < NB; d++) {
+        size_t ix = vidx(layout, N, n, w, d);
+        ql[d] = q[ix]; qdl[d] = qd[ix]; tl[d] = tau[ix];
+      }
     }
-    forwardDynamics<NB, CHAIN>(
-        sn, nb, [&](int d) { return ql[d]; }, [&](int d) { return qdl[d]; }, [&](int d) { return tl[d]; },
+    chainForwardDynamics<NB>(
+        sn, [&](int d) { return ql[d]; }, [&](int d) { return qdl[d]; }, [&](int d) { return tl[d]; },
         [&](int d, double a) { acc[d] = a; });
+    if (HOSTIO) {
+#pragma unroll
+      for (int d = 0; d < NB; d++) {
+        io[threadIdx.x * NB + d] = fma(dt, qdl[d], ql[d]);
+        io[(BLOCK + threadIdx.x) * NB + d] = fma(dt, acc[d], qdl[d]);
+        if (c_topo.has_limits && w < w1) {
+          clip[(size_t)d * N + w] = ql[d];
+          clip[(size_t)(n + d) * N + w] = qdl[d];
+          clip[(size_t)(2 * n + d) * N + w] = tl[d];
+        }
+      }
+      ctaSync();
+      ioCopyOut(qn + (size_t)wb * NB, io, cnt, threadIdx.x, BLOCK);
+      ioCopyOut(qdn + (size_t)wb * NB, io + BLOCK * NB, cnt, threadIdx.x, BLOCK);
+      return;
+    }
 #pragma unroll
     for (int d = 0; d < NB; d++) {
       size_t ix = vidx(layout, N, n, w, d);
@@ -104,33 +166,40 @@ DDB_DI double clipGrad(double g, double x, double lo, double hi) {
   return g;
 }
 
-template <int NB, bool CHAIN, int BLOCK, int MINB>
+template <int NB, bool CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
            const double* __restrict__ gqnAdd, const double* __restrict__ gqdnAdd,
            double* __restrict__ gq, double* __restrict__ gqd, double* __restrict__ gtau, Limits lim) {
   // loss gradient w.r.t. the post-step state = gqn (+ gqnAdd), gqdn (+ gqdnAdd): in a rollout the second term is what the
   // later steps pulled back (SingleShot.cpp:667-670); NULL otherwise
-  const int w = w0 + blockIdx.x * BLOCK + threadIdx.x;
-  if (w >= w1) return;
+  int w = w0 + blockIdx.x * BLOCK + threadIdx.x;
+  if (!HOSTIO && w >= w1) return;
   const int n = c_topo.nd, nb = c_topo.nb, layout = c_topo.layout;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
+  // HOSTIO (chains, world-major, pinned host vectors; see k_forward): the CTA's rows travel through shared memory
+  const int wb = w0 + blockIdx.x * BLOCK;
+  const int cnt = ((wb + BLOCK < w1 ? wb + BLOCK : w1) - wb) * NB;
+  const bool live = w < w1;
+  if (HOSTIO && !live) w = wb;  // threads past the end shadow world wb (results dropped)
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kChainPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
-  // chains read the snapshot through the cp.async staging area (dynamics.cuh, StageA / StageB); trees read global memory
+  // chains read the snapshot through the cp.async staging area (chain.cuh, ChainStageA / ChainStageB); trees read global memory
 #ifdef DDB_HOST_EMULATION
   double2* ddb_stage = nullptr;
 #else
   extern __shared__ double2 ddb_stage[];
 #endif
-  StageA<NB, BLOCK> sa;
-  StageB<NB, BLOCK> sb;
+  ChainStageA<NB, BLOCK> sa;
+  ChainStageB<NB, BLOCK> sb;
   constexpr bool STAGED = CHAIN && DDB_BWD_STAGE;
+  // the I/O rows of the host-buffer variant sit behind the staging area: [3][BLOCK * NB] doubles
+  double* io = HOSTIO ? reinterpret_cast<double*>(ddb_stage) + (STAGED ? ChainStageGeom<NB, BLOCK>::kBytes / sizeof(double) : 0) : nullptr;
   // the loss gradients are the first thing the up sweep consumes and the last thing the adjoint sweep adds: chains ask for them
   // before the staging copies instead of at the point of use
   double lamv[NB], gqv[NB];
-  if (CHAIN) {
+  if (CHAIN && !HOSTIO) {
 #pragma unroll
     for (int d = 0; d < NB; d++) {
       const size_t ix = vidx(layout, N, n, w, d);
@@ -143,16 +212,32 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
     sb.init(sn, ddb_stage);
     sa.start();
   }
+  if (CHAIN && HOSTIO) {
+    ioCopyIn(io, gqn + (size_t)wb * NB, cnt, threadIdx.x, BLOCK);
+    ioCopyIn(io + BLOCK * NB, gqdn + (size_t)wb * NB, cnt, threadIdx.x, BLOCK);
+    ctaSync();
+    const int t = live ? threadIdx.x : 0;
+#pragma unroll
+    for (int d = 0; d < NB; d++) { gqv[d] = io[t * NB + d]; lamv[d] = io[(BLOCK + t) * NB + d]; }
+    ctaSync();
+  }
   // lambda = dL/dqd'
   auto gqnOf = [&](size_t ix) { return gqnAdd ? gqn[ix] + gqnAdd[ix] : gqn[ix]; };
   auto gqdnOf = [&](size_t ix) { return gqdnAdd ? gqdn[ix] + gqdnAdd[ix] : gqdn[ix]; };
   auto lamOf = [&](int d) { return CHAIN ? lamv[d < NB ? d : 0] : gqdnOf(vidx(layout, N, n, w, d)); };
   auto muFree = [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; };
-  if (STAGED) solveInvMass<NB, CHAIN>(sa, nb, lamOf, ws, muFree);
-  else solveInvMass<NB, CHAIN>(sn, nb, lamOf, ws, muFree);
+  if constexpr (CHAIN) {
+    if (STAGED) chainSolveInvMass<NB>(sa, lamOf, ws);
+    else chainSolveInvMass<NB>(ChainPlain{{}, sn}, lamOf, ws);
+  } else {
+    solveInvMass<NB, CHAIN>(sn, nb, lamOf, ws, muFree);
+  }
   if (CHAIN) {
 #pragma unroll
-    for (int i = 0; i < NB; i++) gtau[vidx(layout, N, n, w, i)] = dt * mu[i];
+    for (int i = 0; i < NB; i++) {
+      if (HOSTIO) io[(2 * BLOCK + threadIdx.x) * NB + i] = dt * mu[i];
+      else gtau[vidx(layout, N, n, w, i)] = dt * mu[i];
+    }
   } else {
 #pragma unroll 1
     for (int i = 0; i < nb; i++)
@@ -162,8 +247,13 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
     size_t ix = vidx(layout, N, n, w, d);
     double a = CHAIN ? gqv[d < NB ? d : 0] : gqnOf(ix), l = CHAIN ? lamv[d < NB ? d : 0] : gqdnOf(ix);
     // pos-pos = I, vel-pos = dt I for R^1 joints; pos-vel^T l = -dt dPhi/dq; vel-vel^T l = l - dt dPhi/dqd
-    gq[ix] = fma(-dt, dq, a);
-    gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
+    if (HOSTIO) {
+      io[threadIdx.x * NB + d] = fma(-dt, dq, a);
+      io[(BLOCK + threadIdx.x) * NB + d] = fma(dt, a, fma(-dt, dqd, l));
+    } else {
+      gq[ix] = fma(-dt, dq, a);
+      gqd[ix] = fma(dt, a, fma(-dt, dqd, l));
+    }
   };
   auto out6 = [&](int body, const double* dq6, const double* dqd6) {
     // FreeJoint block: dL/dq = posPos^T g_q' - dt dPhi/dq, dL/dqd = velPos^T g_q' + l - dt dPhi/dqd
@@ -180,8 +270,29 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
       gqd[ix] = sv2 + gqdnOf(ix) - dt * dqd6[k];
     }
   };
-  if (STAGED) idAdjoint<NB, CHAIN>(sb, nb, ws, out1, out6);
-  else idAdjoint<NB, CHAIN>(sn, nb, ws, out1, out6);
+  if constexpr (CHAIN) {
+    if (STAGED) chainIdAdjoint<NB>(sb, ws, out1);
+    else chainIdAdjoint<NB>(ChainPlain{{}, sn}, ws, out1);
+  } else {
+    idAdjoint<NB, CHAIN>(sn, nb, ws, out1, out6);
+  }
+  if (CHAIN && HOSTIO) {
+    if (c_topo.has_limits) {
+      const double* clip = clipSection(snap, nb, N);
+#pragma unroll 1
+      for (int d = 0; d < NB; d++) {
+        double* o = io + threadIdx.x * NB + d;
+        o[0] = clipGrad(o[0], clip[(size_t)d * N + w], lim.pos_lo[d], lim.pos_hi[d]);
+        o[BLOCK * NB] = clipGrad(o[BLOCK * NB], clip[(size_t)(n + d) * N + w], lim.vel_lo[d], lim.vel_hi[d]);
+        o[2 * BLOCK * NB] = clipGrad(o[2 * BLOCK * NB], clip[(size_t)(2 * n + d) * N + w], lim.frc_lo[d], lim.frc_hi[d]);
+      }
+    }
+    ctaSync();
+    ioCopyOut(gq + (size_t)wb * NB, io, cnt, threadIdx.x, BLOCK);
+    ioCopyOut(gqd + (size_t)wb * NB, io + BLOCK * NB, cnt, threadIdx.x, BLOCK);
+    ioCopyOut(gtau + (size_t)wb * NB, io + 2 * BLOCK * NB, cnt, threadIdx.x, BLOCK);
+    return;
+  }
   if (c_topo.has_limits) {
     const double* clip = clipSection(snap, nb, N);
 #pragma unroll 1
@@ -204,14 +315,15 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
   const double dt = c_topo.dt;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kChainPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
-                            [&](int d, double m) { if (forceVel) forceVel[base + (size_t)d * n + j] = dt * m; });
+    if constexpr (CHAIN) chainSolveInvMass<NB>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    else solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+                                 [&](int d, double m) { if (forceVel) forceVel[base + (size_t)d * n + j] = dt * m; });
     if (forceVel) {
       if (CHAIN) {
 #pragma unroll
@@ -223,10 +335,12 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
       }
     }
     if (posVel || velVel) {
-      idAdjoint<NB, CHAIN>(sn, nb, ws, [&](int d, double dq, double dqd) {
+      auto outRow = [&](int d, double dq, double dqd) {
         if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
         if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
-      }, [&](int body, const double* dq6, const double* dqd6) {
+      };
+      if constexpr (CHAIN) chainIdAdjoint<NB>(ChainPlain{{}, sn}, ws, outRow);
+      else idAdjoint<NB, CHAIN>(sn, nb, ws, outRow, [&](int body, const double* dq6, const double* dqd6) {
         const int d0 = c_topo.b[body].dof;
         for (int k = 0; k < 6; k++) {
           if (posVel) posVel[base + (size_t)(d0 + k) * n + j] = -dt * dq6[k];
@@ -266,14 +380,15 @@ k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
   if (w >= N) return;
   const int n = c_topo.nd, nb = c_topo.nb;
-  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kSnapPairs : 0};
+  Snap sn{reinterpret_cast<double2*>(snap), N, w, CHAIN ? kChainPairs : 0};
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
-                            [&](int d, double m) { minv[base + (size_t)j * n + d] = m; });
+    if constexpr (CHAIN) chainSolveInvMass<NB>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    else solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+                                 [&](int d, double m) { minv[base + (size_t)j * n + d] = m; });
     if (CHAIN) {
 #pragma unroll
       for (int i = 0; i < NB; i++) minv[base + (size_t)j * n + i] = mu[i];

@@ -165,3 +165,36 @@ extern "C" int emul_contact_step_deferred(const ddb_topology* topo, const ddb_pa
   for (int k = 0; k < kmax; k++) { x_out[k] = cw.xall()[k]; if (active_out) active_out[k] = cw.activeAll()[k]; }
   return 0;
 }
+
+// The chain kernels (canonical joint frames, chain.cuh) for one world: forward step, backward VJP and M^-1 (nb = 1..8)
+template <int NB>
+static void chainRun(const double* q, const double* qd, const double* tau, const double* gqn, const double* gqdn, double* qn, double* qdn,
+                     double* gq, double* gqd, double* gtau, double* minv, double* jac5) {
+  const int N = 1, nd = c_topo.nd;
+  std::vector<double> snap(snapDoublesPerWorld(c_topo.snapPairs, nd, c_topo.has_limits != 0) * snapWorldsPadded(N) + 8, 0.0);
+  blockIdx.x = 0; threadIdx.x = 0; blockDim.x = 64;
+  k_forward<NB, true, 64, 1>(N, 0, N, q, qd, tau, qn, qdn, snap.data());
+  Limits lim{};
+  k_backward<NB, true, 32, 1>(N, 0, N, snap.data(), gqn, gqdn, nullptr, nullptr, gq, gqd, gtau, lim);
+  k_inv_mass<NB, true, 64, 1>(N, snap.data(), minv);
+  const size_t M = (size_t)nd * nd;
+  k_jacobians<NB, true, 64, 1>(N, snap.data(), jac5, jac5 + M, jac5 + 2 * M, jac5 + 3 * M, jac5 + 4 * M);
+}
+extern "C" int emul_chain_step(const ddb_topology* topo, const ddb_params* params, const double* q, const double* qd, const double* tau,
+                               const double* gqn, const double* gqdn, double* qn, double* qdn, double* gq, double* gqd, double* gtau, double* minv,
+                               double* jac5) {
+  std::string err;
+  bool chain;
+  if (foldTopology(topo, params, c_topo, chain, err) != DDB_OK) return 1;
+  if (!chain || c_topo.has_limits) return 2;
+  canonicalizeChain(topo, c_topo);
+  switch (c_topo.nb) {
+    case 1: chainRun<1>(q, qd, tau, gqn, gqdn, qn, qdn, gq, gqd, gtau, minv, jac5); break;
+    case 2: chainRun<2>(q, qd, tau, gqn, gqdn, qn, qdn, gq, gqd, gtau, minv, jac5); break;
+    case 3: chainRun<3>(q, qd, tau, gqn, gqdn, qn, qdn, gq, gqd, gtau, minv, jac5); break;
+    case 5: chainRun<5>(q, qd, tau, gqn, gqdn, qn, qdn, gq, gqd, gtau, minv, jac5); break;
+    case 7: chainRun<7>(q, qd, tau, gqn, gqdn, qn, qdn, gq, gqd, gtau, minv, jac5); break;
+    default: return 3;
+  }
+  return 0;
+}

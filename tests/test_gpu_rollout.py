@@ -128,12 +128,16 @@ def test_rollout_with_contacts_equals_stepwise():
         assert torch.allclose(r, g, rtol=0, atol=1e-12), (name, float((r - g).abs().max()))
 
 
-def test_host_path_chunked_equals_device_path():
-    """Host-buffer entry points on a large world-major batch: chunks of worlds pipelined over the lanes (copy-in, kernel, copy-out
-    overlap). Every call must equal the device path bit for bit on the data that is in the host buffers at that moment."""
+@pytest.mark.parametrize("zero_copy,N", [(True, 10000), (False, 10000), (True, 77)])
+def test_host_path_equals_device_path(zero_copy, N, monkeypatch):
+    """Host-buffer entry points on a world-major batch. Pinned host buffers: the kernels move their rows between host memory and
+    shared memory themselves (HOSTIO kernels, one launch per call); with DDB_HOST_ZEROCOPY=0 (and for pageable buffers): chunks of
+    worlds pipelined over the lanes (copy-in, kernel, copy-out overlap). Every call must equal the device path bit for bit on the
+    data that is in the host buffers at that moment; N = 77 leaves the last CTA partly filled with an odd number of doubles."""
+    monkeypatch.setenv("DDB_HOST_ZEROCOPY", "1" if zero_copy else "0")
     lib = _abi.load_library()
     desc = skeletons.create_multiarm_robot(5)
-    N, n = 10000, 5
+    n = 5
     topo, params, keep = desc.to_ctypes()
     h = _abi._vp()
     assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
@@ -158,7 +162,10 @@ def test_host_path_chunked_equals_device_path():
         torch.cuda.synchronize()
         for a, b in zip(hout, dout):
             assert torch.equal(a, b.cpu()), call
-    assert launches[0] >= 4  # forward and backward each ran as several chunk launches
+    if zero_copy:
+        assert launches[0] == 2  # one HOSTIO launch each
+    else:
+        assert launches[0] >= 4  # forward and backward each ran as several chunk launches
     # pageable host memory works the same way (the copies are then staged by the driver)
     pin = [np.ascontiguousarray(t.numpy().copy()) for t in hin]
     pout = [np.empty((N, n)) for _ in range(5)]
@@ -167,4 +174,39 @@ def test_host_path_chunked_equals_device_path():
         assert lib.ddb_backward_host(h, pin[3].ctypes.data, pin[4].ctypes.data, *[a.ctypes.data for a in pout[2:]]) == 0
         for a, b in zip(pout, dout):
             assert np.array_equal(a, b.cpu().numpy())
+    lib.ddb_destroy(h)
+
+
+def test_host_path_zero_copy_clips_at_the_limits():
+    """clipLossGradientsToBounds inside the HOSTIO backward (it clips its shared-memory rows, not the host buffers): equal to the
+    device path bit for bit on a chain with finite limits and inputs sitting on them."""
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(3)
+    bodies = desc.skeletons[0].bodies
+    bodies[0].position_lower[:] = -0.5
+    bodies[1].velocity_upper[:] = 0.25
+    bodies[2].force_lower[:] = -1.0
+    N, n = 300, 3
+    q, qd, tau = random_inputs(n, N, 9)
+    q[:150, 0] = -0.5
+    qd[100:250, 1] = 0.25
+    tau[::2, 2] = -1.0
+    g = np.random.default_rng(4).normal(size=(2, N, n))
+    topo, params, keep = desc.to_ctypes()
+    h = _abi._vp()
+    assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
+    hin = [torch.tensor(a, dtype=torch.float64).pin_memory() for a in (q, qd, tau, g[0], g[1])]
+    hout = [torch.zeros(N, n, dtype=torch.float64).pin_memory() for _ in range(5)]
+    dout = [torch.empty(N, n, dtype=torch.float64, device="cuda") for _ in range(5)]
+    assert lib.ddb_forward_host(h, *[t.data_ptr() for t in hin[:3]], hout[0].data_ptr(), hout[1].data_ptr()) == 0, lib.ddb_last_error(h)
+    assert lib.ddb_backward_host(h, hin[3].data_ptr(), hin[4].data_ptr(), *[t.data_ptr() for t in hout[2:]]) == 0, lib.ddb_last_error(h)
+    assert lib.ddb_launch_count(h) == 2
+    din = [t.cuda() for t in hin]
+    assert lib.ddb_forward(h, None, *[t.data_ptr() for t in din[:3]], dout[0].data_ptr(), dout[1].data_ptr(), None, None, None, None) == 0
+    assert lib.ddb_backward(h, None, din[3].data_ptr(), din[4].data_ptr(), *[t.data_ptr() for t in dout[2:]]) == 0
+    torch.cuda.synchronize()
+    for a, b in zip(hout, dout):
+        assert torch.equal(a, b.cpu())
+    assert (hout[2][:150, 0] <= 0).all() and (hout[3][100:250, 1] >= 0).all() and (hout[4][::2, 2] <= 0).all()
+    assert (hout[2][:150, 0] == 0).any()  # some gradients were actually clipped
     lib.ddb_destroy(h)
