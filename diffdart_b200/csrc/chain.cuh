@@ -54,7 +54,9 @@ DDB_DI double pickSdad(bool rev, SV V, SV F) {
   return fma(F.v.x, V.w.y, -(F.v.y * V.w.x));
 }
 
-DDB_DI bool chainRev(int i) { return c_topo.b[i].type == DDB_JOINT_REVOLUTE; }
+// ALLREV: every joint of the chain is revolute (pendulums, arms), known when the handle is created: no selects, no branches
+template <bool ALLREV>
+DDB_DI bool chainRev(int i) { return ALLREV || c_topo.b[i].type == DDB_JOINT_REVOLUTE; }
 DDB_DI void chainCS(bool rev, double qi, double& c, double& s) {
   if (rev) sincos(qi, &s, &c);
   else { c = qi; s = 0.0; }
@@ -183,7 +185,7 @@ struct ChainPlain : SnapReaders<ChainPlain> {
 // ---------------------------------------------------------------------------------------------
 // Forward dynamics (Featherstone ABA, d = k = 0) + snapshot; sweeps as forwardDynamics() in dynamics.cuh.
 // ---------------------------------------------------------------------------------------------
-template <int NB, class QF, class QDF, class TauF, class Store>
+template <int NB, bool ALLREV, class QF, class QDF, class TauF, class Store>
 DDB_DI void chainForwardDynamics(const Snap& sn, QF qOf, QDF qdOf, TauF tauOf, Store store) {
   struct {  // one object (see BwdScratch)
     SV V[NB], AIS[NB], A[NB], bias[NB], eta[NB];
@@ -202,10 +204,10 @@ DDB_DI void chainForwardDynamics(const Snap& sn, QF qOf, QDF qdOf, TauF tauOf, S
 #else
   auto opaque = [](double x) { asm volatile("" : "+d"(x)); return x; };
 #endif
-  auto Tof = [&](int i) -> Xf { return chainT(c_topo.b[i], chainRev(i), opaque(cth[i]), opaque(sth[i])); };
+  auto Tof = [&](int i) -> Xf { return chainT(c_topo.b[i], chainRev<ALLREV>(i), opaque(cth[i]), opaque(sth[i])); };
   auto down1 = [&](int i) {
     const DevBody& b = c_topo.b[i];
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     const double qdi = qdOf(i);
     chainCS(rev, qOf(i), cth[i], sth[i]);
     const Xf t = chainT(b, rev, cth[i], sth[i]);
@@ -228,10 +230,10 @@ DDB_DI void chainForwardDynamics(const Snap& sn, QF qOf, QDF qdOf, TauF tauOf, S
     const SV fg = b.gravity ? mul(b.I, sv(mk(0, 0, 0), G[i])) : svzero();
     bias[i] = -dad(V[i], IV) - fg;
     // partial acceleration ad(V, S qd) (GenericJoint.hpp:1740-1750, dS = 0): all that sweeps 2 and 3 need of V_i
-    eta[i] = adS(chainRev(i), V[i], qdv[i]);
+    eta[i] = adS(chainRev<ALLREV>(i), V[i], qdv[i]);
   };
   auto up = [&](int i) {
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     const SV ais = colS(rev, IA[i]);
     const double ps = 1.0 / pickS(rev, ais);
     // total force u = tau - S^T (IA eta + bias)   (GenericJoint.hpp:2208-2229 with d = k = 0)
@@ -252,7 +254,7 @@ DDB_DI void chainForwardDynamics(const Snap& sn, QF qOf, QDF qdOf, TauF tauOf, S
     }
   };
   auto down2 = [&](int i) {
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     SV Ai = (i > 0) ? AdInvT(Tof(i), A[i - 1]) : svzero();
     // qdd = psi (u - (IA S)^T AdInvT(T, A_parent))   (GenericJoint.hpp:2316-2327)
     const double acc = psi[i] * (u[i] - dot(AIS[i], Ai));
@@ -275,18 +277,18 @@ DDB_DI void chainForwardDynamics(const Snap& sn, QF qOf, QDF qdOf, TauF tauOf, S
 // mu = M^-1 lambda from the snapshot (solveInvMass() in dynamics.cuh): leaves U_i, the spatial velocity body i would have
 // under joint rates mu, and mu_i.
 // ---------------------------------------------------------------------------------------------
-template <int NB, class SN, class LamF>
+template <int NB, bool ALLREV, class SN, class LamF>
 DDB_DI void chainSolveInvMass(const SN& sn, LamF lamOf, BwdScratch<NB>& ws) {
   SV* c = ws.c;
   double* a = ws.a;
   double* mu = ws.mu;
   SV* U = ws.U;
-  auto Tof = [&](int i) -> Xf { const double2 cs = sn.ld(i, cCS); return chainT(c_topo.b[i], chainRev(i), cs.x, cs.y); };
+  auto Tof = [&](int i) -> Xf { const double2 cs = sn.ld(i, cCS); return chainT(c_topo.b[i], chainRev<ALLREV>(i), cs.x, cs.y); };
 #pragma unroll
   for (int i = 0; i < NB; i++) c[i] = svzero();
 #pragma unroll
   for (int i = NB - 1; i >= 0; i--) {
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     sn.beginUp(i);
     const double ai = lamOf(i) - pickS(rev, c[i]);
     a[i] = ai;
@@ -298,7 +300,7 @@ DDB_DI void chainSolveInvMass(const SN& sn, LamF lamOf, BwdScratch<NB>& ws) {
   }
 #pragma unroll
   for (int i = 0; i < NB; i++) {
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     SV Ui = svzero();
     const double ps = sn.ld(i, cPQ).x;
     double m = ps * a[i];
@@ -318,7 +320,7 @@ DDB_DI void chainSolveInvMass(const SN& sn, LamF lamOf, BwdScratch<NB>& ws) {
 // out(dof, dPhi/dq, dPhi/dqd) for Phi(q, qd) = mu^T ID(q, qd, qdd). The terms -mu S, -qd S, -qdd S of X_i U_p, X_i V_p, X_i A_p
 // only touch z components, which dad(S, .) does not look at.
 // ---------------------------------------------------------------------------------------------
-template <int NB, class SN, class Out>
+template <int NB, bool ALLREV, class SN, class Out>
 DDB_DI void chainIdAdjoint(const SN& sn, BwdScratch<NB>& ws, Out out) {
   const SV* U = ws.U;
   SV *pU = ws.pU, *pA = ws.pA, *pV = ws.pV;
@@ -328,7 +330,7 @@ DDB_DI void chainIdAdjoint(const SN& sn, BwdScratch<NB>& ws, Out out) {
 #pragma unroll
   for (int i = NB - 1; i >= 0; i--) {
     const DevBody& b = c_topo.b[i];
-    const bool rev = chainRev(i);
+    const bool rev = chainRev<ALLREV>(i);
     sn.beginAdj(i);
     const SV Vi = sn.ldSV(i, cV), Ai = sn.ldSV(i, cA);
     const double2 g0 = sn.ld(i, cG), g1 = sn.ld(i, cG + 1);

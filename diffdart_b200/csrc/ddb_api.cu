@@ -48,7 +48,7 @@ struct KernelTable {
   void (*bwdHost)(cudaStream_t, int, int, int, double*, const double*, const double*, double*, double*, double*, Limits);
 };
 
-template <int NB, bool CHAIN>
+template <int NB, int CHAIN>
 struct Launch {
   static int grid(int N, int block = kBlock) { return (N + block - 1) / block; }
   static void fwd(cudaStream_t s, int N, int w0, int w1, const double* q, const double* qd, const double* tau, double* qn, double* qdn, double* snap) {
@@ -104,24 +104,38 @@ struct Launch {
   }
 };
 
-KernelTable pickTable(int nb, bool chain) {
-  if (chain) {
+// chain: 0 = tree, 1 = serial chain of 1-DOF joints, 2 = such a chain with revolute joints only (kernels.cuh)
+KernelTable pickTable(int nb, int chain) {
+  if (chain == 1) {
     switch (nb) {
-      case 1: return Launch<1, true>::table();
-      case 2: return Launch<2, true>::table();
-      case 3: return Launch<3, true>::table();
-      case 4: return Launch<4, true>::table();
-      case 5: return Launch<5, true>::table();
-      case 6: return Launch<6, true>::table();
-      case 7: return Launch<7, true>::table();
-      case 8: return Launch<8, true>::table();
+      case 1: return Launch<1, 1>::table();
+      case 2: return Launch<2, 1>::table();
+      case 3: return Launch<3, 1>::table();
+      case 4: return Launch<4, 1>::table();
+      case 5: return Launch<5, 1>::table();
+      case 6: return Launch<6, 1>::table();
+      case 7: return Launch<7, 1>::table();
+      case 8: return Launch<8, 1>::table();
       default: break;
     }
   }
-  if (nb <= 8) return Launch<8, false>::table();
-  if (nb <= 16) return Launch<16, false>::table();
-  if (nb <= 32) return Launch<32, false>::table();
-  return Launch<DDB_MAX_BODIES, false>::table();
+  if (chain == 2) {
+    switch (nb) {
+      case 1: return Launch<1, 2>::table();
+      case 2: return Launch<2, 2>::table();
+      case 3: return Launch<3, 2>::table();
+      case 4: return Launch<4, 2>::table();
+      case 5: return Launch<5, 2>::table();
+      case 6: return Launch<6, 2>::table();
+      case 7: return Launch<7, 2>::table();
+      case 8: return Launch<8, 2>::table();
+      default: break;
+    }
+  }
+  if (nb <= 8) return Launch<8, 0>::table();
+  if (nb <= 16) return Launch<16, 0>::table();
+  if (nb <= 32) return Launch<32, 0>::table();
+  return Launch<DDB_MAX_BODIES, 0>::table();
 }
 
 // The __constant__ topology slot of a device has one owner (handle) at a time. Every entry point that launches kernels holds
@@ -358,7 +372,9 @@ int ddb_create(const ddb_topology* topo, const ddb_params* params, int32_t n_wor
   if (fg && fg[0] == '1') h->chain = false;
   if (h->chain && h->nb > 8) h->chain = false;  // chain kernels exist for up to 8 links
   if (h->chain) canonicalizeChain(topo, h->topo);  // chain kernels work in canonical joint frames (chain.cuh)
-  h->k = pickTable(h->nb, h->chain);
+  int chainKind = h->chain ? 2 : 0;
+  for (int i = 0; h->chain && i < h->nb; i++) if (h->topo.b[i].type != DDB_JOINT_REVOLUTE) chainKind = 1;
+  h->k = pickTable(h->nb, chainKind);
   DDB_CUDA(h, cudaSetDevice(device));
   int slots = params->n_snapshot_slots < 1 ? 1 : params->n_snapshot_slots;
   h->slots.assign(slots, nullptr);

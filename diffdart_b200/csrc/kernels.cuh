@@ -3,6 +3,8 @@
 //   k_backward   BackpropSnapshot::backprop as a vector-Jacobian product (BackpropSnapshot.cpp:115-186,374-428)
 //   k_jacobians  BackpropSnapshot::get{PosPos,PosVel,VelPos,VelVel,ForceVel}Jacobian (:432-735,1237-1360)
 //   k_inv_mass   Skeleton::getInvMassMatrix (Skeleton.cpp:2899-2905,4035-4098)
+// Template parameter CHAIN: 0 = any tree (dynamics.cuh, run-time loops over the topology), 1 = serial chain of 1-DOF joints
+// (chain.cuh, unrolled, canonical joint frames), 2 = such a chain with revolute joints only.
 // The snapshot kept between forward and backward (per slot) is described in dynamics.cuh (struct Snap);
 // q, qd, tau are appended only when joint limits are finite (clipLossGradientsToBounds needs them).
 #pragma once
@@ -55,7 +57,7 @@ DDB_DI void ctaSync() { __syncthreads(); }
 DDB_DI double* ioShared() { extern __shared__ double2 ddb_io_shared[]; return reinterpret_cast<double*>(ddb_io_shared); }
 #endif
 
-template <int NB, bool CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
+template <int NB, int CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
           double* __restrict__ qn, double* __restrict__ qdn, double* __restrict__ snap) {
@@ -89,7 +91,7 @@ k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __r
         ql[d] = q[ix]; qdl[d] = qd[ix]; tl[d] = tau[ix];
       }
     }
-    chainForwardDynamics<NB>(
+    chainForwardDynamics<NB, CHAIN == 2>(
         sn, [&](int d) { return ql[d]; }, [&](int d) { return qdl[d]; }, [&](int d) { return tl[d]; },
         [&](int d, double a) { acc[d] = a; });
     if (HOSTIO) {
@@ -121,7 +123,7 @@ k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __r
       }
     }
   } else {
-    forwardDynamics<NB, CHAIN>(
+    forwardDynamics<NB, false>(
         sn, nb, [&](int d) { return q[vidx(layout, N, n, w, d)]; }, [&](int d) { return qd[vidx(layout, N, n, w, d)]; },
         [&](int d) { return tau[vidx(layout, N, n, w, d)]; },
         [&](int d, double a) {
@@ -166,7 +168,7 @@ DDB_DI double clipGrad(double g, double x, double lo, double hi) {
   return g;
 }
 
-template <int NB, bool CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
+template <int NB, int CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
            const double* __restrict__ gqnAdd, const double* __restrict__ gqdnAdd,
@@ -193,7 +195,7 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
 #endif
   ChainStageA<NB, BLOCK> sa;
   ChainStageB<NB, BLOCK> sb;
-  constexpr bool STAGED = CHAIN && DDB_BWD_STAGE;
+  constexpr bool STAGED = CHAIN != 0 && DDB_BWD_STAGE;
   // the I/O rows of the host-buffer variant sit behind the staging area: [3][BLOCK * NB] doubles
   double* io = HOSTIO ? reinterpret_cast<double*>(ddb_stage) + (STAGED ? ChainStageGeom<NB, BLOCK>::kBytes / sizeof(double) : 0) : nullptr;
   // the loss gradients are the first thing the up sweep consumes and the last thing the adjoint sweep adds: chains ask for them
@@ -227,10 +229,10 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
   auto lamOf = [&](int d) { return CHAIN ? lamv[d < NB ? d : 0] : gqdnOf(vidx(layout, N, n, w, d)); };
   auto muFree = [&](int d, double m) { gtau[vidx(layout, N, n, w, d)] = dt * m; };
   if constexpr (CHAIN) {
-    if (STAGED) chainSolveInvMass<NB>(sa, lamOf, ws);
-    else chainSolveInvMass<NB>(ChainPlain{{}, sn}, lamOf, ws);
+    if (STAGED) chainSolveInvMass<NB, CHAIN == 2>(sa, lamOf, ws);
+    else chainSolveInvMass<NB, CHAIN == 2>(ChainPlain{{}, sn}, lamOf, ws);
   } else {
-    solveInvMass<NB, CHAIN>(sn, nb, lamOf, ws, muFree);
+    solveInvMass<NB, false>(sn, nb, lamOf, ws, muFree);
   }
   if (CHAIN) {
 #pragma unroll
@@ -271,10 +273,10 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
     }
   };
   if constexpr (CHAIN) {
-    if (STAGED) chainIdAdjoint<NB>(sb, ws, out1);
-    else chainIdAdjoint<NB>(ChainPlain{{}, sn}, ws, out1);
+    if (STAGED) chainIdAdjoint<NB, CHAIN == 2>(sb, ws, out1);
+    else chainIdAdjoint<NB, CHAIN == 2>(ChainPlain{{}, sn}, ws, out1);
   } else {
-    idAdjoint<NB, CHAIN>(sn, nb, ws, out1, out6);
+    idAdjoint<NB, false>(sn, nb, ws, out1, out6);
   }
   if (CHAIN && HOSTIO) {
     if (c_topo.has_limits) {
@@ -307,7 +309,7 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
 
 // Each unit vector e_j pulled back through the step gives row j of vel-vel, pos-vel, force-vel.
 // Outputs are [world][col][row] (column-major per world); NULL pointers are skipped.
-template <int NB, bool CHAIN, int BLOCK, int MINB>
+template <int NB, int CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, double* __restrict__ posVel,
             double* __restrict__ velPos, double* __restrict__ velVel, double* __restrict__ forceVel) {
@@ -321,8 +323,8 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    if constexpr (CHAIN) chainSolveInvMass<NB>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
-    else solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+    if constexpr (CHAIN) chainSolveInvMass<NB, CHAIN == 2>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    else solveInvMass<NB, false>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
                                  [&](int d, double m) { if (forceVel) forceVel[base + (size_t)d * n + j] = dt * m; });
     if (forceVel) {
       if (CHAIN) {
@@ -339,8 +341,8 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
         if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
         if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
       };
-      if constexpr (CHAIN) chainIdAdjoint<NB>(ChainPlain{{}, sn}, ws, outRow);
-      else idAdjoint<NB, CHAIN>(sn, nb, ws, outRow, [&](int body, const double* dq6, const double* dqd6) {
+      if constexpr (CHAIN) chainIdAdjoint<NB, CHAIN == 2>(ChainPlain{{}, sn}, ws, outRow);
+      else idAdjoint<NB, false>(sn, nb, ws, outRow, [&](int body, const double* dq6, const double* dqd6) {
         const int d0 = c_topo.b[body].dof;
         for (int k = 0; k < 6; k++) {
           if (posVel) posVel[base + (size_t)(d0 + k) * n + j] = -dt * dq6[k];
@@ -374,7 +376,7 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   }
 }
 
-template <int NB, bool CHAIN, int BLOCK, int MINB>
+template <int NB, int CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const int w = blockIdx.x * BLOCK + threadIdx.x;
@@ -386,8 +388,8 @@ k_inv_mass(int N, double* __restrict__ snap, double* __restrict__ minv) {
   const size_t base = (size_t)w * n * n;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    if constexpr (CHAIN) chainSolveInvMass<NB>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
-    else solveInvMass<NB, CHAIN>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
+    if constexpr (CHAIN) chainSolveInvMass<NB, CHAIN == 2>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    else solveInvMass<NB, false>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
                                  [&](int d, double m) { minv[base + (size_t)j * n + d] = m; });
     if (CHAIN) {
 #pragma unroll

@@ -21,27 +21,27 @@ def chain_step():
     lib = C.CDLL(os.path.join(HERE, "host_emulation", "_build", "libemul.so"))
     dp = C.POINTER(C.c_double)
 
-    def run(desc, q, qd, tau, gqn, gqdn):
+    def run(desc, q, qd, tau, gqn, gqdn, kind=1):
         topo, params, keep = desc.to_ctypes()
         n = len(q)
         outs = [np.zeros(n) for _ in range(5)]
         minv, jac = np.zeros((n, n)), np.zeros((5, n, n))
         rc = lib.emul_chain_step(C.byref(topo), C.byref(params), *[np.ascontiguousarray(a).ctypes.data_as(dp) for a in (q, qd, tau, gqn, gqdn)],
-                                 *[o.ctypes.data_as(dp) for o in outs], minv.ctypes.data_as(dp), jac.ctypes.data_as(dp))
+                                 *[o.ctypes.data_as(dp) for o in outs], minv.ctypes.data_as(dp), jac.ctypes.data_as(dp), kind)
         assert rc == 0, rc
         return outs, minv.T, jac.transpose(0, 2, 1)  # column-major per matrix -> [row][col]
 
     return run
 
 
-def skewed_arm(n, seed):
+def skewed_arm(n, seed, prismatic_every=3):
     """A chain with arbitrary joint axes, joint frames offset and rotated on both sides, off-centre masses and full inertia tensors,
     revolute and prismatic joints mixed: nothing in it is aligned with the canonical frames the kernels work in."""
     rng = np.random.default_rng(seed)
     s = skeletons.Skeleton("skewed")
     parent = None
     for i in range(n):
-        prismatic = (i % 3 == 1)
+        prismatic = prismatic_every > 0 and (i % prismatic_every == 1)
         b = (s.createPrismaticJointAndBodyNodePair if prismatic else s.createRevoluteJointAndBodyNodePair)(parent)
         axis = rng.normal(size=3)
         b.setAxis(list(axis / np.linalg.norm(axis)))
@@ -60,8 +60,10 @@ CASES = {
     "cartpole": lambda: skeletons.create_cartpole(),
     "pendulum5": lambda: skeletons.create_multiarm_robot(5),
     "skewed3": lambda: skewed_arm(3, 1),
-    "skewed7": lambda: skewed_arm(7, 2),
+    "skewed5": lambda: skewed_arm(5, 2),
+    "skewed5_revolute": lambda: skewed_arm(5, 3, prismatic_every=0),
 }
+ALL_REVOLUTE = {"pendulum5", "skewed5_revolute"}
 
 
 @pytest.mark.parametrize("case", sorted(CASES))
@@ -73,7 +75,9 @@ def test_chain_kernels_match_oracle(chain_step, case):
     for trial in range(6):
         q, qd, tau = rng.uniform(-1, 1, n), rng.uniform(-1, 1, n), rng.uniform(-2, 2, n)
         gqn, gqdn = rng.normal(size=n), rng.normal(size=n)
-        (qn, qdn, gq, gqd, gtau), minv, jac = chain_step(desc, q, qd, tau, gqn, gqdn)
+        # kind 1: revolute / prismatic mixed (selects); kind 2: the instantiation for revolute joints only
+        kind = 2 if (case in ALL_REVOLUTE and trial % 2) else 1
+        (qn, qdn, gq, gqd, gtau), minv, jac = chain_step(desc, q, qd, tau, gqn, gqdn, kind)
         oqn, oqdn, ogq, ogqd, ogtau = o.step_backprop(q[None], qd[None], tau[None], gqn[None], gqdn[None], mode="exact")
         assert max_ref_err(qn, oqn[0]) < 1e-12 and max_ref_err(qdn, oqdn[0]) < 1e-11, (case, trial)
         for name, a, b in (("dL/dq", gq, ogq[0]), ("dL/dqd", gqd, ogqd[0]), ("dL/dtau", gtau, ogtau[0])):
