@@ -186,6 +186,7 @@ struct ddb_handle {
   // the upload of this handle's topology into constant memory: the stream it was ordered on and an event behind it
   cudaEvent_t topoReady = nullptr;
   cudaStream_t topoStream = nullptr;
+  bool topoDone = false;
 };
 
 namespace {
@@ -208,22 +209,43 @@ struct ApiScope {
   explicit ApiScope(const ddb_handle* h) : lk(g_devMu[h->device & 63]) {}
 };
 
-// make this handle's topology the one in constant memory (stream-ordered); the caller holds the device's ApiScope
+// make this handle's topology the one in constant memory; the caller holds the device's ApiScope. The upload is ordered on s and,
+// unless s is being captured into a CUDA graph, waited for on the host: afterwards kernels of this handle may run on any stream
+// without further ordering (binding happens once per handle, or once per switch between handles that share a device).
+bool isCapturing(cudaStream_t s) {
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(s, &st) != cudaSuccess) { cudaGetLastError(); return false; }
+  return st != cudaStreamCaptureStatusNone;
+}
 int bindTopology(ddb_handle* h, cudaStream_t s) {
   if (g_owner[h->device] == h) {
-    // the upload was ordered on another stream: this stream's kernels must not overtake it
-    if (s != h->topoStream) DDB_CUDA(h, cudaStreamWaitEvent(s, h->topoReady, 0));
+    if (!h->topoDone && s != h->topoStream) {
+      // the upload was captured on another stream and has not run yet
+      if (isCapturing(s)) return fail(h, DDB_ERR_STATE, "first use of this handle happened inside a stream capture on another stream");
+      DDB_CUDA(h, cudaEventSynchronize(h->topoReady));
+      h->topoDone = true;
+    }
     return DDB_OK;
   }
+  const bool capturing = isCapturing(s);
   // another handle's kernels (on any stream or lane) may still be reading the slot: switching owners drains the device first
-  if (g_owner[h->device] != nullptr) DDB_CUDA(h, cudaDeviceSynchronize());
+  if (g_owner[h->device] != nullptr) {
+    if (capturing) return fail(h, DDB_ERR_STATE, "switching between handles of one device inside a stream capture");
+    DDB_CUDA(h, cudaDeviceSynchronize());
+  }
   g_owner[h->device] = nullptr;
   if (!h->topoReady) DDB_CUDA(h, cudaEventCreateWithFlags(&h->topoReady, cudaEventDisableTiming));
   // (the host copy lives in the handle, pageable: the runtime stages it before the call returns)
   DDB_CUDA(h, cudaMemcpyToSymbolAsync(c_topo, &h->topo, sizeof(DevTopo), 0, cudaMemcpyHostToDevice, s));
   if (h->hasContacts) DDB_CUDA(h, contactBindTopology(&h->topo, &h->ctopo, s));
-  DDB_CUDA(h, cudaEventRecord(h->topoReady, s));
   h->topoStream = s;
+  h->topoDone = false;
+  if (!capturing) {
+    DDB_CUDA(h, cudaStreamSynchronize(s));
+    h->topoDone = true;
+  } else {
+    DDB_CUDA(h, cudaEventRecord(h->topoReady, s));
+  }
   g_owner[h->device] = h;
   return DDB_OK;
 }

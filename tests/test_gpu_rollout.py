@@ -210,3 +210,36 @@ def test_host_path_zero_copy_clips_at_the_limits():
     assert (hout[2][:150, 0] <= 0).all() and (hout[3][100:250, 1] >= 0).all() and (hout[4][::2, 2] <= 0).all()
     assert (hout[2][:150, 0] == 0).any()  # some gradients were actually clipped
     lib.ddb_destroy(h)
+
+
+def test_step_captured_in_a_cuda_graph_on_a_side_stream():
+    """ddb_forward + ddb_backward captured into a CUDA graph on a stream other than the one the handle was first used on (the topology
+    upload was ordered there): replays equal the direct calls bit for bit, and nothing in the entry points breaks the capture."""
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(5)
+    N, n = 2048, 5
+    topo, params, keep = desc.to_ctypes()
+    h = _abi._vp()
+    assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
+    q, qd, tau = random_inputs(n, N, 3)
+    g = np.random.default_rng(8).normal(size=(2, N, n))
+    din = [torch.tensor(a, dtype=torch.float64, device="cuda") for a in (q, qd, tau, g[0], g[1])]
+    ref = [torch.empty(N, n, dtype=torch.float64, device="cuda") for _ in range(5)]
+    out = [torch.zeros(N, n, dtype=torch.float64, device="cuda") for _ in range(5)]
+
+    def step(sp, o):
+        assert lib.ddb_forward(h, sp, *[t.data_ptr() for t in din[:3]], o[0].data_ptr(), o[1].data_ptr(), None, None, None, None) == 0, lib.ddb_last_error(h)
+        assert lib.ddb_backward(h, sp, din[3].data_ptr(), din[4].data_ptr(), *[t.data_ptr() for t in o[2:]]) == 0, lib.ddb_last_error(h)
+
+    step(C.c_void_p(torch.cuda.current_stream().cuda_stream), ref)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        step(C.c_void_p(side.cuda_stream), out)
+    for _ in range(2):
+        graph.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(out, ref):
+        assert torch.equal(a, b)
+    lib.ddb_destroy(h)
