@@ -34,17 +34,18 @@ WORKLOAD = ("pendulum5: 65536 five-link revolute pendulums per GPU, no contact (
             "run as 8-step rollouts with backprop through ddb_rollout_forward / ddb_rollout_backward")
 # Algorithmic HBM bytes per world, SURVEY.md §8(d): forward reads q,qd,tau (3n) and writes q',qd' (2n) = 40n B;
 # backward reads dL/dq',dL/dqd' (2n) + the pre-step state (3n) and writes dL/dq,dL/dqd,dL/dtau (3n) = 64n B.
-# (The design additionally moves a 288 B/body snapshot each way on purpose — DESIGN.md §4 — which shows up in
+# (The design additionally moves a 208 B/body snapshot each way on purpose — DESIGN.md §4 — which shows up in
 # roofline.traffic, not in the algorithmic bytes.)
 FWD_BYTES = 40 * N_DOFS
 BWD_BYTES = 64 * N_DOFS
-# DRAM traffic per whole-batch launch from the `ncu --set full` captures of the committed build (profiles/r01d_ncu_full_summary.csv),
-# bytes: dram__bytes_read.sum + dram__bytes_write.sum. (The forward leaves part of its 94 MB snapshot dirty in L2 when it ends.)
-FWD_TRAFFIC = 7.95e6 + 44.88e6
-BWD_TRAFFIC = 99.70e6 + 4.12e6
-# FP64 flops per world counted from the SASS of the chain<5> kernels (profiles/r01_flops.md): DFMA=2, DADD/DMUL=1
-FWD_FLOPS = 4933
-BWD_FLOPS = 4245
+# DRAM traffic per whole-batch launch from the `ncu --set full` captures of the round-2 chain kernels (profiles/r02a_ncu_full_summary.csv),
+# bytes: dram__bytes_read.sum + dram__bytes_write.sum. (The forward leaves most of its 68 MB snapshot dirty in L2 when it ends.)
+FWD_TRAFFIC = 7.93e6 + 15.90e6
+BWD_TRAFFIC = 73.45e6 + 1.73e6
+# FP64 flops per world of the revolute-chain<5> kernels as executed (ncu: smsp__sass_thread_inst_executed_op_{dfma x2, dmul, dadd} per thread,
+# profiles/r02a_ncu_full_summary.csv; the static SASS counts of profiles/r02_flops.md are 2 % lower): DFMA = 2, DADD / DMUL = 1
+FWD_FLOPS = 3687
+BWD_FLOPS = 3060
 
 
 def inputs(N, seed=1234):
@@ -327,7 +328,7 @@ def run_ours(args):
     lib = _abi.load_library()
     desc = skeletons.create_multiarm_robot(N_DOFS)
     N, n = N_WORLDS, N_DOFS
-    SETS = 8  # rotating buffer sets: 8 x (26 MB of inputs/outputs + 94 MB snapshot slot) = 960 MB >> 126 MB L2: every step is cold
+    SETS = 8  # rotating buffer sets: 8 x (26 MB of inputs/outputs + 68 MB snapshot slot) = 750 MB >> 126 MB L2: every step is cold
     topo, params, keep = desc.to_ctypes(n_snapshot_slots=SETS)
     h = _abi._vp()
     rc = lib.ddb_create(C.byref(topo), C.byref(params), N, local_rank, C.byref(h))
@@ -508,11 +509,11 @@ def run_ours(args):
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "worlds_per_gpu": N, "n_dofs": n, "dt": 1e-3, "rollout_steps": T, "lanes": args.lanes,
-                       "cache": "every rollout writes and re-reads 8 snapshot slots + 8 steps of inputs/outputs (790 MB >> 126 MB L2): steps read cold data"},
+                       "cache": "every rollout writes and re-reads 8 snapshot slots + 8 steps of inputs/outputs (590 MB >> 126 MB L2): steps read cold data"},
             "clocks": sampler.result(),
             "e2e": {"value": world_size * N * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 5 * N * n * 8,
                     "d2h_bytes_per_step": 5 * N * n * 8, "steps": e2e_steps,
-                    "path": "ddb_forward_host + ddb_backward_host with pinned host buffers"},
+                    "path": "ddb_forward_host + ddb_backward_host with pinned host buffers (the kernels read and write the pinned buffers themselves through shared memory; DDB_HOST_ZEROCOPY=0 selects the cudaMemcpyAsync chunk pipeline)"},
             "gpu_launches": launches,
             "kernels": {"k_forward_ms": fwd_ms, "k_backward_ms": bwd_ms, "note": "whole-batch launches timed alone on one stream, rotating cold sets"},
             "single_step": {"value": world_size * N * args.steps / (single_ms * 1e-3), "unit": UNIT, "ms_per_step": single_ms / args.steps,
@@ -527,7 +528,7 @@ def run_ours(args):
                               "kernel": dom[0], "achieved": dom[3] * N / (dom[1] * 1e-3) / 1e12, "frac": dom[3] * N / (dom[1] * 1e-3) / 1e12 / peak.value,
                               "whole_step_achieved": (FWD_FLOPS + BWD_FLOPS) * N * args.steps / (elapsed_ms * 1e-3) / 1e12,
                               "whole_step_frac": (FWD_FLOPS + BWD_FLOPS) * N * args.steps / (elapsed_ms * 1e-3) / 1e12 / peak.value,
-                              "note": "flops per world counted from SASS (profiles/r01_flops.md); whole_step = the timed rollout (chunks of both kernels overlap on the lanes)"},
+                              "note": "flops per world as executed (ncu, profiles/r02a_ncu_full_summary.csv); whole_step = the timed rollout (chunks of both kernels overlap on the lanes)"},
         }
         if not args.no_contact:
             line["contact_rich"] = {"workload": CONTACT_WORKLOAD, "value": world_size * CONTACT_WORLDS / (contact_ms * 1e-3), "unit": UNIT,
