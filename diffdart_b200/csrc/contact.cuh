@@ -26,7 +26,7 @@ struct ShapeDesc {  // per body collision shape (one ShapeNode per body)
 };
 struct ContactTopo {
   int n_pairs, cmax, kmax, nskel;
-  int gradients, bouncing;  // bouncing: some collidable pair has restitution > 1e-3 (the backward pass refuses those). gradients 1: the gradient-enabled solve of forwardPass (short-circuit, standardisation, classification)
+  int gradients, bouncing;  // bouncing: some collidable pair has restitution > 1e-3. gradients 1: the gradient-enabled solve of forwardPass (short-circuit, standardisation, classification)
   double clip_depth;
   int pairA[DDB_MAX_BODIES * 4], pairB[DDB_MAX_BODIES * 4];  // collidable pairs in collision-object order
   ShapeDesc shape[DDB_MAX_BODIES];
@@ -124,7 +124,8 @@ struct ContactSnapLayout {
   __host__ __device__ size_t oMassed() const { return (size_t)cmax * 26; }
   __host__ __device__ size_t oX() const { return oMassed() + (size_t)kmax * nd; }
   __host__ __device__ size_t oVf() const { return oX() + kmax; }
-  __host__ __device__ size_t doubles() const { return oVf() + nd; }
+  __host__ __device__ size_t oRest() const { return oVf() + nd; }  // [kmax] restitution coefficient of a row that bounced (normal rows), else 0
+  __host__ __device__ size_t doubles() const { return oRest() + kmax; }
   __host__ __device__ size_t oBodyA() const { return 0; }
   __host__ __device__ size_t oBodyB() const { return cmax; }
   __host__ __device__ size_t oDim() const { return 2 * (size_t)cmax; }
@@ -458,11 +459,16 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
       if (dim == 3) { for (int t = 1; t < 3; t++) { lo[o + t] = -mu; hi[o + t] = mu; findex[o + t] = o; } }
       // penetration correction is off by default (World.cpp:85); restitution bounce (ContactConstraint.cpp:395-418)
       double bouncing = 0.0;
+      bool didBounce = false;
       if (rest > 1e-3) {
         double restitutionVel = b[o] * rest;
+        didBounce = restitutionVel > 1e-1;
         if (restitutionVel > 1e-1) { if (restitutionVel > bouncing) { bouncing = restitutionVel; if (bouncing > 1e+2) bouncing = 1e+2; } }
       }
       b[o] += bouncing;
+      // ContactConstraint::getCoefficientOfRestitution (ContactConstraint.cpp:929-935) as registerConstraint records it per row
+      // (ConstrainedGroupGradientMatrices.cpp:99-119): the coefficient on the normal row of a contact that bounced, 0 elsewhere
+      if (keepD) for (int k = 0; k < dim; k++) keepD[ContactSnapLayout{nd, ct.cmax, ct.kmax}.oRest() + rowsTotal + o + k] = (k == 0 && didBounce) ? rest : 0.0;
       for (int k = 0; k < dim; k++) cw.keep()[o + k] = c * 4 + k;  // row -> (constraint, direction) for the tests below
     }
     // the impulse tests are independent: with one warp per world every lane runs one on its private pad

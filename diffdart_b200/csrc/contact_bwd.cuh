@@ -16,7 +16,10 @@
 // are the extra mass-matrix terms of the pseudo-inverse derivative, and V_row collects, per clamping / upper-bound row,
 // every vector that multiplies that row's constraint-force Jacobian. The reference evaluates the mass-matrix and Coriolis
 // derivatives by finite differences (BackpropSnapshot.cpp:5990-6027,6121-6157); here they are closed-form sweeps.
-// Restitution (bouncing constraints) is not handled: e = 0.
+// Restitution: with B = diag(1 + e_j) over the clamping rows that bounced (getBounceDiagonals, ConstrainedGroupGradientMatrices.cpp:753)
+// the LCP offset is b_c = -B A_c^T v_f and its Jacobians carry the same factor (BackpropSnapshot.cpp:4252-4299), so wherever y1 meets
+// dB it is yB = B y1: lambda~ = lambda - A_c yB, the row vectors use -yB_j v_f, M^-1 lambda = mu~ + M^-1 A_c yB, and the bilinear
+// mass-matrix terms gain the pair (M^-1 A_c (yB - y1), M^-1 A f_c). The terms of d(Q^+) b keep the plain y1.
 #pragma once
 #include "contact.cuh"
 #include "kernels.cuh"
@@ -32,9 +35,9 @@ struct ContactBwdLayout {
   __host__ __device__ size_t oF() const { return oSP() + (size_t)nd * 6; }             // [kmax][6] world force of each classified row
   __host__ __device__ size_t oAc() const { return oF() + (size_t)kmax * 6; }           // [kmax][nd] constraint-force columns
   __host__ __device__ size_t oMA() const { return oAc() + (size_t)kmax * nd; }         // [kmax][nd] M^-1 (A_c + A_ub E) columns
-  __host__ __device__ size_t oCV() const { return oMA() + (size_t)kmax * nd; }         // 10 x [kmax]: a b f y1 r1 y2 r2 y3 r3 E
-  __host__ __device__ size_t oNV() const { return oCV() + (size_t)10 * kmax; }         // 12 x [nd]
-  __host__ __device__ size_t doubles() const { return oNV() + (size_t)12 * nd; }
+  __host__ __device__ size_t oCV() const { return oMA() + (size_t)kmax * nd; }         // 11 x [kmax]: a b f y1 r1 y2 r2 y3 r3 E yB
+  __host__ __device__ size_t oNV() const { return oCV() + (size_t)11 * kmax; }         // 13 x [nd]
+  __host__ __device__ size_t doubles() const { return oNV() + (size_t)13 * nd; }
   __host__ __device__ size_t ints() const { return (size_t)4 * kmax; }                 // clampRow ubRow ubNormal clampIdxOfRow
 };
 
@@ -172,8 +175,8 @@ struct ContactBwdWork {
   DDB_DI int* ubNormal() const { return i + 2 * L.kmax; }
   DDB_DI int* clampIdxOfRow() const { return i + 3 * L.kmax; }
 };
-enum { CV_A = 0, CV_B, CV_F, CV_Y1, CV_R1, CV_Y2, CV_R2, CV_Y3, CV_R3, CV_E };
-enum { NV_LAMT = 0, NV_MUT, NV_M1, NV_M2, NV_M3, NV_M4, NV_M5, NV_M6, NV_M7, NV_V, NV_DA, NV_VFM1 };
+enum { CV_A = 0, CV_B, CV_F, CV_Y1, CV_R1, CV_Y2, CV_R2, CV_Y3, CV_R3, CV_E, CV_YB };
+enum { NV_LAMT = 0, NV_MUT, NV_M1, NV_M2, NV_M3, NV_M4, NV_M5, NV_M6, NV_M7, NV_V, NV_DA, NV_VFM1, NV_M8 };
 
 // sum over the joints between `body` and its root: g_q[k] += sign * ad(sP_k, Y) . F + Wtot . dF_k, with Y the running sum of
 // V_i sF_i over the dofs at or below the joint of k (getConstraintForcesJacobian's row sum folded over V)
@@ -215,6 +218,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
   const int* rowInfo = keepI + KL.oRowInfo();
   const double* xall = keepD + KL.oX();
   const double* vf = keepD + KL.oVf();
+  const double* restOfRow = keepD + KL.oRest();
   auto massed = [&](int r) { return keepD + KL.oMassed() + (size_t)r * nd; };
   auto contactOf = [&](int r) { return keepD + KL.oContacts() + (size_t)(rowInfo[r] >> 2) * 26; };
   // ---- classification: clamping rows in row order, then upper-bound rows ----
@@ -232,7 +236,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     }
   double* lamT = bw.nv(NV_LAMT);
   for (int d = 0; d < nd; d++) lamT[d] = gqdn[vidx(layout, N, nd, w, d)];
-  bool pinv = false, fcDiffers = false;
+  bool pinv = false, fcDiffers = false, bounced = false;
   if (c > 0) {
     status |= 1;
     // ---- world transforms and screws ----
@@ -318,7 +322,9 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       const double* col = bw.Ac(j);
       const double* ma = bw.MA(j);
       for (int d = 0; d < nd; d++) { sb += col[d] * vf[d]; sa += ma[d] * lamT[d]; }
-      vb[j] = -sb; va[j] = sa; vfc[j] = xall[bw.clampRow()[j]];
+      const double Bj = 1.0 + restOfRow[bw.clampRow()[j]];
+      if (Bj != 1.0) bounced = true;
+      vb[j] = -(Bj * sb); va[j] = sa; vfc[j] = xall[bw.clampRow()[j]];
     }
     // ---- Q = A_c^T M^-1 A and the pseudo-inverse products ----
     LcpView v;
@@ -356,13 +362,18 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     // ---- lambda~ and the n-vectors m1..m7, delta-acceleration ----
     double *m1 = bw.nv(NV_M1), *m2 = bw.nv(NV_M2), *m3 = bw.nv(NV_M3), *m4 = bw.nv(NV_M4), *m5 = bw.nv(NV_M5), *m6 = bw.nv(NV_M6), *m7 = bw.nv(NV_M7);
     double* da = bw.nv(NV_DA);
-    for (int d = 0; d < nd; d++) { m1[d] = m2[d] = m3[d] = m4[d] = m5[d] = m6[d] = m7[d] = da[d] = 0.0; }
+    double* m8 = bw.nv(NV_M8);   // M^-1 A_c (yB - y1): zero without restitution
+    double* yB = bw.cv(CV_YB);
+    for (int d = 0; d < nd; d++) { m1[d] = m2[d] = m3[d] = m4[d] = m5[d] = m6[d] = m7[d] = m8[d] = da[d] = 0.0; }
     for (int j = 0; j < c; j++) {
       const double* col = bw.Ac(j);
       const double* ma = bw.MA(j);
       const double* mc = massed(bw.clampRow()[j]);
+      const double e = restOfRow[bw.clampRow()[j]];
+      yB[j] = (1.0 + e) * y1[j];
       for (int d = 0; d < nd; d++) {
-        lamT[d] -= y1[j] * col[d];
+        lamT[d] -= yB[j] * col[d];
+        m8[d] += (e * y1[j]) * mc[d];
         m1[d] += r1[j] * ma[d]; m2[d] += y1[j] * mc[d]; m3[d] += r2[j] * mc[d]; m4[d] += y2[j] * ma[d];
         m5[d] += r3[j] * mc[d]; m6[d] += y3[j] * ma[d]; m7[d] += (vfc[j] - r1[j]) * ma[d];
         da[d] += vfc[j] * ma[d];
@@ -399,11 +410,13 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
   });
   if (c == 0) return status;
   // ---- extra mass-matrix pairs: dL/dq -= mu_a^T (dM/dq) a_b ----
-  for (int pair = 0; pair < 3; pair++) {
+  if (bounced) for (int d = 0; d < nd; d++) bw.nv(NV_DA)[d] *= dt;  // M^-1 A f_c (the reverse sweep above is done with it)
+  for (int pair = 0; pair < 4; pair++) {
     if (pair == 0 && !fcDiffers) continue;
-    if (pair > 0 && !pinv) continue;
-    const double* ma = pair == 0 ? bw.nv(NV_M2) : (pair == 1 ? bw.nv(NV_M3) : bw.nv(NV_M5));
-    const double* mb = pair == 0 ? bw.nv(NV_M7) : (pair == 1 ? bw.nv(NV_M4) : bw.nv(NV_M6));
+    if ((pair == 1 || pair == 2) && !pinv) continue;
+    if (pair == 3 && !bounced) continue;
+    const double* ma = pair == 0 ? bw.nv(NV_M2) : (pair == 1 ? bw.nv(NV_M3) : (pair == 2 ? bw.nv(NV_M5) : bw.nv(NV_M8)));
+    const double* mb = pair == 0 ? bw.nv(NV_M7) : (pair == 1 ? bw.nv(NV_M4) : (pair == 2 ? bw.nv(NV_M6) : bw.nv(NV_DA)));
     twistsFromRates<NB>(sn, nb, [&](int d) { return ma[d]; }, ws.U, ws.mu);
     twistsFromRates<NB>(sn, nb, [&](int d) { return mb[d]; }, dA, nullptr);
     idAdjointEx<NB, false, 2>(sn, nb, ws, dA, [&](int d, double dq, double) { gq[vidx(layout, N, nd, w, d)] -= dq; },
@@ -415,7 +428,8 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
   // ---- contact geometry: dL/dq += sum_rows (dA_row/dq)^T V_row ----
   {
     const double *y1 = bw.cv(CV_Y1), *r1 = bw.cv(CV_R1), *y2 = bw.cv(CV_Y2), *r2 = bw.cv(CV_R2), *y3 = bw.cv(CV_Y3), *r3 = bw.cv(CV_R3), *vfc = bw.cv(CV_F);
-    const double *m1 = bw.nv(NV_M1), *m2 = bw.nv(NV_M2), *m3 = bw.nv(NV_M3), *m4 = bw.nv(NV_M4), *m5 = bw.nv(NV_M5), *m6 = bw.nv(NV_M6);
+    const double *m1 = bw.nv(NV_M1), *m2 = bw.nv(NV_M2), *m3 = bw.nv(NV_M3), *m4 = bw.nv(NV_M4), *m5 = bw.nv(NV_M5), *m6 = bw.nv(NV_M6), *m8 = bw.nv(NV_M8);
+    const double* yB = bw.cv(CV_YB);
     double* V = bw.nv(NV_V);
     double* acc = bw.nv(NV_VFM1);  // dL/dq contributions of the geometry, accumulated locally
     for (int d = 0; d < nd; d++) acc[d] = 0.0;
@@ -425,9 +439,9 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       const int j = isUb ? bw.ubNormal()[slot - c] : slot;
       const double e = isUb ? bw.cv(CV_E)[slot - c] : 1.0;
       for (int d = 0; d < nd; d++) {
-        const double mu = muT[d] + m2[d];  // M^-1 lambda
+        const double mu = muT[d] + m2[d] + m8[d];  // M^-1 lambda = mu~ + M^-1 A_c yB
         double val = vfc[j] * mu - r1[j] * m2[d] + y2[j] * m3[d] + y3[j] * m5[d];
-        if (!isUb) val += -y1[j] * (vf[d] + m1[d]) + r2[j] * m4[d] + r3[j] * m6[d];
+        if (!isUb) val += -yB[j] * vf[d] - y1[j] * m1[d] + r2[j] * m4[d] + r3[j] * m6[d];
         V[d] = e * val;
       }
       const double* ct = contactOf(r);

@@ -595,7 +595,6 @@ int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* g
   if (rc) return rc;
   if (h->hasContacts) {
     if (h->ctopo.gradients == 0) return fail(h, DDB_ERR_STATE, "ddb_backward: this handle steps with the solver's gradients disabled (reserved[1] = 1)");
-    if (h->ctopo.bouncing) return fail(h, DDB_ERR_STATE, "ddb_backward: restitution > 0 (bouncing constraints) is not supported by the backward pass");
     DDB_CUDA(h, contactBackwardLaunch(s, h->N, h->nb, h->n, h->cmax, h->kmax, h->topo.layout, h->slots[h->cur], h->keepD[h->cur], h->keepI[h->cur],
                                       gqn, gqdn, gq, gqd, gtau, h->cwork_d, h->cwork_i, h->clcp_d, h->clcp_i, h->lim_dev, h->bwdStatus));
     h->launches++;
@@ -617,7 +616,6 @@ int ddb_jacobians(ddb_handle* h, void* stream, double* pp, double* pv, double* v
   if (h->hasContacts) {
     // rows of the five Jacobians by pulling unit loss gradients back through the step (2 n backward passes)
     if (h->ctopo.gradients == 0) return fail(h, DDB_ERR_STATE, "ddb_jacobians: this handle steps with the solver's gradients disabled (reserved[1] = 1)");
-    if (h->ctopo.bouncing) return fail(h, DDB_ERR_STATE, "ddb_jacobians: restitution > 0 (bouncing constraints) is not supported by the backward pass");
     const size_t V = (size_t)h->N * h->n;
     if (!h->jacTmp) DDB_CUDA(h, cudaMalloc(&h->jacTmp, 5 * V * sizeof(double)));
     double *unit = h->jacTmp, *zero = unit + V, *o1 = unit + 2 * V, *o2 = unit + 3 * V, *o3 = unit + 4 * V;

@@ -19,7 +19,8 @@
 //                                   finite-difference recipes for d(M^-1 x)/dq (eps 5e-7, :5990-6027) and dC (eps 1e-7, :6121-6157)
 // The derivative of a FreeJoint's force screw with respect to the joint's own coordinates is taken as ad(position screw,
 // force screw), the closed form of what FreeJoint::getScrewAxisGradientForForce (FreeJoint.cpp:779-814) evaluates.
-// Restitution (bouncing constraints, BackpropSnapshot::getBounceApproximationJacobian) is not restated: e = 0 only.
+// Restitution enters through getBounceDiagonals (1 + e on clamping rows that bounced) in the LCP offset b_c and its Jacobians;
+// BackpropSnapshot::getBounceApproximationJacobian is a stand-alone getter the backprop path does not call (pos-pos is the joints' own).
 #pragma once
 #include "dd_contact.hpp"
 #include "dd_step.hpp"
@@ -294,7 +295,7 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
   const double dt = M.dt;
   // world-level row classification
   std::vector<GradRow> clamp, ub;
-  std::vector<double> fc, bc;
+  std::vector<double> fc, bc, bounce;  // bounce: 1 + restitution coefficient of a clamping row that bounced
   std::vector<int> ubNormalClamp;  // clamping index of the normal row an upper-bound row points at
   std::vector<double> ubE;
   for (const GroupLCP& g : R.groups) {
@@ -309,6 +310,7 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
           if (pass == 0 && g.mapping[r] == -1) {
             clampIdxOfRow[r] = (int)clamp.size();
             clamp.push_back(row); fc.push_back(g.x[r]); bc.push_back(g.b[r]);
+            bounce.push_back(1.0 + ((size_t)r < g.restitution.size() ? g.restitution[r] : 0.0));  // getBounceDiagonals (:753)
           } else if (pass == 1 && g.mapping[r] >= 0) {
             const int fp = g.mapping[r];
             const double upper = g.x[fp] * g.hi[r], lower = g.x[fp] * g.lo[r];
@@ -389,16 +391,18 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
   auto dAcT = [&](const std::vector<double>& v) { Mat o(nc, n); for (int j = 0; j < nc; j++) for (int w = 0; w < n; w++) { double s = 0; for (int i = 0; i < n; i++) s += Jc[j][(size_t)w * n + i] * v[i]; o(j, w) = s; } return o; };
   auto dAubT = [&](const std::vector<double>& v) { Mat o(nu, n); for (int j = 0; j < nu; j++) for (int w = 0; w < n; w++) { double s = 0; for (int i = 0; i < n; i++) s += Ju[j][(size_t)w * n + i] * v[i]; o(j, w) = s; } return o; };
 
+  // getJacobianOfLCPOffsetClampingSubset (BackpropSnapshot.cpp:4252-4299): every variant is getBounceDiagonals().asDiagonal() * -(...)
+  auto bounced = [&](Mat m) { for (int j = 0; j < nc; j++) for (int w = 0; w < m.c; w++) m(j, w) *= bounce[j]; return m; };
   // ---- force-vel and vel-vel ----
   {
-    const Mat dB = scale(mm(AcT, Minv), -dt);
+    const Mat dB = bounced(scale(mm(AcT, Minv), -dt));
     const Mat dF = codSolveMat(Q, dB);
     const Mat fv = mm(Minv, add(mm(A, dF), I_n, dt));
     J.forceVel = fv.a;
   }
   const Mat dCv = dCof(true);
   {
-    const Mat dB = scale(mm(AcT, add(I_n, mm(Minv, dCv), -dt)), -1.0);
+    const Mat dB = bounced(scale(mm(AcT, add(I_n, mm(Minv, dCv), -dt)), -1.0));
     const Mat dF = codSolveMat(Q, dB);
     const Mat vv = add(I_n, mm(Minv, add(mm(A, dF), dCv, -dt)));
     J.velVel = vv.a;
@@ -411,7 +415,7 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
     for (int i = 0; i < n; i++) { f[i] = tau[i] - C[i]; z[i] = dt * f[i] + Afc[i]; }
     const Mat dM = dMinv(z);
     // dB
-    const Mat dB = scale(add(dAcT(vf), scale(mm(AcT, add(dMinv(f), mm(Minv, dCq), -1.0)), dt)), -1.0);
+    const Mat dB = bounced(scale(add(dAcT(vf), scale(mm(AcT, add(dMinv(f), mm(Minv, dCq), -1.0)), dt)), -1.0));
     // dQ_b
     const Mat P = codSolveMat(Q, I_c);
     const std::vector<double> Eempty;
@@ -447,7 +451,7 @@ inline void jacobiansReferenceContact(const Model& M, const double* q, const dou
     const Mat pv = add(dM, mm(Minv, inner));
     J.posVel = pv.a;
   }
-  // ---- pos-pos / vel-pos: World::getPosPosJacobian / getVelPosJacobian (no bouncing constraints: e = 0) ----
+  // ---- pos-pos / vel-pos: World::getPosPosJacobian / getVelPosJacobian (BackpropSnapshot.cpp:1237-1360) ----
   {
     Jacobians K;
     K.resize(n);
@@ -514,7 +518,7 @@ inline bool frozenSetVelocity(const Model& M, const double* q, const double* qd,
   const Screws sc = worldScrews(M, d);
   std::vector<std::vector<double>> colsC, colsU;
   std::vector<int> ubN;
-  std::vector<double> ubE;
+  std::vector<double> ubE, bounceC;  // bounceC: 1 + restitution of the clamping rows that bounced in `ref` (frozen with the active set)
   for (const GroupLCP& g : ref.groups) {
     std::vector<int> clampIdxOfRow(g.n, -1);
     for (int pass = 0; pass < 2; pass++)
@@ -524,7 +528,10 @@ inline bool frozenSetVelocity(const Model& M, const double* q, const double* qd,
           const int r = g.offset[i] + k;
           GradRow row{g.cons[i], k, rowDirection(c, k), zero6<double>()};
           row.F = join(cross(c.contact.point, row.dir), row.dir);
-          if (pass == 0 && g.mapping[r] == -1) { clampIdxOfRow[r] = (int)colsC.size(); colsC.push_back(constraintForces(M, sc, c, row)); }
+          if (pass == 0 && g.mapping[r] == -1) {
+            clampIdxOfRow[r] = (int)colsC.size(); colsC.push_back(constraintForces(M, sc, c, row));
+            bounceC.push_back(1.0 + ((size_t)r < g.restitution.size() ? g.restitution[r] : 0.0));
+          }
           else if (pass == 1 && g.mapping[r] >= 0) {
             const int fp = g.mapping[r];
             const double upper = g.x[fp] * g.hi[r], lower = g.x[fp] * g.lo[r];
@@ -547,7 +554,7 @@ inline bool frozenSetVelocity(const Model& M, const double* q, const double* qd,
   const Mat MA = mm(Minv, A);
   const Mat Q = mm(tr(Ac), MA);
   Mat b(nc, 1);
-  for (int j = 0; j < nc; j++) { double s = 0; for (int i = 0; i < n; i++) s += Ac(i, j) * vel[i]; b(j, 0) = -s; }
+  for (int j = 0; j < nc; j++) { double s = 0; for (int i = 0; i < n; i++) s += Ac(i, j) * vel[i]; b(j, 0) = -bounceC[j] * s; }
   const Mat f = codSolveMat(Q, b);
   const Mat dv = mm(MA, f);
   for (int i = 0; i < n; i++) qdNext[i] = vel[i] + dv(i, 0);

@@ -218,7 +218,34 @@ def fixed_base_arm_on_floor_states(N, seed):
     return q, qd, tau
 
 
+def bouncing_boxes():
+    """Two translating boxes with restitution 0.8 / 0.9 hitting the floor (e = 0.8 * 1.0 resp. 0.9 * 1.0 with the floor's coefficient 1):
+    contacts whose closing speed times e exceeds DART_BOUNCING_VELOCITY_THRESHOLD bounce (ContactConstraint.cpp:395-418), the
+    others do not; the clamping rows that bounced carry 1 + e in getBounceDiagonals."""
+    w = skeletons.WorldDescription()
+    _floor(w)
+    for sk in w.skeletons:
+        for b in sk.bodies:
+            b.setRestitutionCoeff(1.0)
+    _xyz_body(w, "a", box=[1, 1, 1], restitution=0.8)
+    _xyz_body(w, "b", box=[0.5, 0.5, 0.5], mass=0.7, restitution=0.9)
+    return w
+
+
+def bouncing_boxes_states(N, seed):
+    rng = np.random.default_rng(seed)
+    pen = lambda: rng.uniform(1e-4, 3e-3, N)
+    q = np.stack([rng.uniform(-3, -2, N), rng.uniform(-1, 1, N), 0.5 - pen(),
+                  rng.uniform(2, 3, N), rng.uniform(-1, 1, N), 0.25 - pen()], axis=1)
+    qd = rng.uniform(-0.5, 0.5, (N, 6))
+    qd[:, 2] = -rng.uniform(0.0, 1.5, N)     # some slower than 0.1 / e (no bounce), most faster
+    qd[:, 5] = -rng.uniform(0.3, 2.0, N)
+    tau = rng.uniform(-1, 1, (N, 6))
+    return q, qd, tau
+
+
 SCENES = {
+    "bouncing_boxes": (bouncing_boxes, bouncing_boxes_states),
     "fixed_base_arm_on_floor": (fixed_base_arm_on_floor, fixed_base_arm_on_floor_states),
     "box_stack": (box_stack, box_stack_states),
     "free_box_on_floor": (free_box_on_floor, free_box_on_floor_states),

@@ -33,7 +33,7 @@ def rel(a, b):
     return float(np.max(np.abs(a - b) / np.maximum(1.0, np.abs(b))))  # the reference's `equals`: abs below 1, relative above
 
 
-@pytest.mark.parametrize("scene", ["sliding_box", "pendulum_on_floor", "sphere_pendulum_on_floor", "free_box_on_floor", "two_box_stack", "separate_groups"])
+@pytest.mark.parametrize("scene", ["sliding_box", "pendulum_on_floor", "sphere_pendulum_on_floor", "free_box_on_floor", "two_box_stack", "separate_groups", "bouncing_boxes"])
 def test_oracle_contact_jacobians_vs_detector_finite_differences(scene):
     make, states = SCENES[scene]
     o = OracleWorld(make())

@@ -288,18 +288,20 @@ def test_dart_layer_autograd_through_contacts():
     assert checked > N
 
 
-def test_backward_with_restitution_is_refused_not_faked():
-    from contact_scenes import _floor, _xyz_body
-    from diffdart_b200 import skeletons
-    desc = skeletons.WorldDescription()
-    _floor(desc)
-    _xyz_body(desc, "bouncy", box=[1, 1, 1], restitution=0.8)
-    for sk in desc.skeletons:
-        for b in sk.bodies:
-            b.setRestitutionCoeff(0.8)
-    q = np.array([[0.0, 0.0, 0.499]]); qd = np.array([[0.0, 0.0, -1.0]]); tau = np.zeros((1, 3))
+def test_restitution_bounces_and_is_differentiated():
+    """Restitution > 0: contacts closing faster than the bounce threshold leave with -e times their normal velocity, and the backward
+    carries the bounce diagonals (covered against the oracle by the bouncing_boxes scene of the parametrised tests above; here the
+    physics itself and central differences of the layer)."""
+    from contact_scenes import bouncing_boxes
+    from diffdart_b200.dart_layer import dart_layer
+    desc = bouncing_boxes()
+    q = np.array([[-2.0, 0.0, 0.499, 2.0, 0.0, 0.249]]); qd = np.array([[0.0, 0.0, -1.0, 0.0, 0.0, -0.05]]); tau = np.zeros((1, 6))
     world = BatchedWorld(desc, 1)
-    world.setPositions(cuda(q)); world.setVelocities(cuda(qd)); world.setForces(cuda(tau))
-    snap = forwardPass(world)
-    with pytest.raises(RuntimeError, match="restitution"):
-        snap.getJacobians()
+    tq, tqd, tt = (cuda(a).requires_grad_(True) for a in (q, qd, tau))
+    qn, qdn = dart_layer(world, tq, tqd, tt)
+    v = qdn.detach().cpu().numpy()[0]
+    assert abs(v[2] - 0.8 * (1.0 + 9.81e-3)) < 1e-6      # bounced: -e times the pre-contact normal velocity (gravity acted for one step)
+    assert abs(v[5]) < 1e-9                               # too slow to bounce: comes to rest
+    qdn[0, 2].backward()
+    g = tqd.grad.cpu().numpy()[0]
+    assert abs(g[2] + 0.8) < 1e-6 and abs(g[5]) < 1e-12   # d v_z' / d v_z = -e through the bounce diagonal
