@@ -10,7 +10,7 @@
 #define __device__
 #define __host__
 #define __forceinline__ inline
-#define __constant__
+#define __constant__ static  // one copy per translation unit, as on the device
 #define __global__
 #define __restrict__
 #define __launch_bounds__(...)
