@@ -267,6 +267,55 @@ def walker_bench(local_rank, rank):
     return {"ms_per_rollout": e0.elapsed_time(e1), "finite": bool(torch.isfinite(taus.grad).all() and torch.isfinite(q0.grad).all())}
 
 
+CARTPOLE_WORLDS = 1 << 20
+CARTPOLE_WORKLOAD = ("cartpole: 2^20 worlds per GPU of the reference's cartpole fixture (prismatic cart + revolute pole, no contact; BASELINE configs[0] as a "
+                     "batch, SURVEY 8(d) C1: q0 ~ U(-1,1), q1 ~ U(-pi,pi), qd ~ U(-1,1), tau = (U(-10,10), 0)); step = forward step + analytic backward VJP, "
+                     "8-step rollouts with backprop through ddb_rollout_forward / ddb_rollout_backward")
+
+
+def cartpole_bench(lib, local_rank, rank, lanes, rollouts=6):
+    """BASELINE configs[0] as a batch: the north star's 'contact-free 2-link cartpole batch'."""
+    import torch
+
+    from diffdart_b200 import _abi, skeletons
+
+    N, n, T = CARTPOLE_WORLDS, 2, 8
+    dev = torch.device("cuda", local_rank)
+    topo, params, keep = skeletons.create_cartpole().to_ctypes(n_snapshot_slots=T)
+    h = _abi._vp()
+    if lib.ddb_create(C.byref(topo), C.byref(params), N, local_rank, C.byref(h)):
+        raise RuntimeError(lib.ddb_last_error(h).decode())
+    rng = np.random.default_rng(rank)
+    mk = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    q0 = mk(np.stack([rng.uniform(-1, 1, N), rng.uniform(-np.pi, np.pi, N)], axis=1))
+    qd0 = mk(rng.uniform(-1, 1, (N, n)))
+    taus = mk(np.stack([rng.uniform(-10, 10, (T, N)), np.zeros((T, N))], axis=2))
+    gp, gv = torch.randn(T, N, n, dtype=torch.float64, device=dev), torch.randn(T, N, n, dtype=torch.float64, device=dev)
+    poses, vels, gtau = torch.empty_like(taus), torch.empty_like(taus), torch.empty_like(taus)
+    gq0, gqd0 = torch.empty_like(q0), torch.empty_like(q0)
+    sp = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    lib.ddb_set_lanes(h, lanes)
+
+    def roll():
+        r1 = lib.ddb_rollout_forward(h, sp, T, q0.data_ptr(), qd0.data_ptr(), taus.data_ptr(), poses.data_ptr(), vels.data_ptr())
+        r2 = lib.ddb_rollout_backward(h, sp, T, gp.data_ptr(), gv.data_ptr(), gq0.data_ptr(), gqd0.data_ptr(), gtau.data_ptr())
+        if r1 or r2:
+            raise RuntimeError(lib.ddb_last_error(h).decode())
+
+    for _ in range(2):
+        roll()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(rollouts):
+        roll()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / (rollouts * T)
+    lib.ddb_destroy(h)
+    return ms
+
+
 def contact_cpu_baseline(n_worlds=1024):
     """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
     from diffdart_b200 import skeletons
@@ -470,6 +519,12 @@ def run_ours(args):
         e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = time.perf_counter() - t0
+    # ---- BASELINE configs[0] as a batch (its own handle): 2^20 cartpoles ----
+    try:
+        cartpole_ms = cartpole_bench(lib, local_rank, rank, args.lanes)
+    except Exception as exc:  # optional workload: report, never fail the headline
+        cartpole_ms = float("nan")
+        print("cartpole batch failed: %s" % str(exc)[:200], file=sys.stderr)
     # ---- second workload: contact-rich box stacking (its own handle) ----
     contact_ms, contact_tiers = float("nan"), {}
     if not args.no_contact:
@@ -489,10 +544,10 @@ def run_ours(args):
             walker = {"error": str(exc)[:200]}
     walker_ms = walker["ms_per_rollout"] if walker and "ms_per_rollout" in walker else float("nan")
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -530,6 +585,13 @@ def run_ours(args):
                               "whole_step_frac": (FWD_FLOPS + BWD_FLOPS) * N * args.steps / (elapsed_ms * 1e-3) / 1e12 / peak.value,
                               "note": "flops per world as executed (ncu, profiles/r02a_ncu_full_summary.csv); whole_step = the timed rollout (chunks of both kernels overlap on the lanes)"},
         }
+        if cartpole_ms == cartpole_ms:
+            cp_bytes = 104 * 2  # 104 n bytes per world-step (VJP)
+            line["cartpole_batch"] = {"workload": CARTPOLE_WORKLOAD, "value": world_size * CARTPOLE_WORLDS / (cartpole_ms * 1e-3), "unit": UNIT,
+                                      "ms_per_step": cartpole_ms, "worlds_per_gpu": CARTPOLE_WORLDS, "scaling": "weak",
+                                      "algorithmic_gb_per_s": cp_bytes * CARTPOLE_WORLDS / (cartpole_ms * 1e-3) / 1e9,
+                                      "snapshot_gb_per_s": 2 * 2 * 13 * 16 * CARTPOLE_WORLDS / (cartpole_ms * 1e-3) / 1e9,
+                                      "note": "snapshot_gb_per_s = the 208 B per body the forward writes and the backward reads back (the traffic that binds this small model)"}
         if not args.no_contact:
             line["contact_rich"] = {"workload": CONTACT_WORKLOAD, "value": world_size * CONTACT_WORLDS / (contact_ms * 1e-3), "unit": UNIT,
                                     "ms_per_step": contact_ms, "worlds_per_gpu": CONTACT_WORLDS, "scaling": "weak",
