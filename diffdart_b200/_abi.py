@@ -10,7 +10,7 @@ DDB_MAX_BODIES = 48
 DDB_MAX_DOFS = 48
 
 JOINT_WELD, JOINT_REVOLUTE, JOINT_PRISMATIC, JOINT_FREE = 0, 1, 2, 3
-SHAPE_NONE, SHAPE_BOX, SHAPE_SPHERE = 0, 1, 2
+SHAPE_NONE, SHAPE_BOX, SHAPE_SPHERE, SHAPE_CAPSULE = 0, 1, 2, 3
 LAYOUT_WORLD_MAJOR, LAYOUT_DOF_MAJOR = 0, 1
 
 ERRORS = {1: "DDB_ERR_INVALID", 2: "DDB_ERR_CUDA", 3: "DDB_ERR_NO_DEVICE", 4: "DDB_ERR_STATE"}

@@ -357,14 +357,83 @@ DDB_COL_DI int sphereSphere(double r0_, const Pose& c0, double r1_, const Pose& 
   return 1;
 }
 
-// collide(o1, o2) dispatcher (DARTCollide.cpp:4675-5183) for SHAPE_BOX / SHAPE_SPHERE
+// collideCapsuleBox / collideBoxCapsule (DARTCollide.cpp:4217-4361): when the contact lies beyond an end plane of the cylinder part the
+// reference collides that end's sphere with the box (collideSphereBox / collideBoxSphere on T * translate(0, 0, +-height / 2)); it takes
+// the contact position from libccd's MPR, which is not part of the reference tree. Here the end is chosen in closed form: with
+// f(t) = squared distance of the axis point e0 + t (e1 - e0) to the box (convex in t), end 0 is the closest feature iff f'(0) > 0,
+// end 1 iff f'(1) < 0; an end point inside the box counts as that end. Everything else (closest feature on the cylinder part: the
+// reference's pipe contacts, createCapsuleMeshContact :2887-3300) is not carried: returns -1.
+DDB_COL_DI int capsuleBox(const double* cap, const Pose& Tc, const double* boxSize, const Pose& Tb, bool capsuleIsFirst, ContactPoint* out) {
+  const double r = cap[0], hh = 0.5 * cap[1];
+  const double half[3] = {0.5 * boxSize[0], 0.5 * boxSize[1], 0.5 * boxSize[2]};
+  double e[2][3], pl[2][3];  // end centres in the world and in the box frame
+  for (int s = 0; s < 2; s++) {
+    const double z = s == 0 ? -hh : hh;
+    for (int i = 0; i < 3; i++) e[s][i] = Tc.R[3 * i + 2] * z + Tc.p[i];
+    const double d[3] = {e[s][0] - Tb.p[0], e[s][1] - Tb.p[1], e[s][2] - Tb.p[2]};
+    for (int k = 0; k < 3; k++) pl[s][k] = colDot(Tb.R, k, d);
+  }
+  // derivative of the squared distance along the axis at both ends, and the distances themselves
+  double slope[2] = {0.0, 0.0}, dist2[2] = {0.0, 0.0};
+  for (int s = 0; s < 2; s++)
+    for (int k = 0; k < 3; k++) {
+      double g = 0.0;
+      if (pl[s][k] > half[k]) g = pl[s][k] - half[k];
+      else if (pl[s][k] < -half[k]) g = pl[s][k] + half[k];
+      slope[s] += g * (pl[1][k] - pl[0][k]);
+      dist2[s] += g * g;
+    }
+  int end = -1;
+  if (dist2[0] == 0.0 && dist2[1] == 0.0) return -1;
+  if (dist2[0] == 0.0) end = 0;
+  else if (dist2[1] == 0.0) end = 1;
+  else if (slope[0] > 0.0) end = 0;
+  else if (slope[1] < 0.0) end = 1;
+  if (end < 0) {
+    // closest feature on the cylinder part: only a miss can be reported (no point of the axis within the radius of the box)
+    // f is convex: its minimum over [0, 1] is at least min(f(0) + slope terms ...) - decided by bisection on f'
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 60; it++) {
+      const double t = 0.5 * (lo + hi);
+      double sl = 0.0;
+      for (int k = 0; k < 3; k++) {
+        const double x = pl[0][k] + t * (pl[1][k] - pl[0][k]);
+        double g = 0.0;
+        if (x > half[k]) g = x - half[k];
+        else if (x < -half[k]) g = x + half[k];
+        sl += g * (pl[1][k] - pl[0][k]);
+      }
+      if (sl > 0.0) hi = t; else lo = t;
+    }
+    const double t = 0.5 * (lo + hi);
+    double f = 0.0;
+    for (int k = 0; k < 3; k++) {
+      const double x = pl[0][k] + t * (pl[1][k] - pl[0][k]);
+      double g = 0.0;
+      if (x > half[k]) g = x - half[k];
+      else if (x < -half[k]) g = x + half[k];
+      f += g * g;
+    }
+    return f > r * r ? 0 : -1;
+  }
+  Pose Ts = Tc;
+  for (int i = 0; i < 3; i++) Ts.p[i] = e[end][i];
+  return boxSphereImpl(boxSize, Tb, r, Ts, capsuleIsFirst, out);
+}
+
+// collide(o1, o2) dispatcher (DARTCollide.cpp:4675-5183) for SHAPE_BOX / SHAPE_SPHERE / SHAPE_CAPSULE; -1 = a pair this path does not carry
 DDB_COL_DI int collidePair(int shape1, const double* size1, const Pose& T1, int shape2, const double* size2, const Pose& T2, ContactPoint* out) {
   if (shape1 == 2) {                                                     // sphere
     if (shape2 == 2) return sphereSphere(size1[0], T1, size2[0], T2, out);
     if (shape2 == 1) return boxSphereImpl(size2, T2, size1[0], T1, true, out);   // collideSphereBox
+    if (shape2 == 3) return -1;
   } else if (shape1 == 1) {                                              // box
     if (shape2 == 2) return boxSphereImpl(size1, T1, size2[0], T2, false, out);  // collideBoxSphere
     if (shape2 == 1) return boxBox(size1, T1, size2, T2, out);
+    if (shape2 == 3) return capsuleBox(size2, T2, size1, T1, false, out);        // collideBoxCapsule
+  } else if (shape1 == 3) {                                              // capsule
+    if (shape2 == 1) return capsuleBox(size1, T1, size2, T2, true, out);         // collideCapsuleBox
+    return -1;
   }
   return 0;
 }

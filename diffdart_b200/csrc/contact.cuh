@@ -316,6 +316,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     shapePose(cw.W(bb), sb, Tb);
     ContactPoint pts[8];
     const int np = collidePair(sa.shape, sa.size, Ta, sb.shape, sb.size, Tb, pts);
+    if (np < 0) out.tier_mask |= 1 << 9;  // a capsule pair in a configuration this path does not carry (collide.cuh): reported, never guessed
     for (int k = 0; k < np; k++) {
       const ContactPoint& c = pts[k];
       bool close = false;

@@ -105,6 +105,14 @@ class BodyNode:
         return self
 
 
+    def setCapsuleShape(self, radius, height, R=None, p=None):
+        """CapsuleShape(radius, height): axis = local z, `height` is the length of the cylinder part (dart/dynamics/CapsuleShape.hpp)."""
+        self.shape_type = _abi.SHAPE_CAPSULE
+        self.shape_size = np.array([radius, height, 0.0])
+        self.shape_offset = _iso(R, p)
+        return self
+
+
 class Skeleton:
     def __init__(self, name="skeleton"):
         self.name = name

@@ -53,7 +53,8 @@ enum {
 };
 
 /* Collision shapes handled by the in-tree narrow phase (dart/collision/dart/DARTCollide.cpp). */
-enum { DDB_SHAPE_NONE = 0, DDB_SHAPE_BOX = 1, DDB_SHAPE_SPHERE = 2 };
+enum { DDB_SHAPE_NONE = 0, DDB_SHAPE_BOX = 1, DDB_SHAPE_SPHERE = 2,
+       DDB_SHAPE_CAPSULE = 3 /* axis = local z; against boxes only, and only where an end cap is the closest feature (see ddb_collide_pairs) */ };
 
 enum { DDB_LAYOUT_WORLD_MAJOR = 0, DDB_LAYOUT_DOF_MAJOR = 1 };
 
@@ -87,7 +88,7 @@ typedef struct ddb_body {
   double moment[6];    /* Ixx Iyy Izz Ixy Ixz Iyz (Inertia.cpp:394-409)      */
   double friction;     /* BodyNodeAspect.hpp:47 default 1.0                  */
   double restitution;  /* BodyNodeAspect.hpp:48 default 0.0                  */
-  double shape_size[3];/* box: full extents; sphere: radius in [0]           */
+  double shape_size[3];/* box: full extents; sphere: radius in [0]; capsule: radius in [0], height of the cylinder part in [1] */
   ddb_transform shape_offset;    /* ShapeNode relative transform             */
 } ddb_body;
 
@@ -172,7 +173,7 @@ int ddb_jacobians(ddb_handle* h, void* cuda_stream,
  * ConstrainedGroupGradientMatrices.cpp:167-324,467-697). ddb_params.reserved[0] caps the contacts per world
  * (default 64); rows = 3 * contacts.
  * status_out of ddb_forward = solver tier mask per world (bit 0 short-circuit, 1 Dantzig, 2 PGS, 3 friction dropped,
- * 8 capacity hit); active_set_out [N][max_rows] = ConstraintMapping per LCP row (-1 CLAMPING, -2 NOT_CLAMPING,
+ * 8 capacity hit, 9 a capsule pair in a configuration this path does not carry: its contacts are missing from the step); active_set_out [N][max_rows] = ConstraintMapping per LCP row (-1 CLAMPING, -2 NOT_CLAMPING,
  * -3 ILLEGAL, -4 IRRELEVANT = no such row, >= 0 UPPER_BOUND pointing at its normal row).
  */
 int32_t ddb_contact_capacity(const ddb_handle* h, int32_t* max_contacts, int32_t* max_rows);
@@ -276,6 +277,11 @@ int ddb_lcp_valid(int32_t device, void* cuda_stream, int32_t n_problems, int32_t
  * shape: DDB_SHAPE_*; size [n][3] (box extents / radius in [0]); T [n][12] (R row-major, p).
  * contacts_out [n][8][26]: point, normal, edgeAClosest, edgeAFixed, edgeADir, edgeBClosest, edgeBFixed, edgeBDir (3 each),
  * penetrationDepth, ContactType (Contact.hpp:43-80); counts_out [n]. Bit-identical to the reference's box-box.
+ * Capsules (DDB_SHAPE_CAPSULE, size = radius, height): collideCapsuleBox / collideBoxCapsule (:4217-4361) hand the pair to the sphere-box
+ * routine with the sphere of the capsule end that the contact lies beyond; the reference finds the contact position with libccd's MPR
+ * (not part of the reference tree), here the end is the one from which the distance of the capsule's axis to the box grows strictly.
+ * Where the closest feature is the cylinder part (the reference's pipe contacts, createCapsuleMeshContact :2887-3300) and for
+ * capsule-capsule / capsule-sphere pairs the pair is NOT carried: counts_out = -1, and a step reports bit 9 of its status.
  */
 int ddb_collide_pairs(int32_t device, void* cuda_stream, int32_t n_pairs, const int32_t* shape1_dev, const double* size1_dev,
                       const double* T1_dev, const int32_t* shape2_dev, const double* size2_dev, const double* T2_dev,

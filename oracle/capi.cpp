@@ -217,6 +217,7 @@ void ddo_step_contacts(void* h, const double* q, const double* qd, const double*
     rows += g.n;
     tiers |= 1 << g.tier;
   }
+  if (R.unsupportedPair) tiers |= 1 << 9;
   counts[1] = rows; counts[2] = (int)R.groups.size(); counts[3] = tiers;
 }
 

@@ -110,8 +110,49 @@ inline bool isReactive(const Model& M, int body) {
   return false;
 }
 
-// all-pairs narrow phase in collision-object order (one shape per body, flattened body order)
-inline std::vector<Contact> collideWorld(const Model& M, const Dyn<double>& d) {
+// collideCapsuleBox / collideBoxCapsule (DARTCollide.cpp:4217-4361): the end sphere the contact lies beyond goes to the sphere-box routine.
+// The reference takes the contact position from libccd's MPR (not in the reference tree: parity unpinned there); here the end is the one
+// from which the squared distance of the capsule's axis to the box grows strictly (see collide.cuh: capsuleBox, the same arithmetic).
+// Returns the contact count, or -1 where the closest feature is the cylinder part (the reference's pipe contacts, not carried).
+inline int capsuleBox(const double* cap, const double* Tc, const double* boxSize, const double* Tb, bool capsuleFirst, Contact& c) {
+  const double r = cap[0], hh = 0.5 * cap[1];
+  const double half[3] = {0.5 * boxSize[0], 0.5 * boxSize[1], 0.5 * boxSize[2]};
+  double e[2][3], pl[2][3];
+  for (int s = 0; s < 2; s++) {
+    const double z = s == 0 ? -hh : hh;
+    for (int i = 0; i < 3; i++) e[s][i] = Tc[3 * i + 2] * z + Tc[9 + i];
+    const double dd[3] = {e[s][0] - Tb[9], e[s][1] - Tb[10], e[s][2] - Tb[11]};
+    for (int k = 0; k < 3; k++) pl[s][k] = Tb[k] * dd[0] + Tb[3 + k] * dd[1] + Tb[6 + k] * dd[2];
+  }
+  auto gap = [&](double x, int k) { return x > half[k] ? x - half[k] : (x < -half[k] ? x + half[k] : 0.0); };
+  double slope[2] = {0.0, 0.0}, dist2[2] = {0.0, 0.0};
+  for (int s = 0; s < 2; s++)
+    for (int k = 0; k < 3; k++) { const double g = gap(pl[s][k], k); slope[s] += g * (pl[1][k] - pl[0][k]); dist2[s] += g * g; }
+  int end = -1;
+  if (dist2[0] == 0.0 && dist2[1] == 0.0) return -1;
+  if (dist2[0] == 0.0) end = 0;
+  else if (dist2[1] == 0.0) end = 1;
+  else if (slope[0] > 0.0) end = 0;
+  else if (slope[1] < 0.0) end = 1;
+  if (end < 0) {
+    double lo = 0.0, hi = 1.0;
+    for (int it = 0; it < 60; it++) {
+      const double t = 0.5 * (lo + hi);
+      double sl = 0.0;
+      for (int k = 0; k < 3; k++) sl += gap(pl[0][k] + t * (pl[1][k] - pl[0][k]), k) * (pl[1][k] - pl[0][k]);
+      if (sl > 0.0) hi = t; else lo = t;
+    }
+    const double t = 0.5 * (lo + hi);
+    double f = 0.0;
+    for (int k = 0; k < 3; k++) { const double g = gap(pl[0][k] + t * (pl[1][k] - pl[0][k]), k); f += g * g; }
+    return f > r * r ? 0 : -1;
+  }
+  return boxSphere(boxSize, Tb, r, e[end], capsuleFirst, c);
+}
+
+// all-pairs narrow phase in collision-object order (one shape per body, flattened body order); *unsupported is set when a capsule
+// pair is in a configuration this path does not carry
+inline std::vector<Contact> collideWorld(const Model& M, const Dyn<double>& d, bool* unsupported = nullptr) {
   std::vector<Contact> total;
   std::vector<int> obj;
   for (int i = 0; i < M.nb; i++) if (M.b[i].shape != DDB_SHAPE_NONE) obj.push_back(i);
@@ -141,10 +182,14 @@ inline std::vector<Contact> collideWorld(const Model& M, const Dyn<double>& d) {
       } else {
         Contact c;
         int n = 0;
-        if (s1 == DDB_SHAPE_SPHERE && s2 == DDB_SHAPE_SPHERE) n = sphereSphere(M.b[i].shapeSize[0], T1 + 9, M.b[j].shapeSize[0], T2 + 9, c);
+        if (s1 == DDB_SHAPE_CAPSULE && s2 == DDB_SHAPE_BOX) n = capsuleBox(M.b[i].shapeSize.v, T1, M.b[j].shapeSize.v, T2, true, c);
+        else if (s1 == DDB_SHAPE_BOX && s2 == DDB_SHAPE_CAPSULE) n = capsuleBox(M.b[j].shapeSize.v, T2, M.b[i].shapeSize.v, T1, false, c);
+        else if (s1 == DDB_SHAPE_CAPSULE || s2 == DDB_SHAPE_CAPSULE) n = -1;
+        else if (s1 == DDB_SHAPE_SPHERE && s2 == DDB_SHAPE_SPHERE) n = sphereSphere(M.b[i].shapeSize[0], T1 + 9, M.b[j].shapeSize[0], T2 + 9, c);
         else if (s1 == DDB_SHAPE_SPHERE && s2 == DDB_SHAPE_BOX) n = boxSphere(M.b[j].shapeSize.v, T2, M.b[i].shapeSize[0], T1 + 9, true, c);
         else if (s1 == DDB_SHAPE_BOX && s2 == DDB_SHAPE_SPHERE) n = boxSphere(M.b[i].shapeSize.v, T1, M.b[j].shapeSize[0], T2 + 9, false, c);
-        if (n) pair.push_back(c);
+        if (n < 0 && unsupported) *unsupported = true;
+        if (n > 0) pair.push_back(c);
       }
       // postProcess (DARTCollisionDetector.cpp:349-386): drop contacts within 3e-12 of one already recorded
       for (Contact& c : pair) {
@@ -590,6 +635,7 @@ inline void solveGroupGrad(GroupLCP& g, const std::vector<double>& cache, bool m
 }
 
 struct ContactStepResult {
+  bool unsupportedPair = false;  // a capsule pair in a configuration this path does not carry (status bit 9)
   std::vector<double> qNext, qdNext, preConstraintVel;
   std::vector<Contact> contacts;
   std::vector<Constraint> constraints;
@@ -608,7 +654,7 @@ inline void stepWithContacts(const Model& M, const double* q, const double* qd, 
   R.preConstraintVel = vel;
   d.setVelocities(vel.data());  // body velocities now reflect the unconstrained velocity update
   d.artInertia();
-  R.contacts = collideWorld(M, d);
+  R.contacts = collideWorld(M, d, &R.unsupportedPair);
   R.constraints = buildConstraints(M, d, R.contacts);
   std::vector<int> groupOf;
   const int ng = buildGroups(M, R.constraints, groupOf);

@@ -322,8 +322,69 @@ def walker_on_ground_states(N, seed):
     return q, qd, tau
 
 
+# ---- capsules: a planar two-legged hopper in the reference's .skel format (tests/fixtures/capsule_hopper.skel, written for this repo) ----
+HOPPER_SKEL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fixtures", "capsule_hopper.skel")
+
+
+def capsule_hopper_on_ground(max_contacts=8):
+    from diffdart_b200.skel_loader import load_skel
+
+    return load_skel(HOPPER_SKEL)[0].setMaxContacts(max_contacts)
+
+
+def capsule_hopper_on_ground_states(N, seed):
+    """Standing on the end caps of both shins, 0-5 mm inside the ground (shin ends reach 0.11 below the root height at the zero pose),
+    small joint angles so that the cap stays the closest feature; qd ~ U(-0.3, 0.3), joint torques ~ U(-3, 3)."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 7))
+    q[:, 0] = rng.uniform(-0.5, 0.5, N)
+    q[:, 1] = -0.1105 - rng.uniform(0.0, 5e-3, N)
+    q[:, 2:] = rng.uniform(-0.05, 0.05, (N, 5))
+    q[:, 3] -= q[:, 2]
+    q[:, 5] -= q[:, 2]
+    qd = rng.uniform(-0.3, 0.3, (N, 7))
+    tau = np.zeros((N, 7))
+    tau[:, 3:] = rng.uniform(-3, 3, (N, 4))
+    return q, qd, tau
+
+
+SCENES["capsule_hopper_on_ground"] = (capsule_hopper_on_ground, capsule_hopper_on_ground_states)
+
+HALF_CHEETAH_SKEL = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "skel", "half_cheetah.skel")
+
+
+def half_cheetah_available():
+    """The reference's data/skel/half_cheetah.skel (BASELINE configs[3]) is not part of this repo: the scene exists when it has been copied
+    to baseline/_ref/skel/ (git-ignored; it travels to the GPU box):
+      mkdir -p baseline/_ref/skel && cp /root/reference/data/skel/half_cheetah.skel baseline/_ref/skel/"""
+    return os.path.exists(HALF_CHEETAH_SKEL)
+
+
+def half_cheetah_on_ground(max_contacts=8):
+    from diffdart_b200.skel_loader import load_skel
+
+    return load_skel(HALF_CHEETAH_SKEL)[0].setMaxContacts(max_contacts)
+
+
+def half_cheetah_on_ground_states(N, seed):
+    """The model's zero pose lowered until the end caps of both foot capsules are 0-6 mm inside the ground (they reach 0.10-0.12 below
+    the root at the zero pose), small joint noise, qd ~ U(-0.3, 0.3), joint torques ~ U(-20, 20) on the six leg joints
+    (the reference's half_cheetah_bench.py drives the same joints)."""
+    rng = np.random.default_rng(seed)
+    q = np.zeros((N, 9))
+    q[:, 0] = rng.uniform(-0.5, 0.5, N)
+    q[:, 1] = -0.120 - rng.uniform(0.0, 6e-3, N)
+    q[:, 2:] = rng.uniform(-0.02, 0.02, (N, 7))
+    qd = rng.uniform(-0.3, 0.3, (N, 9))
+    tau = np.zeros((N, 9))
+    tau[:, 3:] = rng.uniform(-20, 20, (N, 6))
+    return q, qd, tau
+
+
 # scenes only the GPU tests run (the host emulation of a 35-body world is slow)
 GPU_SCENES = dict(SCENES)
 GPU_SCENES["walker_on_ground"] = (walker_on_ground, walker_on_ground_states)
 if atlas_available():
     GPU_SCENES["atlas_on_ground"] = (atlas_on_ground, atlas_on_ground_states)
+if half_cheetah_available():
+    GPU_SCENES["half_cheetah_on_ground"] = (half_cheetah_on_ground, half_cheetah_on_ground_states)
