@@ -316,6 +316,53 @@ def cartpole_bench(lib, local_rank, rank, lanes, rollouts=6):
     return ms
 
 
+CHEETAH_WORLDS, CHEETAH_STEPS = 32768, 20
+CHEETAH_WORKLOAD = ("half_cheetah: 32768 worlds per GPU of the reference's data/skel/half_cheetah.skel (9 DOFs, capsule links on a box ground, dt = 0.002; "
+                    "BASELINE configs[3]) loaded through diffdart_b200.skel_loader, one 20-step trajectory rollout with backprop through the contact "
+                    "solutions via dart_rollout (loss = |q_T|^2 + |qd_T|^2), joint torques ~ U(-20, 20) on the six leg joints")
+
+
+def cheetah_bench(local_rank, rank):
+    """BASELINE configs[3] on the reference's own model file, present when it has been copied to baseline/_ref/skel (tests/contact_scenes.py)."""
+    import torch
+
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from contact_scenes import half_cheetah_available, half_cheetah_on_ground, half_cheetah_on_ground_states
+    from diffdart_b200.rollout import dart_rollout
+    from diffdart_b200.world import BatchedWorld
+
+    if not half_cheetah_available():
+        return None
+    N, T = CHEETAH_WORLDS, CHEETAH_STEPS
+    dev = torch.device("cuda", local_rank)
+    q, qd, tau = half_cheetah_on_ground_states(N, 17 + rank)
+    world = BatchedWorld(half_cheetah_on_ground(), N, device=local_rank)
+    cu = lambda a: torch.tensor(a, dtype=torch.float64, device=dev)
+    q0, qd0 = cu(q).requires_grad_(), cu(qd).requires_grad_()
+    taus = cu(np.broadcast_to(tau, (T, N, 9)).copy()).requires_grad_()
+
+    def run():
+        for t in (q0, qd0, taus):
+            t.grad = None
+        poses, vels = dart_rollout(world, q0, qd0, taus)
+        ((poses[-1] ** 2).sum() + (vels[-1] ** 2).sum()).backward()
+
+    run()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    # solver tier masks of the last forward step the handle ran (bit 9: a capsule pair in a pipe configuration, not carried)
+    world._lib.ddb_rollout_forward(world._h, None, 1, q0.data_ptr(), qd0.data_ptr(), taus.data_ptr(), torch.empty_like(q0).data_ptr(), torch.empty_like(q0).data_ptr())
+    counts = np.zeros((N, 4), dtype=np.int32)
+    world._lib.ddb_contact_debug_host(world._h, counts.ctypes.data_as(C.c_void_p), -1, None, None, None, None, None, None, None, None, None)
+    return {"ms_per_rollout": ms, "finite": bool(torch.isfinite(taus.grad).all() and torch.isfinite(q0.grad).all()),
+            "worlds_with_uncarried_pipe_contact_at_last_step": int(((counts[:, 3] & 512) != 0).sum())}
+
+
 def contact_cpu_baseline(n_worlds=1024):
     """The oracle on the same workload: forwardPass with contacts + the reference's Jacobian recipe, one core, a few worlds."""
     from diffdart_b200 import skeletons
@@ -543,11 +590,18 @@ def run_ours(args):
         except Exception as exc:  # optional workload: report, never fail the headline
             walker = {"error": str(exc)[:200]}
     walker_ms = walker["ms_per_rollout"] if walker and "ms_per_rollout" in walker else float("nan")
+    cheetah = None
+    if not args.no_contact:
+        try:
+            cheetah = cheetah_bench(local_rank, rank)
+        except Exception as exc:  # optional workload: report, never fail the headline
+            cheetah = {"error": str(exc)[:200]}
+    cheetah_ms = cheetah["ms_per_rollout"] if cheetah and "ms_per_rollout" in cheetah else float("nan")
     # ---- reduce over ranks (max time) ----
-    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms], dtype=torch.float64, device=dev)
+    t = torch.tensor([elapsed_ms, e2e_s * 1e3, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms, cheetah_ms], dtype=torch.float64, device=dev)
     if world_size > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms = [float(x) for x in t.cpu()]
+    elapsed_ms, e2e_ms, fwd_ms, bwd_ms, contact_ms, single_ms, atlas_ms, jac_ms, walker_ms, cartpole_ms, cheetah_ms = [float(x) for x in t.cpu()]
     peak = ctypes_double()
     lib.ddb_measure_fp64_peak(local_rank, C.byref(peak))
     if rank == 0:
@@ -618,6 +672,14 @@ def run_ours(args):
                                           "finite": walker["finite"]}
             else:
                 line["walker_rollout"] = walker
+        if cheetah is not None:
+            if "ms_per_rollout" in cheetah:
+                line["half_cheetah_rollout"] = {"workload": CHEETAH_WORKLOAD, "value": world_size * CHEETAH_WORLDS * CHEETAH_STEPS / (cheetah_ms * 1e-3), "unit": UNIT,
+                                                "ms_per_rollout": cheetah_ms, "worlds_per_gpu": CHEETAH_WORLDS, "rollout_steps": CHEETAH_STEPS, "scaling": "weak",
+                                                "finite": cheetah["finite"],
+                                                "worlds_with_uncarried_pipe_contact_at_first_step_rank0": cheetah["worlds_with_uncarried_pipe_contact_at_last_step"]}
+            else:
+                line["half_cheetah_rollout"] = cheetah
         if world_size == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             v1, s1 = cpu_world_steps(N_WORLDS, threads)
