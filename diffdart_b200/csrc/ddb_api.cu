@@ -183,6 +183,20 @@ struct ddb_handle {
   cudaStream_t hstream = nullptr;
   double* stage = nullptr;  // device staging: 3n in + 2n out (+ 2n + 3n for backward), see *_host
   size_t stageDoubles = 0;
+  // CUDA graphs of the contact-free rollouts (RolloutGraphs below)
+  struct RolloutGraph {
+    int kind = 0, T = 0, K = 0;
+    const void* args[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaGraphExec_t exec = nullptr;
+    bool same(int kind_, int T_, int K_, const void* const* a) const {
+      if (kind != kind_ || T != T_ || K != K_) return false;
+      for (int i = 0; i < 6; i++) if (args[i] != a[i]) return false;
+      return true;
+    }
+  };
+  std::vector<RolloutGraph> graphs;  // instantiated graphs, most recently used last
+  RolloutGraph lastCall;             // the arguments of the previous rollout call (a graph is built when a call repeats)
+  cudaStream_t capStream = nullptr;  // origin stream of the captures (the caller's stream may be the legacy default stream, which cannot be captured)
   // the upload of this handle's topology into constant memory: the stream it was ordered on and an event behind it
   cudaEvent_t topoReady = nullptr;
   cudaStream_t topoStream = nullptr;
@@ -460,6 +474,8 @@ int ddb_destroy(ddb_handle* h) {
   for (cudaEvent_t e : h->laneDone) cudaEventDestroy(e);
   if (h->forkEv) cudaEventDestroy(h->forkEv);
   if (h->gradRun) cudaFree(h->gradRun);
+  for (auto& g : h->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  if (h->capStream) cudaStreamDestroy(h->capStream);
   delete h;
   return DDB_OK;
 }
@@ -663,6 +679,53 @@ int ddb_set_lanes(ddb_handle* h, int32_t n_lanes) {
   return DDB_OK;
 }
 
+}  // extern "C"
+
+namespace {
+// Optional (DDB_ROLLOUT_GRAPHS=1): when a contact-free rollout call repeats with the same arguments (the same buffers, as in a training
+// loop that reuses its tensors) the second call records its 2 x T x lanes launches into a CUDA graph on an internal stream, and this and
+// every later call with those arguments replays it with one cudaGraphLaunch on the caller's stream. Results are the kernels' own: the
+// graph holds exactly the launches the direct path makes (tests/test_gpu_rollout.py). Off by default: measured on B200 the host issues
+// the launches of 12 us kernels fast enough, on one GPU (33.1 us per step either way) and with eight ranks on one host (33.3 us direct,
+// 34.2 us replayed, 2000-step timed regions), and building the graph costs about a millisecond on the call that repeats.
+bool rolloutGraphsEnabled() { const char* e = getenv("DDB_ROLLOUT_GRAPHS"); return e && e[0] == '1'; }
+constexpr size_t kMaxRolloutGraphs = 8;
+
+// returns the instantiated graph for these arguments, building it with `enqueue(origin stream)` when the call repeats; nullptr = launch directly
+template <class Enqueue>
+cudaGraphExec_t rolloutGraph(ddb_handle* h, cudaStream_t s, int kind, int T, int K, const void* const* args, Enqueue enqueue) {
+  if (!rolloutGraphsEnabled() || isCapturing(s)) return nullptr;
+  for (size_t i = 0; i < h->graphs.size(); i++)
+    if (h->graphs[i].same(kind, T, K, args)) {
+      ddb_handle::RolloutGraph g = h->graphs[i];
+      h->graphs.erase(h->graphs.begin() + i);
+      h->graphs.push_back(g);
+      return g.exec;
+    }
+  const bool repeated = h->lastCall.same(kind, T, K, args);
+  h->lastCall.kind = kind; h->lastCall.T = T; h->lastCall.K = K;
+  for (int i = 0; i < 6; i++) h->lastCall.args[i] = args[i];
+  if (!repeated) return nullptr;
+  if (!h->capStream && cudaStreamCreateWithFlags(&h->capStream, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (cudaStreamBeginCapture(h->capStream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const int rc = enqueue(h->capStream);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(h->capStream, &graph);
+  ddb_handle::RolloutGraph g = h->lastCall;
+  if (rc != DDB_OK || e != cudaSuccess || !graph || cudaGraphInstantiate(&g.exec, graph, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    return nullptr;
+  }
+  cudaGraphDestroy(graph);
+  if (h->graphs.size() >= kMaxRolloutGraphs) { cudaGraphExecDestroy(h->graphs.front().exec); h->graphs.erase(h->graphs.begin()); }
+  h->graphs.push_back(g);
+  return g.exec;
+}
+}  // namespace
+
+extern "C" {
+
 __global__ void k_add_inplace(size_t n, double* __restrict__ a, const double* __restrict__ b) {
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) a[i] += b[i];
 }
@@ -691,21 +754,27 @@ int ddb_rollout_forward(ddb_handle* h, void* stream, int32_t T, const double* q0
   rc = ensureLanes(h);
   if (rc) return rc;
   const int K = h->nLanes;
-  rc = forkLanes(h, s, K);
-  if (rc) return rc;
-  for (int t = 0; t < T; t++)
-    for (int c = 0; c < K; c++) {
-      int w0, w1;
-      chunkRange(h->N, K, c, &w0, &w1);
-      if (w0 >= w1) continue;
-      h->k.fwd(h->lanes[c], h->N, w0, w1, t ? q_seq + (t - 1) * V : q0, t ? qd_seq + (t - 1) * V : qd0, tau + t * V, q_seq + t * V, qd_seq + t * V,
-               h->slots[t]);
-      h->launches++;
-    }
-  DDB_CUDA(h, cudaGetLastError());
+  auto enqueue = [&](cudaStream_t origin) -> int {
+    int r = forkLanes(h, origin, K);
+    if (r) return r;
+    for (int t = 0; t < T; t++)
+      for (int c = 0; c < K; c++) {
+        int w0, w1;
+        chunkRange(h->N, K, c, &w0, &w1);
+        if (w0 >= w1) continue;
+        h->k.fwd(h->lanes[c], h->N, w0, w1, t ? q_seq + (t - 1) * V : q0, t ? qd_seq + (t - 1) * V : qd0, tau + t * V, q_seq + t * V, qd_seq + t * V,
+                 h->slots[t]);
+      }
+    DDB_CUDA(h, cudaGetLastError());
+    return joinLanes(h, origin, K);
+  };
+  const void* gargs[6] = {q0, qd0, tau, q_seq, qd_seq, nullptr};
+  if (cudaGraphExec_t exec = rolloutGraph(h, s, 0, T, K, gargs, enqueue)) DDB_CUDA(h, cudaGraphLaunch(exec, s));
+  else if ((rc = enqueue(s)) != DDB_OK) return rc;
+  for (int c = 0; c < K; c++) { int w0, w1; chunkRange(h->N, K, c, &w0, &w1); if (w1 > w0) h->launches += T; }
   for (int t = 0; t < T; t++) h->slotValid[t] = 1;
   h->cur = T - 1;
-  return joinLanes(h, s, K);
+  return DDB_OK;
 }
 
 // Reverse sweep over the retained steps (SingleShot::backpropGradientWrt, SingleShot.cpp:650-700): g_q_seq[t], g_qd_seq[t] are the
@@ -745,20 +814,26 @@ int ddb_rollout_backward(ddb_handle* h, void* stream, int32_t T, const double* g
   rc = ensureLanes(h);
   if (rc) return rc;
   const int K = h->nLanes;
-  rc = forkLanes(h, s, K);
-  if (rc) return rc;
-  for (int t = T - 1; t >= 0; t--)
-    for (int c = 0; c < K; c++) {
-      int w0, w1;
-      chunkRange(h->N, K, c, &w0, &w1);
-      if (w0 >= w1) continue;
-      const int o = t & 1;
-      h->k.bwd(h->lanes[c], h->N, w0, w1, h->slots[t], g_q_seq + t * V, g_qd_seq + t * V, t < T - 1 ? run[1 - o][0] : nullptr,
-               t < T - 1 ? run[1 - o][1] : nullptr, t ? run[o][0] : g_q0, t ? run[o][1] : g_qd0, g_tau + t * V, h->lim);
-      h->launches++;
-    }
-  DDB_CUDA(h, cudaGetLastError());
-  return joinLanes(h, s, K);
+  auto enqueue = [&](cudaStream_t origin) -> int {
+    int r = forkLanes(h, origin, K);
+    if (r) return r;
+    for (int t = T - 1; t >= 0; t--)
+      for (int c = 0; c < K; c++) {
+        int w0, w1;
+        chunkRange(h->N, K, c, &w0, &w1);
+        if (w0 >= w1) continue;
+        const int o = t & 1;
+        h->k.bwd(h->lanes[c], h->N, w0, w1, h->slots[t], g_q_seq + t * V, g_qd_seq + t * V, t < T - 1 ? run[1 - o][0] : nullptr,
+                 t < T - 1 ? run[1 - o][1] : nullptr, t ? run[o][0] : g_q0, t ? run[o][1] : g_qd0, g_tau + t * V, h->lim);
+      }
+    DDB_CUDA(h, cudaGetLastError());
+    return joinLanes(h, origin, K);
+  };
+  const void* gargs[6] = {g_q_seq, g_qd_seq, g_q0, g_qd0, g_tau, nullptr};
+  if (cudaGraphExec_t exec = rolloutGraph(h, s, 1, T, K, gargs, enqueue)) DDB_CUDA(h, cudaGraphLaunch(exec, s));
+  else if ((rc = enqueue(s)) != DDB_OK) return rc;
+  for (int c = 0; c < K; c++) { int w0, w1; chunkRange(h->N, K, c, &w0, &w1); if (w1 > w0) h->launches += T; }
+  return DDB_OK;
 }
 
 // ---- host-buffer entry points (the e2e path): H2D, kernel, D2H on the handle's own stream ----

@@ -243,3 +243,49 @@ def test_step_captured_in_a_cuda_graph_on_a_side_stream():
     for a, b in zip(out, ref):
         assert torch.equal(a, b)
     lib.ddb_destroy(h)
+
+
+def test_repeated_rollout_calls_replay_a_cuda_graph_with_the_same_bits(monkeypatch):
+    """A contact-free rollout called again with the same buffers is recorded into a CUDA graph on its second call and replayed from then
+    on (ddb_api.cu: rolloutGraph). Every call must give the bits of the direct launches (DDB_ROLLOUT_GRAPHS=0), also after the inputs in
+    the buffers have changed, and a call with other buffers must not reuse the graph."""
+    lib = _abi.load_library()
+    desc = skeletons.create_multiarm_robot(5)
+    N, n, T = 3000, 5, 5
+    rng = np.random.default_rng(12)
+    mk = lambda *shape: torch.tensor(rng.uniform(-1, 1, shape), dtype=torch.float64, device="cuda")
+
+    def run(graphs, calls):
+        monkeypatch.setenv("DDB_ROLLOUT_GRAPHS", "1" if graphs else "0")
+        topo, params, keep = desc.to_ctypes()
+        h = _abi._vp()
+        assert lib.ddb_create(C.byref(topo), C.byref(params), N, 0, C.byref(h)) == 0
+        sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        q0, qd0, taus, gp, gv = (torch.empty(*s, dtype=torch.float64, device="cuda") for s in ((N, n), (N, n), (T, N, n), (T, N, n), (T, N, n)))
+        outs = [torch.zeros(T, N, n, dtype=torch.float64, device="cuda") for _ in range(3)] + [torch.zeros(N, n, dtype=torch.float64, device="cuda") for _ in range(2)]
+        res = []
+        for src in calls:
+            for dst, a in zip((q0, qd0, taus, gp, gv), src):
+                dst.copy_(a)
+            assert lib.ddb_rollout_forward(h, sp, T, q0.data_ptr(), qd0.data_ptr(), taus.data_ptr(), outs[0].data_ptr(), outs[1].data_ptr()) == 0, lib.ddb_last_error(h)
+            assert lib.ddb_rollout_backward(h, sp, T, gp.data_ptr(), gv.data_ptr(), outs[3].data_ptr(), outs[4].data_ptr(), outs[2].data_ptr()) == 0, lib.ddb_last_error(h)
+            torch.cuda.synchronize()
+            res.append([o.clone() for o in outs])
+        # other output buffers: must not replay the graph that writes into `outs`
+        other = [torch.zeros_like(o) for o in outs]
+        assert lib.ddb_rollout_forward(h, sp, T, q0.data_ptr(), qd0.data_ptr(), taus.data_ptr(), other[0].data_ptr(), other[1].data_ptr()) == 0
+        assert lib.ddb_rollout_backward(h, sp, T, gp.data_ptr(), gv.data_ptr(), other[3].data_ptr(), other[4].data_ptr(), other[2].data_ptr()) == 0
+        torch.cuda.synchronize()
+        res.append(other)
+        launches = lib.ddb_launch_count(h)
+        lib.ddb_destroy(h)
+        return res, launches
+
+    calls = [(mk(N, n), mk(N, n), mk(T, N, n), mk(T, N, n), mk(T, N, n)) for _ in range(4)]
+    direct, l0 = run(False, calls)
+    graphed, l1 = run(True, calls)
+    assert l0 == l1  # the launch count is the number of kernels that ran, replayed or not
+    for a, b in zip(direct, graphed):
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert not torch.equal(direct[0][0], direct[1][0])  # (the calls really differ)
