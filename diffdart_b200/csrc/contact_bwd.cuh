@@ -37,7 +37,8 @@ struct ContactBwdLayout {
   __host__ __device__ size_t oMA() const { return oAc() + (size_t)kmax * nd; }         // [kmax][nd] M^-1 (A_c + A_ub E) columns
   __host__ __device__ size_t oCV() const { return oMA() + (size_t)kmax * nd; }         // 11 x [kmax]: a b f y1 r1 y2 r2 y3 r3 E yB
   __host__ __device__ size_t oNV() const { return oCV() + (size_t)11 * kmax; }         // 13 x [nd]
-  __host__ __device__ size_t doubles() const { return oNV() + (size_t)13 * nd; }
+  __host__ __device__ size_t oPriv() const { return oNV() + (size_t)13 * nd; }         // 2 x [32][nd]: per-lane V_row and dL/dq contributions of one round of rows
+  __host__ __device__ size_t doubles() const { return oPriv() + (size_t)2 * 32 * nd; }
   __host__ __device__ size_t ints() const { return (size_t)4 * kmax; }                 // clampRow ubRow ubNormal clampIdxOfRow
 };
 
@@ -170,6 +171,8 @@ struct ContactBwdWork {
   DDB_DI double* MA(int j) const { return d + L.oMA() + (size_t)j * L.nd; }
   DDB_DI double* cv(int which) const { return d + L.oCV() + (size_t)which * L.kmax; }
   DDB_DI double* nv(int which) const { return d + L.oNV() + (size_t)which * L.nd; }
+  DDB_DI double* privV(int lane) const { return d + L.oPriv() + (size_t)lane * L.nd; }
+  DDB_DI double* privG(int lane) const { return d + L.oPriv() + (size_t)(32 + lane) * L.nd; }
   DDB_DI int* clampRow() const { return i; }
   DDB_DI int* ubRow() const { return i + L.kmax; }
   DDB_DI int* ubNormal() const { return i + 2 * L.kmax; }
@@ -201,7 +204,11 @@ struct ContactBwdLocals {  // one object: see the note on BwdScratch (stack colo
   SV dA[NB];
 };
 
-// status bits written per world: 1 = contact rows present, 2 = pseudo-inverse branch (rank-deficient Q)
+// status bits written per world: 1 = contact rows present, 2 = pseudo-inverse branch (rank-deficient Q).
+// One world per warp (lcpStride == 1): the tree sweeps run redundantly on the 32 lanes; the loops over independent rows, matrix
+// entries and DOFs (constraint-force columns, Q, the n-vectors, the contact-geometry term of every classified row) are split across
+// the lanes WITHOUT changing any summation order: a lane owns whole entries, and the per-row contributions to dL/dq are added in row
+// order from per-lane buffers, so the result is the one-thread result bit for bit.
 template <int NB>
 DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, const double* keepD, const int* keepI, const ContactBwdWork& bw,
                                 double* lcpD, int* lcpI, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
@@ -209,6 +216,10 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
   const int nb = c_topo.nb, nd = c_topo.nd;
   const double dt = c_topo.dt;
   const ContactTopo& ctp = c_ctopo;
+  int coopLane = 0, coopN = 1;
+#ifndef DDB_HOST_EMULATION
+  if (lcpStride == 1) { coopLane = threadIdx.x & 31; coopN = 32; }
+#endif
   ContactBwdLocals<NB> loc;
   BwdScratch<NB>& ws = loc.ws;
   SV* dA = loc.dA;
@@ -283,7 +294,10 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       }
     }
     // ---- world force and constraint-force column of every classified row (clamping slots 0..c-1, upper-bound slots c..c+u-1) ----
-    for (int slot = 0; slot < c + u; slot++) {
+    coopSyncWarp(coopN);
+    for (int sbase = 0; sbase < c + u; sbase += coopN) {
+      const int slot = sbase + coopLane;
+      if (slot >= c + u) continue;
       const int r = slot < c ? bw.clampRow()[slot] : bw.ubRow()[slot - c];
       const double* ct = contactOf(r);
       const int k = rowInfo[r] & 3, cons = rowInfo[r] >> 2;
@@ -306,51 +320,57 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     // ---- M^-1 A columns, b_c, f_c, a = A^T M^-1 lambda ----
     double *va = bw.cv(CV_A), *vb = bw.cv(CV_B), *vfc = bw.cv(CV_F), *y1 = bw.cv(CV_Y1), *r1 = bw.cv(CV_R1);
     double *y2 = bw.cv(CV_Y2), *r2 = bw.cv(CV_R2), *y3 = bw.cv(CV_Y3), *r3 = bw.cv(CV_R3);
-    for (int j = 0; j < c; j++) {
-      const double* m = massed(bw.clampRow()[j]);
-      double* ma = bw.MA(j);
-      for (int d = 0; d < nd; d++) ma[d] = m[d];
+    coopSyncWarp(coopN);
+    for (int dbase = 0; dbase < nd; dbase += coopN) {  // a lane owns DOF d of every column (the upper-bound rows add in their order)
+      const int d = dbase + coopLane;
+      if (d >= nd) continue;
+      for (int j = 0; j < c; j++) bw.MA(j)[d] = massed(bw.clampRow()[j])[d];
+      for (int k = 0; k < u; k++) bw.MA(bw.ubNormal()[k])[d] += bw.cv(CV_E)[k] * massed(bw.ubRow()[k])[d];
     }
-    for (int k = 0; k < u; k++) {
-      const double* m = massed(bw.ubRow()[k]);
-      double* ma = bw.MA(bw.ubNormal()[k]);
-      const double e = bw.cv(CV_E)[k];
-      for (int d = 0; d < nd; d++) ma[d] += e * m[d];
-    }
-    for (int j = 0; j < c; j++) {
+    coopSyncWarp(coopN);
+    for (int j = 0; j < c; j++) if (restOfRow[bw.clampRow()[j]] != 0.0) bounced = true;
+    for (int jbase = 0; jbase < c; jbase += coopN) {
+      const int j = jbase + coopLane;
+      if (j >= c) continue;
       double sb = 0.0, sa = 0.0;
       const double* col = bw.Ac(j);
       const double* ma = bw.MA(j);
       for (int d = 0; d < nd; d++) { sb += col[d] * vf[d]; sa += ma[d] * lamT[d]; }
       const double Bj = 1.0 + restOfRow[bw.clampRow()[j]];
-      if (Bj != 1.0) bounced = true;
       vb[j] = -(Bj * sb); va[j] = sa; vfc[j] = xall[bw.clampRow()[j]];
     }
     // ---- Q = A_c^T M^-1 A and the pseudo-inverse products ----
     LcpView v;
     v.init(lcpD, lcpI, c, ctp.kmax, lcpStride);
-    for (int i = 0; i < c; i++) {
+    coopSyncWarp(coopN);
+    for (int ebase = 0; ebase < c * c; ebase += coopN) {  // a lane owns whole entries of Q
+      const int e = ebase + coopLane;
+      if (e >= c * c) continue;
+      const int i = e / c, j = e % c;
       const double* col = bw.Ac(i);
-      for (int j = 0; j < c; j++) {
-        const double* ma = bw.MA(j);
-        double s = 0.0;
-        for (int d = 0; d < nd; d++) s += col[d] * ma[d];
-        v.Araw(i, j) = s;
-      }
+      const double* ma = bw.MA(j);
+      double s = 0.0;
+      for (int d = 0; d < nd; d++) s += col[d] * ma[d];
+      v.Araw(i, j) = s;
+      // one decomposition of Q serves P b, P^T a, P y1 and P^T r1 (BackpropSnapshot.cpp:3875-3876,3925-3932)
+      v.db[(size_t)(v.oL + i * c + j) * v.st] = s;
     }
-    // one decomposition of Q serves P b, P^T a, P y1 and P^T r1 (BackpropSnapshot.cpp:3875-3876,3925-3932)
-    for (int i = 0; i < c; i++) for (int j = 0; j < c; j++) v.db[(size_t)(v.oL + i * c + j) * v.st] = v.Araw(i, j);
+    coopSyncWarp(coopN);
     const int rank = codFactorDev(v, c);
     codApplyDev(v, c, rank, true, [&](int i) { return va[i]; }, [&](int i, double x) { y1[i] = x; });
     codApplyDev(v, c, rank, false, [&](int i) { return vb[i]; }, [&](int i, double x) { r1[i] = x; });
     pinv = rank < c;
     if (pinv) {
       status |= 2;
-      for (int i = 0; i < c; i++) {
+      coopSyncWarp(coopN);
+      for (int ibase = 0; ibase < c; ibase += coopN) {
+        const int i = ibase + coopLane;
+        if (i >= c) continue;
         double s1 = 0.0, s2 = 0.0;
         for (int j = 0; j < c; j++) { s1 += v.Araw(i, j) * r1[j]; s2 += v.Araw(j, i) * y1[j]; }
         r2[i] = vb[i] - s1; y3[i] = va[i] - s2;
       }
+      coopSyncWarp(coopN);
       codApplyDev(v, c, rank, false, [&](int i) { return y1[i]; }, [&](int i, double x) { y2[i] = x; });
       codApplyDev(v, c, rank, true, [&](int i) { return r1[i]; }, [&](int i, double x) { r3[i] = x; });
     } else {
@@ -364,22 +384,25 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     double* da = bw.nv(NV_DA);
     double* m8 = bw.nv(NV_M8);   // M^-1 A_c (yB - y1): zero without restitution
     double* yB = bw.cv(CV_YB);
-    for (int d = 0; d < nd; d++) { m1[d] = m2[d] = m3[d] = m4[d] = m5[d] = m6[d] = m7[d] = m8[d] = da[d] = 0.0; }
-    for (int j = 0; j < c; j++) {
-      const double* col = bw.Ac(j);
-      const double* ma = bw.MA(j);
-      const double* mc = massed(bw.clampRow()[j]);
-      const double e = restOfRow[bw.clampRow()[j]];
-      yB[j] = (1.0 + e) * y1[j];
-      for (int d = 0; d < nd; d++) {
-        lamT[d] -= yB[j] * col[d];
-        m8[d] += (e * y1[j]) * mc[d];
-        m1[d] += r1[j] * ma[d]; m2[d] += y1[j] * mc[d]; m3[d] += r2[j] * mc[d]; m4[d] += y2[j] * ma[d];
-        m5[d] += r3[j] * mc[d]; m6[d] += y3[j] * ma[d]; m7[d] += (vfc[j] - r1[j]) * ma[d];
-        da[d] += vfc[j] * ma[d];
+    for (int j = 0; j < c; j++) yB[j] = (1.0 + restOfRow[bw.clampRow()[j]]) * y1[j];  // (every lane: the stores coincide)
+    coopSyncWarp(coopN);
+    for (int dbase = 0; dbase < nd; dbase += coopN) {  // a lane owns DOF d of every n-vector; the rows add in their order
+      const int d = dbase + coopLane;
+      if (d >= nd) continue;
+      double lt = lamT[d], a1 = 0.0, a2 = 0.0, a3 = 0.0, a4 = 0.0, a5 = 0.0, a6 = 0.0, a7 = 0.0, a8 = 0.0, ad = 0.0;
+      for (int j = 0; j < c; j++) {
+        const double col = bw.Ac(j)[d], ma = bw.MA(j)[d], mc = massed(bw.clampRow()[j])[d];
+        const double e = restOfRow[bw.clampRow()[j]];
+        lt -= yB[j] * col;
+        a8 += (e * y1[j]) * mc;
+        a1 += r1[j] * ma; a2 += y1[j] * mc; a3 += r2[j] * mc; a4 += y2[j] * ma;
+        a5 += r3[j] * mc; a6 += y3[j] * ma; a7 += (vfc[j] - r1[j]) * ma;
+        ad += vfc[j] * ma;
       }
+      lamT[d] = lt; m1[d] = a1; m2[d] = a2; m3[d] = a3; m4[d] = a4; m5[d] = a5; m6[d] = a6; m7[d] = a7; m8[d] = a8;
+      da[d] = ad * (1.0 / dt);
     }
-    for (int d = 0; d < nd; d++) da[d] *= 1.0 / dt;
+    coopSyncWarp(coopN);
   }
   // ---- mu~ = M^-1 lambda~, dL/dtau ----
   double* muT = bw.nv(NV_MUT);
@@ -430,33 +453,51 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     const double *y1 = bw.cv(CV_Y1), *r1 = bw.cv(CV_R1), *y2 = bw.cv(CV_Y2), *r2 = bw.cv(CV_R2), *y3 = bw.cv(CV_Y3), *r3 = bw.cv(CV_R3), *vfc = bw.cv(CV_F);
     const double *m1 = bw.nv(NV_M1), *m2 = bw.nv(NV_M2), *m3 = bw.nv(NV_M3), *m4 = bw.nv(NV_M4), *m5 = bw.nv(NV_M5), *m6 = bw.nv(NV_M6), *m8 = bw.nv(NV_M8);
     const double* yB = bw.cv(CV_YB);
-    double* V = bw.nv(NV_V);
     double* acc = bw.nv(NV_VFM1);  // dL/dq contributions of the geometry, accumulated locally
-    for (int d = 0; d < nd; d++) acc[d] = 0.0;
-    for (int slot = 0; slot < c + u; slot++) {
-      const bool isUb = slot >= c;
-      const int r = isUb ? bw.ubRow()[slot - c] : bw.clampRow()[slot];
-      const int j = isUb ? bw.ubNormal()[slot - c] : slot;
-      const double e = isUb ? bw.cv(CV_E)[slot - c] : 1.0;
-      for (int d = 0; d < nd; d++) {
-        const double mu = muT[d] + m2[d] + m8[d];  // M^-1 lambda = mu~ + M^-1 A_c yB
-        double val = vfc[j] * mu - r1[j] * m2[d] + y2[j] * m3[d] + y3[j] * m5[d];
-        if (!isUb) val += -yB[j] * vf[d] - y1[j] * m1[d] + r2[j] * m4[d] + r3[j] * m6[d];
-        V[d] = e * val;
-      }
-      const double* ct = contactOf(r);
-      const int k = rowInfo[r] & 3, cons = rowInfo[r] >> 2;
-      const int bodyA = keepI[KL.oBodyA() + cons], bodyB = keepI[KL.oBodyB() + cons];
-      const SV F = ldSVp(bw.F(slot));
-      const V3 dir = F.v;
-      SV Wtot = svzero();
-      for (int side = 0; side < 2; side++)
-        for (int jb = side == 0 ? bodyA : bodyB; jb >= 0; jb = c_topo.b[jb].parent) {
-          const DevBody& b = c_topo.b[jb];
-          for (int z = 0; z < b.ndof; z++) Wtot = Wtot + ((side == 0 ? 1.0 : -1.0) * V[b.dof + z]) * ldSVp(bw.sF(b.dof + z));
+    for (int d = 0; d < nd; d++) acc[d] = 0.0;  // (every lane: the stores coincide)
+    coopSyncWarp(coopN);
+    // rows in rounds of coopN: lane L works out the contribution of row base + L into its private buffer, then the lanes add the
+    // buffers DOF by DOF in row order (a row touches a DOF at most once: its two bodies belong to different skeletons)
+    for (int sbase = 0; sbase < c + u; sbase += coopN) {
+      const int slot = sbase + coopLane;
+      double* V = bw.privV(coopLane);
+      double* G = bw.privG(coopLane);
+      for (int d = 0; d < nd; d++) G[d] = 0.0;
+      if (slot < c + u) {
+        const bool isUb = slot >= c;
+        const int r = isUb ? bw.ubRow()[slot - c] : bw.clampRow()[slot];
+        const int j = isUb ? bw.ubNormal()[slot - c] : slot;
+        const double e = isUb ? bw.cv(CV_E)[slot - c] : 1.0;
+        for (int d = 0; d < nd; d++) {
+          const double mu = muT[d] + m2[d] + m8[d];  // M^-1 lambda = mu~ + M^-1 A_c yB
+          double val = vfc[j] * mu - r1[j] * m2[d] + y2[j] * m3[d] + y3[j] * m5[d];
+          if (!isUb) val += -yB[j] * vf[d] - y1[j] * m1[d] + r2[j] * m4[d] + r3[j] * m6[d];
+          V[d] = e * val;
         }
-      chainGeometryVjp(bw, ct, k, dir, F, Wtot, V, bodyA, true, 1.0, acc);
-      chainGeometryVjp(bw, ct, k, dir, F, Wtot, V, bodyB, false, -1.0, acc);
+        const double* ct = contactOf(r);
+        const int k = rowInfo[r] & 3, cons = rowInfo[r] >> 2;
+        const int bodyA = keepI[KL.oBodyA() + cons], bodyB = keepI[KL.oBodyB() + cons];
+        const SV F = ldSVp(bw.F(slot));
+        const V3 dir = F.v;
+        SV Wtot = svzero();
+        for (int side = 0; side < 2; side++)
+          for (int jb = side == 0 ? bodyA : bodyB; jb >= 0; jb = c_topo.b[jb].parent) {
+            const DevBody& b = c_topo.b[jb];
+            for (int z = 0; z < b.ndof; z++) Wtot = Wtot + ((side == 0 ? 1.0 : -1.0) * V[b.dof + z]) * ldSVp(bw.sF(b.dof + z));
+          }
+        chainGeometryVjp(bw, ct, k, dir, F, Wtot, V, bodyA, true, 1.0, G);
+        chainGeometryVjp(bw, ct, k, dir, F, Wtot, V, bodyB, false, -1.0, G);
+      }
+      coopSyncWarp(coopN);
+      const int active = (c + u - sbase) < coopN ? (c + u - sbase) : coopN;
+      for (int dbase = 0; dbase < nd; dbase += coopN) {
+        const int d = dbase + coopLane;
+        if (d >= nd) continue;
+        double a = acc[d];
+        for (int L = 0; L < active; L++) a += bw.privG(L)[d];
+        acc[d] = a;
+      }
+      coopSyncWarp(coopN);
     }
     for (int d = 0; d < nd; d++) gq[vidx(layout, N, nd, w, d)] += acc[d];
   }
