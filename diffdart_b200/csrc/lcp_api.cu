@@ -81,7 +81,11 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
                                               int fiLocal, double hi_r, double diag, double f_r, double& acc, double& hi_e, double& lo_e,
                                               double& x_new) {
   // S[r][blk0 + jj] is only used by the lanes below the diagonal (jj < lane), where it sits in this lane's packed row: one base
-  // pointer per block instead of index arithmetic per step (the other lanes read a neighbouring entry of the shared array and drop it)
+  // pointer per block instead of index arithmetic per step. A lane's residual matters until its own step (its x is taken there):
+  // from then on it keeps subtracting whatever follows its row in shared memory (in bounds: the triangle is followed by the vectors)
+  // instead of paying a compare and two selects per step to stand still, and the element of the next step is fetched without
+  // clamping the index at the block's end for the same reason. ncu on a heavy launch: 67 % of the solver's instructions are these
+  // steps, 44 instructions per step before this change (profiles/README.md, round 2).
   const double* __restrict__ rowS = S + (r * (r + 1)) / 2 + blk0;
   const double* __restrict__ scb = sc + blk0;
   auto elem = [&](int jj) { return rowS[jj] * scb[jj] * f_r; };
@@ -89,12 +93,12 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
 #pragma unroll 8
   for (int jj = 0; jj < cnt; jj++) {
     const double a = a_next;
-    a_next = elem(jj + 1 < cnt ? jj + 1 : jj);
+    a_next = elem(jj + 1);
     double nx = FIRST ? acc / diag : acc;
     nx = fmax(lo_e, fmin(nx, hi_e));
     if (lane == jj) x_new = nx;
     const double xj = __shfl_sync(0xffffffffu, nx, jj);
-    if (lane > jj) acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
+    acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
     if (fiLocal == jj) { hi_e = hi_r * xj; lo_e = -hi_e; }  // the friction bound follows the live normal impulse
   }
 }
