@@ -34,26 +34,7 @@ def chain_step():
     return run
 
 
-def skewed_arm(n, seed, prismatic_every=3):
-    """A chain with arbitrary joint axes, joint frames offset and rotated on both sides, off-centre masses and full inertia tensors,
-    revolute and prismatic joints mixed: nothing in it is aligned with the canonical frames the kernels work in."""
-    rng = np.random.default_rng(seed)
-    s = skeletons.Skeleton("skewed")
-    parent = None
-    for i in range(n):
-        prismatic = prismatic_every > 0 and (i % prismatic_every == 1)
-        b = (s.createPrismaticJointAndBodyNodePair if prismatic else s.createRevoluteJointAndBodyNodePair)(parent)
-        axis = rng.normal(size=3)
-        b.setAxis(list(axis / np.linalg.norm(axis)))
-        Rp, Rc = orc.exp_map_rot(rng.normal(size=3) * 0.7), orc.exp_map_rot(rng.normal(size=3) * 0.7)
-        b.setTransformFromParentBodyNode(p=list(rng.uniform(-0.5, 0.5, 3)), R=Rp)
-        b.setTransformFromChildBodyNode(p=list(rng.uniform(-0.3, 0.3, 3)), R=Rc)
-        b.setMass(float(rng.uniform(0.5, 2.0))).setLocalCOM(list(rng.uniform(-0.2, 0.2, 3)))
-        A = rng.normal(size=(3, 3))
-        J = A @ A.T + 0.5 * np.eye(3)
-        b.setMomentOfInertia(J[0, 0], J[1, 1], J[2, 2], J[0, 1], J[0, 2], J[1, 2])
-        parent = b
-    return skeletons.WorldDescription().addSkeleton(s).setGravity([0.3, -9.81, 1.1])
+from util import skewed_arm  # noqa: E402
 
 
 CASES = {

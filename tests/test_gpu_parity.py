@@ -109,6 +109,27 @@ def test_chain_lengths(links):
     check_against_oracle(desc, *random_inputs(links, 40, links), seed=links)
 
 
+@pytest.mark.parametrize("links,prismatic_every", [(2, 3), (3, 3), (4, 0), (5, 3), (5, 0), (6, 2), (7, 3), (8, 0), (8, 3)])
+def test_skewed_chains(links, prismatic_every):
+    """The chain kernels work in canonical joint frames (joint axis = local z, chain.cuh) and come in two instantiations per length:
+    revolute joints only (prismatic_every = 0) and revolute / prismatic mixed. Chains with arbitrary axes, joint frames offset and rotated
+    on both sides, off-centre masses and full inertia tensors: nothing in them is aligned with the frames the kernels use."""
+    from util import skewed_arm
+
+    desc = skewed_arm(links, 100 + links, prismatic_every)
+    q, qd, tau = random_inputs(links, 40, links)
+    check_against_oracle(desc, q, 0.5 * qd, tau, seed=links)
+
+
+def test_largest_tree():
+    """DDB_MAX_BODIES bodies / DOFs: the capacity of the topology descriptor."""
+    desc = skeletons.create_random_tree(48, 99)
+    n = desc.getNumDofs()
+    assert n == 48
+    q, qd, tau = random_inputs(n, 8, 99)
+    check_against_oracle(desc, q, 0.3 * qd, tau, seed=99)
+
+
 @pytest.mark.parametrize("seed,nb", [(11, 3), (12, 6), (13, 10), (14, 20), (15, 40)])
 def test_random_trees(seed, nb):
     """Branching trees with revolute + prismatic joints, skewed axes/offsets/COMs, 3-D gravity."""
@@ -204,19 +225,18 @@ def test_error_paths():
     assert lib.ddb_snapshot_select(h, 3) == 1
     assert lib.ddb_forward(h, None, None, g.data_ptr(), g.data_ptr(), g.data_ptr(), g.data_ptr(), None, None, None, None) == 1
     lib.ddb_destroy(h)
-    # restitution > 0 (the bounce approximation, BackpropSnapshot.cpp:1141-1234) is not restated: the backward through such
-    # a world is refused with a message, never approximated
-    bouncy = skeletons.create_box_stack(2)
-    for sk in bouncy.skeletons:
-        for b in sk.bodies:
-            b.setRestitutionCoeff(0.5)
-    topo, params, keep = bouncy.to_ctypes()
+    # a handle that steps with the constraint solver's gradients disabled (plain World::step, ddb_params.reserved[1] = 1) keeps no
+    # classification of its contact rows: the backward through such a step is refused with a message, never approximated
+    stack = skeletons.create_box_stack(2)
+    topo, params, keep = stack.to_ctypes()
+    params.reserved[1] = 1
     h = _abi._vp()
     assert lib.ddb_create(C.byref(topo), C.byref(params), 8, 0, C.byref(h)) == 0
     g6 = torch.zeros(8, 12, dtype=torch.float64, device="cuda")
     assert lib.ddb_forward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.clone().data_ptr(), g6.clone().data_ptr(), None, None, None, None) == 0
     assert lib.ddb_backward(h, None, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr()) == 4
-    assert b"restitution" in lib.ddb_last_error(h)
+    assert b"gradients disabled" in lib.ddb_last_error(h)
+    assert lib.ddb_jacobians(h, None, g6.data_ptr(), None, None, None, None) == 4
     # rollouts: the reverse sweep needs the forward sweep
     assert lib.ddb_rollout_backward(h, None, 2, g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr(), g6.data_ptr()) == 4
     lib.ddb_destroy(h)
