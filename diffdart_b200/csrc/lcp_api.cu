@@ -94,8 +94,11 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
   for (int jj = 0; jj < cnt; jj++) {
     const double a = a_next;
     a_next = elem(jj + 1);
-    double nx = FIRST ? acc / diag : acc;
-    nx = fmax(lo_e, fmin(nx, hi_e));
+    const double cand = FIRST ? acc / diag : acc;
+    // projection onto [lo_e, hi_e] (lo_e <= hi_e) with two independent comparisons of the candidate, as the reference writes it
+    // (PgsBoxedLcpSolver.cpp:139-150), instead of fmin / fmax, whose NaN handling costs 6-7 instructions each on the critical path
+    double nx = cand < lo_e ? lo_e : cand;
+    nx = cand > hi_e ? hi_e : nx;  // (the upper bound is tested first there)
     if (lane == jj) x_new = nx;
     const double xj = __shfl_sync(0xffffffffu, nx, jj);
     acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
@@ -159,7 +162,9 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
       const bool active = !(diag < opt.epsilonForDivision);
       const double old_x = xs[r], hi_r = his[r];
       const int fi = fis[r];
-      const double f_r = iter == 0 ? 1.0 : 1.0 / diag;  // row normalisation (PgsBoxedLcpSolver.cpp:171-178)
+      // row normalisation (PgsBoxedLcpSolver.cpp:171-178); rows that are not iterated get 0 so that their residual stays finite
+      // (the projection below selects with comparisons: a NaN would pass through it)
+      const double f_r = !active ? 0.0 : (iter == 0 ? 1.0 : 1.0 / diag);
       // phase 1
       double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
       int j = 0;
