@@ -102,7 +102,10 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
     if (lane == jj) x_new = nx;
     const double xj = __shfl_sync(0xffffffffu, nx, jj);
     acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
-    if (fiLocal == jj) { hi_e = hi_r * xj; lo_e = -hi_e; }  // the friction bound follows the live normal impulse
+    if (fiLocal == jj) {  // the friction bound follows the live normal impulse; -hi_e by flipping the sign bit (an integer op off the FP64 pipe)
+      hi_e = hi_r * xj;
+      lo_e = __longlong_as_double(__double_as_longlong(hi_e) ^ (long long)0x8000000000000000ULL);
+    }
   }
 }
 
@@ -172,7 +175,14 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
         a0 = __fma_rn(S[tr + j], ys[j], a0); a1 = __fma_rn(S[tr + j + 1], ys[j + 1], a1); a2 = __fma_rn(S[tr + j + 2], ys[j + 2], a2); a3 = __fma_rn(S[tr + j + 3], ys[j + 3], a3);
       }
       for (; j < blk0; j++) a0 += S[tr + j] * ys[j];
-      for (j = blk0; j < blkEnd; j++) if (j > r) a1 += S[(j * (j + 1)) / 2 + r] * ys[j];
+      // the rows of this block behind row r (old values): four partial sums as in the loops around it; rows at or before r are
+      // masked out through their x (the matrix element read instead is some other finite entry of the triangle)
+      for (j = blk0; j + 3 < blkEnd; j += 4) {
+        const double y0 = j > r ? ys[j] : 0.0, y1 = j + 1 > r ? ys[j + 1] : 0.0, y2 = j + 2 > r ? ys[j + 2] : 0.0, y3 = j + 3 > r ? ys[j + 3] : 0.0;
+        a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], y0, a0); a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], y1, a1);
+        a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], y2, a2); a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], y3, a3);
+      }
+      for (; j < blkEnd; j++) a1 = __fma_rn(S[(j * (j + 1)) / 2 + r], j > r ? ys[j] : 0.0, a1);
       for (j = blkEnd; j + 3 < n; j += 4) {
         a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], ys[j], a0); a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], ys[j + 1], a1);
         a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], ys[j + 2], a2); a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], ys[j + 3], a3);
