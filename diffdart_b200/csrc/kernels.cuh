@@ -19,6 +19,19 @@
 #endif
 #endif
 
+// register cap of the chain forward / backward kernels: __launch_bounds__(BLOCK, MINB) by default; DDB_MAXNREG_FWD / _BWD = N caps them
+// with __maxnreg__(N) instead (ptxas only offers 255 / 168 / 128 ... through the min-blocks argument; A/B timing of 9 and 10 warps per SM)
+#ifdef DDB_MAXNREG_FWD
+#define DDB_FWD_BOUNDS __maxnreg__(DDB_MAXNREG_FWD)
+#else
+#define DDB_FWD_BOUNDS __launch_bounds__(BLOCK, MINB)
+#endif
+#ifdef DDB_MAXNREG_BWD
+#define DDB_BWD_BOUNDS __maxnreg__(DDB_MAXNREG_BWD)
+#else
+#define DDB_BWD_BOUNDS __launch_bounds__(BLOCK, MINB)
+#endif
+
 namespace ddb {
 
 struct Limits {  // device arrays of length n (valid only when c_topo.has_limits)
@@ -58,7 +71,7 @@ DDB_DI double* ioShared() { extern __shared__ double2 ddb_io_shared[]; return re
 #endif
 
 template <int NB, int CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
-__global__ void __launch_bounds__(BLOCK, MINB)
+__global__ void DDB_FWD_BOUNDS
 k_forward(int N, int w0, int w1, const double* __restrict__ q, const double* __restrict__ qd, const double* __restrict__ tau,
           double* __restrict__ qn, double* __restrict__ qdn, double* __restrict__ snap) {
   // worlds [w0, w1) of the N-world batch (the host splits a batch into chunks that run on different streams)
@@ -169,7 +182,7 @@ DDB_DI double clipGrad(double g, double x, double lo, double hi) {
 }
 
 template <int NB, int CHAIN, int BLOCK, int MINB, bool HOSTIO = false>
-__global__ void __launch_bounds__(BLOCK, MINB)
+__global__ void DDB_BWD_BOUNDS
 k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __restrict__ gqn, const double* __restrict__ gqdn,
            const double* __restrict__ gqnAdd, const double* __restrict__ gqdnAdd,
            double* __restrict__ gq, double* __restrict__ gqd, double* __restrict__ gtau, Limits lim) {
