@@ -158,6 +158,6 @@ EXPORTED_SYMBOLS = [
     "ddb_num_dofs", "ddb_forward", "ddb_backward", "ddb_jacobians", "ddb_inv_mass_matrix", "ddb_snapshot_select",
     "ddb_snapshot_current", "ddb_snapshot_reserve", "ddb_forward_host", "ddb_backward_host", "ddb_jacobians_host",
     "ddb_launch_count", "ddb_measure_fp64_peak", "ddb_lcp_solve", "ddb_lcp_valid", "ddb_collide_pairs", "ddb_contact_capacity", "ddb_contact_debug_host",
-    "ddb_contact_pgs_sweeps_host", "ddb_contact_profile_host", "ddb_rollout_forward", "ddb_rollout_backward", "ddb_set_lanes", "ddb_lemke_solve",
+    "ddb_contact_pgs_sweeps_host", "ddb_contact_pgs_rows_host", "ddb_contact_profile_host", "ddb_rollout_forward", "ddb_rollout_backward", "ddb_set_lanes", "ddb_lemke_solve",
     "ddb_lcp_cache_get", "ddb_lcp_cache_set",
 ]

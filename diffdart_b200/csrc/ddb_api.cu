@@ -602,6 +602,14 @@ int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out) {
   return DDB_OK;
 }
 
+int ddb_contact_pgs_rows_host(ddb_handle* h, int32_t* rows_out) {
+  if (!h || !h->hasContacts || !rows_out) return fail(h, DDB_ERR_STATE, "no contact stage on this handle");
+  DDB_CUDA(h, cudaSetDevice(h->device));
+  DDB_CUDA(h, cudaDeviceSynchronize());
+  DDB_CUDA(h, cudaMemcpy2D(rows_out, sizeof(int), h->pgsCtrl + 5, 8 * sizeof(int), sizeof(int), h->N, cudaMemcpyDeviceToHost));
+  return DDB_OK;
+}
+
 int ddb_backward(ddb_handle* h, void* stream, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau) {
   if (!h || !gqn || !gqdn || !gq || !gqd || !gtau) return fail(h, DDB_ERR_INVALID, "ddb_backward: null pointer");
   if (!h->slotValid[h->cur]) return fail(h, DDB_ERR_STATE, "ddb_backward: no forward pass retained in the current snapshot slot");

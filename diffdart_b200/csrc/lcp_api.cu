@@ -77,15 +77,18 @@ constexpr int kPgsRequests = 4;  // PGS solves a world can hand over per step (2
 // matrix element of the next step is fetched (and scaled) ahead of the shuffle. Rows that are not iterated (zero
 // diagonal) carry lo = hi = their value, so the projection returns it unchanged.
 template <bool FIRST>
-__device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, const double* __restrict__ sc, int blk0, int r, int cnt, int lane,
-                                              int fiLocal, double hi_r, double diag, double f_r, double& acc, double& hi_e, double& lo_e,
-                                              double& x_new) {
+__device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, const double* __restrict__ sc, double* __restrict__ xsb, int blk0, int r,
+                                              int cnt, int lane, int fiLocal, double bh, double bl, double xn, double diag, double f_r, double acc) {
   // S[r][blk0 + jj] is only used by the lanes below the diagonal (jj < lane), where it sits in this lane's packed row: one base
   // pointer per block instead of index arithmetic per step. A lane's residual matters until its own step (its x is taken there):
   // from then on it keeps subtracting whatever follows its row in shared memory (in bounds: the triangle is followed by the vectors)
   // instead of paying a compare and two selects per step to stand still, and the element of the next step is fetched without
   // clamping the index at the block's end for the same reason. ncu on a heavy launch: 67 % of the solver's instructions are these
   // steps, 44 instructions per step before this change (profiles/README.md, round 2).
+  // The bounds of a row are (bl, bh) * xn: xn is the live normal impulse of a friction row (bh = mu, bl = -mu; taken from the
+  // broadcast in the step of its normal row when that row is in this block) and 1 for every other row (bl = lo, bh = hi), so a
+  // step pays one compare and select for xn and two independent multiplies instead of selects on both bounds behind a multiply and
+  // a negation. The owner of step jj writes its x straight to shared memory (one predicated store instead of two selects per step).
   const double* __restrict__ rowS = S + (r * (r + 1)) / 2 + blk0;
   const double* __restrict__ scb = sc + blk0;
   auto elem = [&](int jj) { return rowS[jj] * scb[jj] * f_r; };
@@ -95,17 +98,15 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
     const double a = a_next;
     a_next = elem(jj + 1);
     const double cand = FIRST ? acc / diag : acc;
+    const double hi_e = bh * xn, lo_e = bl * xn;
     // projection onto [lo_e, hi_e] (lo_e <= hi_e) with two independent comparisons of the candidate, as the reference writes it
     // (PgsBoxedLcpSolver.cpp:139-150), instead of fmin / fmax, whose NaN handling costs 6-7 instructions each on the critical path
     double nx = cand < lo_e ? lo_e : cand;
     nx = cand > hi_e ? hi_e : nx;  // (the upper bound is tested first there)
-    if (lane == jj) x_new = nx;
+    if (lane == jj) xsb[jj] = nx;
     const double xj = __shfl_sync(0xffffffffu, nx, jj);
     acc = __fma_rn(-a, xj, acc);  // (this translation unit is built with -fmad=false for the Dantzig solver)
-    if (fiLocal == jj) {  // the friction bound follows the live normal impulse; -hi_e by flipping the sign bit (an integer op off the FP64 pipe)
-      hi_e = hi_r * xj;
-      lo_e = __longlong_as_double(__double_as_longlong(hi_e) ^ (long long)0x8000000000000000ULL);
-    }
+    xn = fiLocal == jj ? xj : xn;
   }
 }
 
@@ -122,9 +123,8 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
 // footprint and doubles the worlds resident on an SM. Triangular offsets of 16 consecutive rows are distinct modulo
 // 16, so the lane-owns-row reads are free of bank conflicts in both halves of the triangle.
 // ---------------------------------------------------------------------------------------------------------------
-template <int CAP>
 __global__ void __launch_bounds__(32)
-k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
+k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
            double* __restrict__ ans_x, int* __restrict__ ans_ok, PgsOptions opt) {
   const int w = blockIdx.x, lane = threadIdx.x;
   const int n = ctrl[8 * w + 2];
@@ -189,15 +189,17 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
       }
       for (; j < n; j++) a0 += S[(j * (j + 1)) / 2 + r] * ys[j];
       double acc = (bs[r] - ((a0 + a1) + (a2 + a3))) * f_r;
-      // phase 2
-      double x_new = old_x;
-      double hi_e = hi_r, lo_e = los[r];
-      if (fi >= 0) { hi_e = hi_r * xs[fi]; lo_e = -hi_e; }  // a normal row of an earlier block is final; one of this block is replaced in its step
-      if (!active) { hi_e = lo_e = iter == 0 ? 0.0 : old_x; }
-      if (iter == 0) pgsBlockSteps<true>(S, sc, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, hi_r, active ? diag : 1.0, f_r, acc, hi_e, lo_e, x_new);
-      else pgsBlockSteps<false>(S, sc, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, hi_r, diag, f_r, acc, hi_e, lo_e, x_new);
+      // phase 2: bounds (bl, bh) * xn (pgsBlockSteps)
+      double bh = hi_r, bl = los[r], xn = 1.0;
+      if (fi >= 0) { bl = -hi_r; xn = xs[fi]; }  // a normal row of an earlier block is final; one of this block is replaced in its step
+      if (!active) { bh = bl = iter == 0 ? 0.0 : old_x; xn = 1.0; }
+      __syncwarp();  // (every lane has read what it needs of xs before the owners of this block's rows overwrite them)
+      if (iter == 0) pgsBlockSteps<true>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, active ? diag : 1.0, f_r, acc);
+      else pgsBlockSteps<false>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, diag, f_r, acc);
+      __syncwarp();
       if (valid) {
-        xs[r] = x_new; ys[r] = sc[r] * x_new;
+        const double x_new = xs[r];
+        ys[r] = sc[r] * x_new;
         if (active) {
           if (iter == 0) { if (fabs(x_new - old_x) > opt.deltaXThreshold) mine = false; }
           else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs((x_new - old_x) / x_new) > opt.relativeDeltaXTolerance) mine = false; }
@@ -216,6 +218,7 @@ k_pgs_warp(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict
     ctrl[8 * w + 1] = slot + 1;
     ctrl[8 * w + 2] = 0;
     ctrl[8 * w + 3] += sweeps;  // statistics: Gauss-Seidel sweeps spent on this world in this step
+    if (n > ctrl[8 * w + 5]) ctrl[8 * w + 5] = n;  // ... and the largest reduced problem it handed to the solver
   }
 }
 
@@ -346,26 +349,34 @@ static long long* contactProfileBuffer() {  // one buffer per device (the curren
   }
   return buf[dev];
 }
-template <int CAP>
-static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
+// Shared memory of one world of at most cap rows: packed triangle, six vectors, the friction indices
+static size_t pgsWarpBytes(int cap) { return (size_t)((cap * (cap + 1)) / 2 + 6 * cap) * sizeof(double) + cap * sizeof(int); }
+// The size classes (nLow, cap] of the warp solver. A world's shared memory is sized by its class, and the resident worlds per SM
+// (all the latency hiding this solver has: Gauss-Seidel is one dependent chain per world) by that: box stacking hands over problems of
+// 60 ... 108 rows in steps of 6 (two contacts), and a class that ends just above a frequent size holds 6 or 7 worlds per SM where
+// a coarser one held 5 (measured).
+static const int kPgsCaps[] = {24, 36, 48, 60, 66, 72, 78, 84, 90, 96, 102, 108, 116, 128, 144, 160, 192};
+constexpr int kPgsClasses = sizeof(kPgsCaps) / sizeof(kPgsCaps[0]);
+constexpr int kPgsWarpMax = 192;
+static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int cap, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
                                  const PgsOptions& pgs) {
-  const size_t bytes = (size_t)((CAP * (CAP + 1)) / 2 + 6 * CAP) * sizeof(double) + CAP * sizeof(int);
-  static bool configured[64] = {false};  // per instantiation and device: the attribute belongs to the function in that context
+  static bool configured[64] = {false};  // per device: the attribute belongs to the function in that context
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!configured[dev & 63]) {
-    e = cudaFuncSetAttribute(k_pgs_warp<CAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    e = cudaFuncSetAttribute(k_pgs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pgsWarpBytes(kPgsWarpMax));
     if (e != cudaSuccess) return e;
     configured[dev & 63] = true;
   }
-  k_pgs_warp<CAP><<<N, 32, bytes, s>>>(N, kmax, nLow, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+  k_pgs_warp<<<N, 32, pgsWarpBytes(cap), s>>>(N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
   return cudaGetLastError();
 }
 // helper streams of the concurrent PGS size classes, one set per device
+constexpr int kPgsStreams = 8;
 struct PgsStreams {
-  cudaStream_t st[5];
-  cudaEvent_t fork, join[5];
+  cudaStream_t st[kPgsStreams];
+  cudaEvent_t fork, join[kPgsStreams];
 };
 static PgsStreams* pgsStreams() {
   static PgsStreams sets[64];
@@ -374,7 +385,7 @@ static PgsStreams* pgsStreams() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   if (!ready[dev]) {
     PgsStreams& p = sets[dev];
-    for (int i = 0; i < 5; i++) {
+    for (int i = 0; i < kPgsStreams; i++) {
       if (cudaStreamCreateWithFlags(&p.st[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
       if (cudaEventCreateWithFlags(&p.join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
     }
@@ -384,7 +395,7 @@ static PgsStreams* pgsStreams() {
   return &sets[dev];
 }
 void contactPgsSizes(int N, int kmax, size_t* ctrl_ints, size_t* ans_doubles, size_t* ans_ints) {
-  *ctrl_ints = (size_t)N * 8;  // done, answered, pending rows, sweeps (statistics), resume tier, 3 spare
+  *ctrl_ints = (size_t)N * 8;  // done, answered, pending rows, sweeps (statistics), resume tier, largest problem (statistics), 2 spare
   *ans_doubles = (size_t)N * kPgsRequests * kmax;
   *ans_ints = (size_t)N * kPgsRequests;
 }
@@ -402,25 +413,37 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (pass == kPgsRequests) break;
-    // size classes by shared-memory footprint: 10, 7, 5, 3 and 1 resident worlds per SM. The classes touch disjoint worlds,
-    // so they run side by side on helper streams (fork / join on events): the small problems fill the SMs while the few
-    // worlds that need all 10000 sweeps finish.
+    // The size classes touch disjoint worlds, so they run side by side on helper streams (fork / join on events): the small
+    // problems fill the SMs while the few worlds that need all 10000 sweeps finish.
     PgsStreams* ps = pgsStreams();
     if (!ps) return cudaErrorUnknown;
     if ((e = cudaEventRecord(ps->fork, s)) != cudaSuccess) return e;
-    auto onHelper = [&](int i, auto launch) -> cudaError_t {
-      cudaError_t r = cudaStreamWaitEvent(ps->st[i], ps->fork, 0);
-      if (r != cudaSuccess) return r;
-      if ((r = launch(ps->st[i])) != cudaSuccess) return r;
-      if ((r = cudaEventRecord(ps->join[i], ps->st[i])) != cudaSuccess) return r;
-      return cudaStreamWaitEvent(s, ps->join[i], 0);
+    bool used[kPgsStreams] = {false};
+    int nLaunched = 0;
+    auto onHelper = [&](auto launch) -> cudaError_t {
+      const int i = nLaunched++ % kPgsStreams;
+      cudaError_t r = cudaSuccess;
+      if (!used[i]) { used[i] = true; if ((r = cudaStreamWaitEvent(ps->st[i], ps->fork, 0)) != cudaSuccess) return r; }
+      return launch(ps->st[i]);
     };
-    if ((e = onHelper(0, [&](cudaStream_t hs) { return launchPgsWarp<64>(hs, N, kmax, 0, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (kmax > 64 && (e = onHelper(1, [&](cudaStream_t hs) { return launchPgsWarp<76>(hs, N, kmax, 64, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (kmax > 76 && (e = onHelper(2, [&](cudaStream_t hs) { return launchPgsWarp<92>(hs, N, kmax, 76, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (kmax > 92 && (e = onHelper(3, [&](cudaStream_t hs) { return launchPgsWarp<116>(hs, N, kmax, 92, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (kmax > 116 && (e = onHelper(4, [&](cudaStream_t hs) { return launchPgsWarp<192>(hs, N, kmax, 116, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
-    if (launches) (*launches) += 1 + (kmax > 64) + (kmax > 76) + (kmax > 92) + (kmax > 116) + (kmax > 192);
+    // (the largest problems first: they are the last to finish)
+    if (kmax > kPgsWarpMax) {
+      if ((e = onHelper([&](cudaStream_t hs) {
+             k_pgs_thread<<<(N + 63) / 64, 64, 0, hs>>>(N, kmax, kPgsWarpMax, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+             return cudaGetLastError();
+           })) != cudaSuccess) return e;
+    }
+    for (int c = kPgsClasses - 1; c >= 0; c--) {
+      const int nLow = c ? kPgsCaps[c - 1] : 0;
+      if (nLow >= kmax) continue;
+      if ((e = onHelper([&](cudaStream_t hs) { return launchPgsWarp(hs, N, kmax, nLow, kPgsCaps[c], ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    }
+    for (int i = 0; i < kPgsStreams; i++) {
+      if (!used[i]) continue;
+      if ((e = cudaEventRecord(ps->join[i], ps->st[i])) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(s, ps->join[i], 0)) != cudaSuccess) return e;
+    }
+    if (launches) (*launches) += nLaunched;
   }
   return cudaSuccess;
 }

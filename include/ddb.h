@@ -195,6 +195,8 @@ int ddb_contact_profile_host(int64_t* ticks_out);
 
 /* Statistics of the last ddb_forward: Gauss-Seidel sweeps the PGS fallback spent per world (host array [N]). */
 int ddb_contact_pgs_sweeps_host(ddb_handle* h, int32_t* sweeps_out);
+/* ... and the size (rows of the reduced problem) of the largest problem each world handed to it; 0 = none (host array [N]). */
+int ddb_contact_pgs_rows_host(ddb_handle* h, int32_t* rows_out);
 
 /* Replaces BackpropSnapshot::getInvMassMatrix / getMassMatrix helpers
    (python/_diffdart/neural/BackpropSnapshot.cpp:42-146): [N][n][n] col-major. */

@@ -47,6 +47,9 @@ world._lib.ddb_contact_pgs_sweeps_host(world._h, sw.ctypes.data_as(C.c_void_p))
 rows = counts[:, 1]
 stats = {"sweeps_mean": float(sw.mean()), "sweeps_p50": float(np.percentile(sw, 50)), "sweeps_p90": float(np.percentile(sw, 90)), "sweeps_max": int(sw.max()),
          "frac_10000": float((sw >= 10000).mean()), "rows_hist": {str(b): int(((rows > lo) & (rows <= b)).sum()) for lo, b in ((0, 64), (64, 92), (92, 116), (116, 160), (160, 999))}}
+pr = np.zeros(N, dtype=np.int32)
+world._lib.ddb_contact_pgs_rows_host(world._h, pr.ctypes.data_as(C.c_void_p))
+stats["pgs_rows_exact"] = {int(k): int(v) for k, v in zip(*np.unique(pr, return_counts=True))}
 tiers = {int(k): int(v) for k, v in zip(*np.unique(counts[:, 3], return_counts=True))}
 print(json.dumps({"workload": "box_stack forward, backward", "N": N, "ms_per_step": ms, "ms_backward": ms_bwd, "world_steps_per_s": N / ((ms + ms_bwd) * 1e-3),
                   "contacts_mean": float(counts[:, 0].mean()), "rows_mean": float(counts[:, 1].mean()), "tier_mask_hist": tiers, "pgs": stats}))
