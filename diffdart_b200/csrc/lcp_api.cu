@@ -123,10 +123,18 @@ __device__ __forceinline__ void pgsBlockSteps(const double* __restrict__ S, cons
 // footprint and doubles the worlds resident on an SM. Triangular offsets of 16 consecutive rows are distinct modulo
 // 16, so the lane-owns-row reads are free of bank conflicts in both halves of the triangle.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+// Problems of more than one row block run as a PAIR of warps: while warp 0 walks the 32 dependent steps of block b, warp 1 sums
+// phase 1 of block b + 1 over every column except those of block b (whose new values do not exist yet) and leaves the partial sum
+// in shared memory; warp 0 then only adds the 32 columns of block b before it starts on block b + 1. A world is one dependent
+// chain, and the SM holds as many worlds as their matrices fit: the helper shortens the chain (phase 1 was 40 % of a sweep's
+// latency at 84 rows) with issue slots that were idle. One CTA barrier per block; the helper runs one block ahead, across the end
+// of a sweep as well (its sum is dropped when the sweep turns out to be the last).
+template <bool PAIR>
+__global__ void __launch_bounds__(PAIR ? 64 : 32)
 k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i,
            double* __restrict__ ans_x, int* __restrict__ ans_ok, PgsOptions opt) {
-  const int w = blockIdx.x, lane = threadIdx.x;
+  const int w = blockIdx.x, lane = threadIdx.x & 31, warp = PAIR ? threadIdx.x >> 5 : 0;
+  const int nthreads = PAIR ? 64 : 32;
   const int n = ctrl[8 * w + 2];
   if (ctrl[8 * w] || n <= nLow || n > CAP) return;
   extern __shared__ double sm[];
@@ -138,25 +146,76 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
   double* ys = xs + CAP;    // scale * x
   double* sc = ys + CAP;    // column scale of the reduced problem
   int* fis = reinterpret_cast<int*>(sc + CAP);
+  double* part = sc + CAP + (CAP + 1) / 2;             // PAIR: [2][32] partial sums of the helper
+  int* stop = reinterpret_cast<int*>(part + 64);      // PAIR: the sweep just finished was the last
+  auto ctaSync = [&]() { if (PAIR) __syncthreads(); else __syncwarp(); };
   LcpView v;
   v.init(lcp_d + (size_t)w * lcpScratchDoubles(kmax), lcp_i + (size_t)w * lcpScratchInts(kmax), n, kmax, 1);
-  for (int i = lane; i < n; i += 32) {
+  for (int i = threadIdx.x; i < n; i += nthreads) {
     bs[i] = v.b(i); los[i] = v.lo(i); his[i] = v.hi(i); xs[i] = v.x(i); fis[i] = v.findex(i);
     sc[i] = v.tmp(i);  // buildReduced leaves the column scales here (powers of two)
   }
-  __syncwarp();
-  for (int r = 0; r < n; r++)
+  ctaSync();
+  for (int r = warp; r < n; r += PAIR ? 2 : 1)
     for (int j = lane; j <= r; j += 32) S[(r * (r + 1)) / 2 + j] = v.Araw(r, j) / sc[j];
-  for (int i = lane; i < n; i += 32) ys[i] = sc[i] * xs[i];
-  __syncwarp();
+  for (int i = threadIdx.x; i < n; i += nthreads) ys[i] = sc[i] * xs[i];
+  ctaSync();
   const int nblk = (n + 31) >> 5;
+  // the three column ranges of phase 1 for row r (tr = its offset in the triangle), four partial sums
+  struct Sum4 { double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0; __device__ double total() const { return (a0 + a1) + (a2 + a3); } };
+  auto rowPart = [&](Sum4& a, int tr, int j0, int j1) {  // columns before the block: this row of the triangle
+    int j = j0;
+    for (; j + 3 < j1; j += 4) {
+      a.a0 = __fma_rn(S[tr + j], ys[j], a.a0); a.a1 = __fma_rn(S[tr + j + 1], ys[j + 1], a.a1);
+      a.a2 = __fma_rn(S[tr + j + 2], ys[j + 2], a.a2); a.a3 = __fma_rn(S[tr + j + 3], ys[j + 3], a.a3);
+    }
+    for (; j < j1; j++) a.a0 += S[tr + j] * ys[j];
+  };
+  // the rows of this block behind row r (old values): rows at or before r are masked out through their x (the matrix element
+  // read instead is some other finite entry of the triangle)
+  auto inBlock = [&](Sum4& a, int r, int blk0, int blkEnd) {
+    int j = blk0;
+    for (; j + 3 < blkEnd; j += 4) {
+      const double y0 = j > r ? ys[j] : 0.0, y1 = j + 1 > r ? ys[j + 1] : 0.0, y2 = j + 2 > r ? ys[j + 2] : 0.0, y3 = j + 3 > r ? ys[j + 3] : 0.0;
+      a.a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], y0, a.a0); a.a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], y1, a.a1);
+      a.a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], y2, a.a2); a.a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], y3, a.a3);
+    }
+    for (; j < blkEnd; j++) a.a1 = __fma_rn(S[(j * (j + 1)) / 2 + r], j > r ? ys[j] : 0.0, a.a1);
+  };
+  auto colPart = [&](Sum4& a, int r, int j0, int j1) {  // columns behind the block: column r of the triangle
+    int j = j0;
+    for (; j + 3 < j1; j += 4) {
+      a.a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], ys[j], a.a0); a.a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], ys[j + 1], a.a1);
+      a.a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], ys[j + 2], a.a2); a.a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], ys[j + 3], a.a3);
+    }
+    for (; j < j1; j++) a.a0 += S[(j * (j + 1)) / 2 + r] * ys[j];
+  };
+  auto rowOf = [&](int blk) { const int blk0 = blk << 5, blkEnd = min(blk0 + 32, n); return blk0 + lane < n ? blk0 + lane : blkEnd - 1; };
+  // helper (PAIR): phase 1 of block blk without the columns of the block before it (in sweep order: the last block for block 0)
+  auto helperSum = [&](int blk, double* out) {
+    const int blk0 = blk << 5, blkEnd = min(blk0 + 32, n), r = rowOf(blk), tr = (r * (r + 1)) / 2;
+    Sum4 a;
+    if (blk > 0) { rowPart(a, tr, 0, blk0 - 32); inBlock(a, r, blk0, blkEnd); colPart(a, r, blkEnd, n); }
+    else { inBlock(a, r, blk0, blkEnd); colPart(a, r, blkEnd, (nblk - 1) << 5); }
+    out[lane] = a.total();
+  };
   bool converged = false;
-  int sweeps = 0;
+  int sweeps = 0, t = 0;
+  if (PAIR) {
+    if (warp == 1) helperSum(0, part);
+    if (threadIdx.x == 0) *stop = 0;
+    __syncthreads();
+  }
   // sweep 0 works on the raw matrix (divides by the diagonal, absolute stopping rule); later sweeps on the normalised rows
   for (int iter = 0; iter < opt.maxIteration; iter++) {
     bool mine = true;  // possibleToTerminate restricted to this lane's rows
     sweeps++;
-    for (int blk = 0; blk < nblk; blk++) {
+    for (int blk = 0; blk < nblk; blk++, t++) {
+      if (warp == 1) {
+        helperSum(blk + 1 < nblk ? blk + 1 : 0, part + 32 * ((t + 1) & 1));
+        __syncthreads();
+        continue;
+      }
       const int blk0 = blk << 5, blkEnd = min(blk0 + 32, n);
       const bool valid = blk0 + lane < n;
       const int r = valid ? blk0 + lane : blkEnd - 1;  // idle lanes shadow the last row (their results are dropped)
@@ -168,27 +227,18 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
       // row normalisation (PgsBoxedLcpSolver.cpp:171-178); rows that are not iterated get 0 so that their residual stays finite
       // (the projection below selects with comparisons: a NaN would pass through it)
       const double f_r = !active ? 0.0 : (iter == 0 ? 1.0 : 1.0 / diag);
-      // phase 1
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      int j = 0;
-      for (; j + 3 < blk0; j += 4) {
-        a0 = __fma_rn(S[tr + j], ys[j], a0); a1 = __fma_rn(S[tr + j + 1], ys[j + 1], a1); a2 = __fma_rn(S[tr + j + 2], ys[j + 2], a2); a3 = __fma_rn(S[tr + j + 3], ys[j + 3], a3);
+      // phase 1 (PAIR: what the helper left out, on top of its sum)
+      Sum4 a;
+      double sum;
+      if (PAIR) {
+        if (blk > 0) rowPart(a, tr, blk0 - 32, blk0);
+        else colPart(a, r, (nblk - 1) << 5, n);
+        sum = part[32 * (t & 1) + lane] + a.total();
+      } else {
+        rowPart(a, tr, 0, blk0); inBlock(a, r, blk0, blkEnd); colPart(a, r, blkEnd, n);
+        sum = a.total();
       }
-      for (; j < blk0; j++) a0 += S[tr + j] * ys[j];
-      // the rows of this block behind row r (old values): four partial sums as in the loops around it; rows at or before r are
-      // masked out through their x (the matrix element read instead is some other finite entry of the triangle)
-      for (j = blk0; j + 3 < blkEnd; j += 4) {
-        const double y0 = j > r ? ys[j] : 0.0, y1 = j + 1 > r ? ys[j + 1] : 0.0, y2 = j + 2 > r ? ys[j + 2] : 0.0, y3 = j + 3 > r ? ys[j + 3] : 0.0;
-        a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], y0, a0); a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], y1, a1);
-        a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], y2, a2); a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], y3, a3);
-      }
-      for (; j < blkEnd; j++) a1 = __fma_rn(S[(j * (j + 1)) / 2 + r], j > r ? ys[j] : 0.0, a1);
-      for (j = blkEnd; j + 3 < n; j += 4) {
-        a0 = __fma_rn(S[(j * (j + 1)) / 2 + r], ys[j], a0); a1 = __fma_rn(S[((j + 1) * (j + 2)) / 2 + r], ys[j + 1], a1);
-        a2 = __fma_rn(S[((j + 2) * (j + 3)) / 2 + r], ys[j + 2], a2); a3 = __fma_rn(S[((j + 3) * (j + 4)) / 2 + r], ys[j + 3], a3);
-      }
-      for (; j < n; j++) a0 += S[(j * (j + 1)) / 2 + r] * ys[j];
-      double acc = (bs[r] - ((a0 + a1) + (a2 + a3))) * f_r;
+      double acc = (bs[r] - sum) * f_r;
       // phase 2: bounds (bl, bh) * xn (pgsBlockSteps)
       double bh = hi_r, bl = los[r], xn = 1.0;
       if (fi >= 0) { bl = -hi_r; xn = xs[fi]; }  // a normal row of an earlier block is final; one of this block is replaced in its step
@@ -205,11 +255,17 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
           else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs((x_new - old_x) / x_new) > opt.relativeDeltaXTolerance) mine = false; }
         }
       }
-      __syncwarp();
+      if (PAIR) {
+        if (blk == nblk - 1) { const bool all = __all_sync(0xffffffffu, mine); if (lane == 0) *stop = all ? 1 : 0; }
+        __syncthreads();
+      } else {
+        __syncwarp();
+      }
     }
-    converged = __all_sync(0xffffffffu, mine);
+    converged = PAIR ? *stop != 0 : __all_sync(0xffffffffu, mine);
     if (converged) break;
   }
+  if (warp == 1) return;
   const int slot = ctrl[8 * w + 1];
   double* ax = ans_x + ((size_t)w * kPgsRequests + slot) * kmax;
   for (int i = lane; i < n; i += 32) ax[i] = xs[i];
@@ -350,12 +406,16 @@ static long long* contactProfileBuffer() {  // one buffer per device (the curren
   return buf[dev];
 }
 // Shared memory of one world of at most cap rows: packed triangle, six vectors, the friction indices
-static size_t pgsWarpBytes(int cap) { return (size_t)((cap * (cap + 1)) / 2 + 6 * cap) * sizeof(double) + cap * sizeof(int); }
+// (+ the helper's two partial-sum buffers and the stop flag of the warp pairs)
+static size_t pgsWarpBytes(int cap) {
+  return (size_t)((cap * (cap + 1)) / 2 + 6 * cap + (cap + 1) / 2 + (cap > 32 ? 65 : 0)) * sizeof(double);
+}
 // The size classes (nLow, cap] of the warp solver. A world's shared memory is sized by its class, and the resident worlds per SM
 // (all the latency hiding this solver has: Gauss-Seidel is one dependent chain per world) by that: box stacking hands over problems of
 // 60 ... 108 rows in steps of 6 (two contacts), and a class that ends just above a frequent size holds 6 or 7 worlds per SM where
 // a coarser one held 5 (measured).
-static const int kPgsCaps[] = {24, 36, 48, 60, 66, 72, 78, 84, 90, 96, 102, 108, 116, 128, 144, 160, 192};
+// Classes above 32 rows (more than one row block) run as warp pairs.
+static const int kPgsCaps[] = {16, 24, 32, 40, 48, 60, 66, 72, 78, 84, 90, 96, 102, 108, 116, 128, 144, 160, 192};
 constexpr int kPgsClasses = sizeof(kPgsCaps) / sizeof(kPgsCaps[0]);
 constexpr int kPgsWarpMax = 192;
 static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int cap, int* ctrl, double* lcp_d, int* lcp_i, double* ans_x, int* ans_ok,
@@ -365,11 +425,12 @@ static cudaError_t launchPgsWarp(cudaStream_t s, int N, int kmax, int nLow, int 
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (!configured[dev & 63]) {
-    e = cudaFuncSetAttribute(k_pgs_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pgsWarpBytes(kPgsWarpMax));
+    e = cudaFuncSetAttribute(k_pgs_warp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pgsWarpBytes(kPgsWarpMax));
     if (e != cudaSuccess) return e;
     configured[dev & 63] = true;
   }
-  k_pgs_warp<<<N, 32, pgsWarpBytes(cap), s>>>(N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+  if (nLow >= 32) k_pgs_warp<true><<<N, 64, pgsWarpBytes(cap), s>>>(N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+  else k_pgs_warp<false><<<N, 32, pgsWarpBytes(cap), s>>>(N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
   return cudaGetLastError();
 }
 // helper streams of the concurrent PGS size classes, one set per device
