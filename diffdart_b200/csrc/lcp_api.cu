@@ -145,8 +145,9 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
   double* xs = his + CAP;   // x
   double* ys = xs + CAP;    // scale * x
   double* sc = ys + CAP;    // column scale of the reduced problem
-  int* fis = reinterpret_cast<int*>(sc + CAP);
-  double* part = sc + CAP + (CAP + 1) / 2;             // PAIR: [2][32] partial sums of the helper
+  double* fs = sc + CAP;    // 1 / diagonal of the scaled matrix; 0 for rows that are not iterated (diagonal below epsilonForDivision)
+  int* fis = reinterpret_cast<int*>(fs + CAP);
+  double* part = fs + CAP + (CAP + 1) / 2;             // PAIR: [2][32] partial sums of the helper
   int* stop = reinterpret_cast<int*>(part + 64);      // PAIR: the sweep just finished was the last
   auto ctaSync = [&]() { if (PAIR) __syncthreads(); else __syncwarp(); };
   LcpView v;
@@ -159,6 +160,12 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
   for (int r = warp; r < n; r += PAIR ? 2 : 1)
     for (int j = lane; j <= r; j += 32) S[(r * (r + 1)) / 2 + j] = v.Araw(r, j) / sc[j];
   for (int i = threadIdx.x; i < n; i += nthreads) ys[i] = sc[i] * xs[i];
+  ctaSync();
+  // (the division of the row normalisation once, not in every sweep)
+  for (int i = threadIdx.x; i < n; i += nthreads) {
+    const double d = S[(i * (i + 1)) / 2 + i] * sc[i];
+    fs[i] = d < opt.epsilonForDivision ? 0.0 : 1.0 / d;
+  }
   ctaSync();
   const int nblk = (n + 31) >> 5;
   // the three column ranges of phase 1 for row r (tr = its offset in the triangle), four partial sums
@@ -220,13 +227,13 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
       const bool valid = blk0 + lane < n;
       const int r = valid ? blk0 + lane : blkEnd - 1;  // idle lanes shadow the last row (their results are dropped)
       const int tr = (r * (r + 1)) / 2;
-      const double diag = S[tr + r] * sc[r];
-      const bool active = !(diag < opt.epsilonForDivision);
+      const double inv = fs[r];
+      const bool active = inv != 0.0;
       const double old_x = xs[r], hi_r = his[r];
       const int fi = fis[r];
       // row normalisation (PgsBoxedLcpSolver.cpp:171-178); rows that are not iterated get 0 so that their residual stays finite
       // (the projection below selects with comparisons: a NaN would pass through it)
-      const double f_r = !active ? 0.0 : (iter == 0 ? 1.0 : 1.0 / diag);
+      const double f_r = !active ? 0.0 : (iter == 0 ? 1.0 : inv);
       // phase 1 (PAIR: what the helper left out, on top of its sum)
       Sum4 a;
       double sum;
@@ -244,15 +251,16 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
       if (fi >= 0) { bl = -hi_r; xn = xs[fi]; }  // a normal row of an earlier block is final; one of this block is replaced in its step
       if (!active) { bh = bl = iter == 0 ? 0.0 : old_x; xn = 1.0; }
       __syncwarp();  // (every lane has read what it needs of xs before the owners of this block's rows overwrite them)
-      if (iter == 0) pgsBlockSteps<true>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, active ? diag : 1.0, f_r, acc);
-      else pgsBlockSteps<false>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, diag, f_r, acc);
+      if (iter == 0) pgsBlockSteps<true>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, active ? S[tr + r] * sc[r] : 1.0, f_r, acc);
+      else pgsBlockSteps<false>(S, sc, xs + blk0, blk0, r, blkEnd - blk0, lane, active ? fi - blk0 : -1, bh, bl, xn, 1.0, f_r, acc);
       __syncwarp();
       if (valid) {
         const double x_new = xs[r];
         ys[r] = sc[r] * x_new;
         if (active) {
           if (iter == 0) { if (fabs(x_new - old_x) > opt.deltaXThreshold) mine = false; }
-          else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs((x_new - old_x) / x_new) > opt.relativeDeltaXTolerance) mine = false; }
+          // |dx / x| > tolerance (PgsBoxedLcpSolver.cpp:238-244) without the division: |x| > epsilonForDivision > 0 here
+          else if (fabs(x_new) > opt.epsilonForDivision) { if (fabs(x_new - old_x) > opt.relativeDeltaXTolerance * fabs(x_new)) mine = false; }
         }
       }
       if (PAIR) {
@@ -405,10 +413,10 @@ static long long* contactProfileBuffer() {  // one buffer per device (the curren
   }
   return buf[dev];
 }
-// Shared memory of one world of at most cap rows: packed triangle, six vectors, the friction indices
+// Shared memory of one world of at most cap rows: packed triangle, seven vectors, the friction indices
 // (+ the helper's two partial-sum buffers and the stop flag of the warp pairs)
 static size_t pgsWarpBytes(int cap) {
-  return (size_t)((cap * (cap + 1)) / 2 + 6 * cap + (cap + 1) / 2 + (cap > 32 ? 65 : 0)) * sizeof(double);
+  return (size_t)((cap * (cap + 1)) / 2 + 7 * cap + (cap + 1) / 2 + (cap > 32 ? 65 : 0)) * sizeof(double);
 }
 // The size classes (nLow, cap] of the warp solver. A world's shared memory is sized by its class, and the resident worlds per SM
 // (all the latency hiding this solver has: Gauss-Seidel is one dependent chain per world) by that: box stacking hands over problems of
