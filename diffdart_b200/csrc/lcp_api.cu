@@ -6,6 +6,13 @@
 #include "contact_bwd.cuh"
 #include "contact_api.h"
 
+// resident CTAs per SM the contact kernels are compiled for (register cap 255 / 168 / 128 at 1-2 / 3 / 4 CTAs of 128 threads)
+#ifndef DDB_KC_MINB
+#define DDB_KC_MINB 1
+#endif
+#ifndef DDB_KCB_MINB
+#define DDB_KCB_MINB 1
+#endif
 using namespace ddb;
 
 namespace {
@@ -308,7 +315,7 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
 // broadcasts, stores coincide), so a batch of N worlds keeps N warps in flight instead of N / 32. The stage is a chain of
 // dependent memory accesses (pivoting solvers, Householder sweeps); what bounds it is how many of those chains the SMs
 // can overlap, not arithmetic, and the redundant lanes cost nothing that matters (FP64 issue stays far below the pipe).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, DDB_KC_MINB)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
           int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
@@ -340,7 +347,7 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
 
 // BackpropSnapshot::backprop through the contact solution of the step retained in this slot, one world per thread
 template <int NB>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(64, DDB_KCB_MINB)
 k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL, double* __restrict__ snap, const double* __restrict__ keep_d,
                    const int* __restrict__ keep_i, const double* __restrict__ gqn, const double* __restrict__ gqdn, double* __restrict__ gq,
                    double* __restrict__ gqd, double* __restrict__ gtau, double* __restrict__ work_d, int* __restrict__ work_i,
