@@ -309,6 +309,7 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
   ans_ok[(size_t)w * kPgsRequests + slot] = ok ? 1 : 0;
   ctrl[8 * w + 1] = slot + 1;
   ctrl[8 * w + 2] = 0;
+  if (n > ctrl[8 * w + 5]) ctrl[8 * w + 5] = n;
 }
 
 // The contact stage of World::step, one world per WARP: the 32 lanes run the same scalar code on the same data (loads are
@@ -502,17 +503,21 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
       if (!used[i]) { used[i] = true; if ((r = cudaStreamWaitEvent(ps->st[i], ps->fork, 0)) != cudaSuccess) return r; }
       return launch(ps->st[i]);
     };
-    // (the largest problems first: they are the last to finish)
-    if (kmax > kPgsWarpMax) {
+    // (the largest problems first: they are the last to finish.) DDB_PGS_WARP_MAX=<rows> in the environment sends smaller problems
+    // to the scalar kernel as well: that path is otherwise only reached by worlds of more than 64 contacts (tests)
+    int warpMax = kPgsWarpMax;
+    if (const char* env = getenv("DDB_PGS_WARP_MAX")) { const int m = atoi(env); if (m >= 0 && m < warpMax) warpMax = m; }
+    if (kmax > warpMax) {
       if ((e = onHelper([&](cudaStream_t hs) {
-             k_pgs_thread<<<(N + 63) / 64, 64, 0, hs>>>(N, kmax, kPgsWarpMax, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+             k_pgs_thread<<<(N + 63) / 64, 64, 0, hs>>>(N, kmax, warpMax, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
              return cudaGetLastError();
            })) != cudaSuccess) return e;
     }
     for (int c = kPgsClasses - 1; c >= 0; c--) {
       const int nLow = c ? kPgsCaps[c - 1] : 0;
-      if (nLow >= kmax) continue;
-      if ((e = onHelper([&](cudaStream_t hs) { return launchPgsWarp(hs, N, kmax, nLow, kPgsCaps[c], ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+      if (nLow >= kmax || nLow >= warpMax) continue;
+      const int cap = kPgsCaps[c] < warpMax ? kPgsCaps[c] : warpMax;
+      if ((e = onHelper([&](cudaStream_t hs) { return launchPgsWarp(hs, N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
     }
     for (int i = 0; i < kPgsStreams; i++) {
       if (!used[i]) continue;

@@ -76,6 +76,30 @@ def test_contact_step_matches_oracle(scene):
             assert np.allclose(x[:len(r["x"])], r["x"], rtol=1e-8, atol=1e-11)
 
 
+def test_scalar_pgs_kernel_for_large_problems(monkeypatch):
+    """Problems above the warp solver's 192 rows go to the scalar k_pgs_thread; DDB_PGS_WARP_MAX lowers that limit so that the box stack's
+    60 ... 108-row problems take that path (and the classes below the limit the warp path, in the same launch)."""
+    monkeypatch.setenv("DDB_PGS_WARP_MAX", "80")
+    make, states = SCENES["box_stack"]
+    desc = make()
+    N = 48
+    q, qd, tau = states(N, 9)
+    world = BatchedWorld(PlainStepDescription(desc), N)
+    world.setPositions(cuda(q)); world.setVelocities(cuda(qd)); world.setForces(cuda(tau))
+    forwardPass(world)
+    qdn = world.getVelocities().cpu().numpy()
+    counts, _, _ = contact_debug(world, -1)
+    rows = np.zeros(N, dtype=np.int32)
+    assert world._lib.ddb_contact_pgs_rows_host(world._h, rows.ctypes.data_as(C.c_void_p)) == 0
+    assert (rows > 80).any() and ((rows > 0) & (rows <= 80)).any(), rows   # both paths were taken
+    o = OracleWorld(desc)
+    for w in range(N):
+        r = o.step_contacts(q[w], qd[w], tau[w])
+        assert list(counts[w]) == [len(r["contacts"]), len(r["x"]), r["n_groups"], r["tier_mask"]], w
+        tol = (1e-6, 1e-8) if r["tier_mask"] & 12 else (1e-9, 1e-11)
+        assert np.allclose(qdn[w], r["qd_next"], rtol=tol[0], atol=tol[1]), w
+
+
 @pytest.mark.parametrize("scene", sorted(SCENES))
 def test_forward_pass_rollout_active_set_bit_exact(scene):
     """neural::forwardPass (gradient-enabled solve) over a rollout that carries the solver's cached solution: the active
