@@ -172,6 +172,32 @@ struct ChainStageB : ChainStageBase<NB, BLOCK>, SnapReaders<ChainStageB<NB, BLOC
   DDB_DI void beginAdj(int) const { cpAsyncWait<ChainStageGeom<NB, BLOCK>::kBufs - 1>(); }
   DDB_DI void endAdj(int i) const { B::requestB(i - ChainStageGeom<NB, BLOCK>::kBufs); }
 };
+// The whole snapshot of this thread's world copied to shared memory once (cp.async, 13 pairs per body): for the kernels that walk
+// it n times (k_jacobians, k_inv_mass: one pull-back per DOF), whose plain reads were three of every six cycles of a warp (long
+// scoreboard; ncu, profiles/README.md round 2). A thread reads only its own column, so no CTA barrier is needed.
+template <int NB, int BLOCK>
+struct ChainResident : SnapReaders<ChainResident<NB, BLOCK>> {
+  static constexpr int kRows = kChainPairs * NB;
+  static constexpr size_t kBytes = (size_t)kRows * BLOCK * sizeof(double2);
+  static constexpr bool kFits = kBytes <= 72 * 1024;  // three CTAs per SM
+  const double2* sm;
+  DDB_DI void load(const Snap& sn, double2* smemBase) {
+    double2* col = smemBase + threadIdx.x;
+    const double2* g = sn.base + sn.origin();
+    const size_t strideN = sn.rowStride();
+    const unsigned a = sharedAddr(col);
+#pragma unroll
+    for (int r = 0; r < kRows; r++) cpAsync16(a + (unsigned)(r * BLOCK * (int)sizeof(double2)), g + (size_t)r * strideN);
+    cpAsyncCommit();
+    cpAsyncWait<0>();
+    sm = col;
+  }
+  DDB_DI double2 ld(int body, int k) const { return sm[(kChainPairs * body + k) * BLOCK]; }
+  DDB_DI void beginUp(int) const {}
+  DDB_DI void endDown(int) const {}
+  DDB_DI void beginAdj(int) const {}
+  DDB_DI void endAdj(int) const {}
+};
 // plain reads of the snapshot with the same interface (A/B timing with DDB_BWD_STAGE=0, k_jacobians, k_inv_mass, host emulation)
 struct ChainPlain : SnapReaders<ChainPlain> {
   Snap sn;

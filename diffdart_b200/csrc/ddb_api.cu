@@ -71,7 +71,19 @@ struct Launch {
     k_backward<NB, CHAIN, kBlockB, kMinBB><<<grid(w1 - w0, kBlockB), kBlockB, smem, s>>>(N, w0, w1, snap, gqn, gqdn, gqnAdd, gqdnAdd, gq, gqd, gtau, lim);
   }
   static void jac(cudaStream_t s, int N, double* snap, double* pp, double* pv, double* vp, double* vv, double* fv) {
-    k_jacobians<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, pp, pv, vp, vv, fv);
+    // chains small enough keep their snapshot in shared memory for the n pull-backs (kernels.cuh, kJacResident)
+    const size_t smem = kJacResident<NB, CHAIN, kBlock> ? ChainResident<NB, kBlock>::kBytes : 0;
+    if (smem) {
+      static bool once[64] = {false};  // per instantiation and device
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (!once[dev & 63]) {
+        cudaFuncSetAttribute(k_jacobians<NB, CHAIN, kBlock, kMinB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_jacobians<NB, CHAIN, kBlock, kMinB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        once[dev & 63] = true;
+      }
+    }
+    k_jacobians<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, smem, s>>>(N, snap, pp, pv, vp, vv, fv);
   }
   static void minv(cudaStream_t s, int N, double* snap, double* out) {
     k_inv_mass<NB, CHAIN, kBlock, kMinB><<<grid(N), kBlock, 0, s>>>(N, snap, out);

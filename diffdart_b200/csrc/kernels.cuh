@@ -11,6 +11,9 @@
 #include "dynamics.cuh"
 #include "chain.cuh"
 
+#ifndef DDB_JAC_RESIDENT
+#define DDB_JAC_RESIDENT 1  // 0: k_jacobians / k_inv_mass read the snapshot with plain loads (A/B timing only)
+#endif
 #ifndef DDB_BWD_STAGE
 #ifdef DDB_HOST_EMULATION
 #define DDB_BWD_STAGE 0  // (no cp.async on the host)
@@ -322,6 +325,11 @@ k_backward(int N, int w0, int w1, double* __restrict__ snap, const double* __res
 
 // Each unit vector e_j pulled back through the step gives row j of vel-vel, pos-vel, force-vel.
 // Outputs are [world][col][row] (column-major per world); NULL pointers are skipped.
+#ifdef DDB_HOST_EMULATION
+template <int NB, int CHAIN, int BLOCK> constexpr bool kJacResident = false;
+#else
+template <int NB, int CHAIN, int BLOCK> constexpr bool kJacResident = CHAIN != 0 && DDB_JAC_RESIDENT && ChainResident<NB, BLOCK>::kFits;
+#endif
 template <int NB, int CHAIN, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB)
 k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, double* __restrict__ posVel,
@@ -334,9 +342,20 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   BwdScratch<NB> ws;
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
+  auto reader = [&]() {  // chains small enough keep the snapshot in shared memory for the n pull-backs (ChainResident)
+    if constexpr (CHAIN != 0 && kJacResident<NB, CHAIN, BLOCK>) {
+      extern __shared__ double2 ddb_stage[];
+      ChainResident<NB, BLOCK> r;
+      r.load(sn, ddb_stage);
+      return r;
+    } else {
+      return ChainPlain{{}, sn};
+    }
+  };
+  const auto rd = reader();
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
-    if constexpr (CHAIN) chainSolveInvMass<NB, CHAIN == 2>(ChainPlain{{}, sn}, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
+    if constexpr (CHAIN) chainSolveInvMass<NB, CHAIN == 2>(rd, [&](int d) { return d == j ? 1.0 : 0.0; }, ws);
     else solveInvMass<NB, false>(sn, nb, [&](int d) { return d == j ? 1.0 : 0.0; }, ws,
                                  [&](int d, double m) { if (forceVel) forceVel[base + (size_t)d * n + j] = dt * m; });
     if (forceVel) {
@@ -354,7 +373,7 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
         if (posVel) posVel[base + (size_t)d * n + j] = -dt * dq;
         if (velVel) velVel[base + (size_t)d * n + j] = (d == j ? 1.0 : 0.0) - dt * dqd;
       };
-      if constexpr (CHAIN) chainIdAdjoint<NB, CHAIN == 2>(ChainPlain{{}, sn}, ws, outRow);
+      if constexpr (CHAIN) chainIdAdjoint<NB, CHAIN == 2>(rd, ws, outRow);
       else idAdjoint<NB, false>(sn, nb, ws, outRow, [&](int body, const double* dq6, const double* dqd6) {
         const int d0 = c_topo.b[body].dof;
         for (int k = 0; k < 6; k++) {
