@@ -293,6 +293,104 @@ k_pgs_warp(int N, int kmax, int nLow, int CAP, int* __restrict__ ctrl, double* _
   }
 }
 
+// Problems of at most 32 rows (one row block: Atlas' feet, the walkers): lane r keeps row r of the matrix in REGISTERS, normalised
+// once after sweep 0 as the reference does (A_ij * (1 / A_ii), PgsBoxedLcpSolver.cpp:171-178), and one residual that serves two
+// sweeps: up to its own step a lane subtracts the new x_j (j < r) of this sweep, from its own step on it rebuilds b_r - sum_{j > r}
+// A_rj x_j for the next one. A step is {project, broadcast by one shuffle, one DFMA}: no phase 1, no matrix in shared memory, no
+// element loads on the way. Sweep order, projections and stopping rules are the reference's; the summation order inside a row is not.
+template <bool FIRST>
+__device__ __forceinline__ void pgsSmallSweep(int n, int lane, const double (&a)[32], double start, int fi, double bh, double bl, double diag,
+                                              double& acc, double& x_r) {
+  double xn = 1.0;  // live normal impulse of a friction row (its normal row precedes it: replaced before this lane's own step)
+#pragma unroll
+  for (int jj = 0; jj < 32; jj++) {
+    if (jj >= n) break;
+    const double cand = FIRST ? acc / diag : acc;
+    const double hi_e = bh * xn, lo_e = bl * xn;
+    double nx = cand < lo_e ? lo_e : cand;
+    nx = cand > hi_e ? hi_e : nx;  // (PgsBoxedLcpSolver.cpp:139-150: the upper bound is tested first)
+    const double xj = __shfl_sync(0xffffffffu, nx, jj);
+    const bool own = lane == jj;
+    x_r = own ? xj : x_r;
+    acc = own ? start : __fma_rn(-a[jj], xj, acc);
+    xn = fi == jj ? xj : xn;
+  }
+}
+
+__global__ void __launch_bounds__(32)
+k_pgs_small(int N, int kmax, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i, double* __restrict__ ans_x,
+            int* __restrict__ ans_ok, PgsOptions opt) {
+  const int w = blockIdx.x, lane = threadIdx.x;
+  const int n = ctrl[8 * w + 2];
+  if (ctrl[8 * w] || n <= 0 || n > 32) return;
+  LcpView v;
+  v.init(lcp_d + (size_t)w * lcpScratchDoubles(kmax), lcp_i + (size_t)w * lcpScratchInts(kmax), n, kmax, 1);
+  const bool valid = lane < n;
+  const int r = valid ? lane : n - 1;  // idle lanes shadow the last row (their results are dropped; they never own a step)
+  // row r of the reduced matrix A[keep][keep] * diag(scale), its upper part from the symmetric lower one as k_pgs_warp reads it
+  const double sc_r = v.tmp(r);  // buildReduced leaves the column scales here (powers of two)
+  double a[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) a[j] = j >= n ? 0.0 : (j <= r ? v.Araw(r, j) : v.Araw(j, r) / sc_r * v.tmp(j));
+  double diag = 0.0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) diag = j == r ? a[j] : diag;
+  const bool active = !(diag < opt.epsilonForDivision);
+  const double inv = active ? 1.0 / diag : 0.0;
+  const double b_r = v.b(r), hi_r = v.hi(r);
+  const int fi = active ? v.findex(r) : -1;
+  double x_r = v.x(r);
+  double bh = hi_r, bl = v.lo(r);
+  if (fi >= 0) bl = -hi_r;
+  if (!active) {  // rows that are not iterated: 0 in sweep 0, unchanged afterwards; a zero row keeps their residual finite
+    bh = bl = 0.0;
+#pragma unroll
+    for (int j = 0; j < 32; j++) a[j] = 0.0;
+  }
+  // residual of sweep 0: b_r - sum_{j > r} A_rj x_j over the initial x
+  double acc = active ? b_r : 0.0;
+#pragma unroll
+  for (int jj = 0; jj < 32; jj++) {
+    if (jj >= n) break;
+    const double xj = __shfl_sync(0xffffffffu, x_r, jj);
+    acc = jj > lane ? __fma_rn(-a[jj], xj, acc) : acc;
+  }
+  bool converged = false;
+  int sweeps = 1;
+  {
+    const double old_x = x_r;
+    pgsSmallSweep<true>(n, lane, a, active ? b_r : 0.0, fi, bh, bl, active ? diag : 1.0, acc, x_r);
+    const bool mine = !(valid && active && fabs(x_r - old_x) > opt.deltaXThreshold);
+    converged = __all_sync(0xffffffffu, mine);
+  }
+  if (!converged) {
+    // row normalisation; the residual under way (raw so far) with it
+    acc *= inv;
+#pragma unroll
+    for (int j = 0; j < 32; j++) a[j] *= inv;
+    const double start = b_r * inv;
+    if (!active) bh = bl = x_r;  // (0 after sweep 0)
+    for (int iter = 1; iter < opt.maxIteration; iter++) {
+      sweeps++;
+      const double old_x = x_r;
+      pgsSmallSweep<false>(n, lane, a, start, fi, bh, bl, 1.0, acc, x_r);
+      // |dx / x| > tolerance (PgsBoxedLcpSolver.cpp:238-244) without the division: |x| > epsilonForDivision > 0 here
+      const bool mine = !(valid && active && fabs(x_r) > opt.epsilonForDivision && fabs(x_r - old_x) > opt.relativeDeltaXTolerance * fabs(x_r));
+      converged = __all_sync(0xffffffffu, mine);
+      if (converged) break;
+    }
+  }
+  const int slot = ctrl[8 * w + 1];
+  if (valid) ans_x[((size_t)w * kPgsRequests + slot) * kmax + r] = x_r;
+  if (lane == 0) {
+    ans_ok[(size_t)w * kPgsRequests + slot] = converged ? 1 : 0;
+    ctrl[8 * w + 1] = slot + 1;
+    ctrl[8 * w + 2] = 0;
+    ctrl[8 * w + 3] += sweeps;
+    if (n > ctrl[8 * w + 5]) ctrl[8 * w + 5] = n;
+  }
+}
+
 // problems too large for shared memory: the scalar solver, one world per thread
 __global__ void __launch_bounds__(64)
 k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restrict__ lcp_d, int* __restrict__ lcp_i, double* __restrict__ ans_x,
@@ -503,7 +601,9 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
       if (!used[i]) { used[i] = true; if ((r = cudaStreamWaitEvent(ps->st[i], ps->fork, 0)) != cudaSuccess) return r; }
       return launch(ps->st[i]);
     };
-    // (the largest problems first: they are the last to finish.) DDB_PGS_WARP_MAX=<rows> in the environment sends smaller problems
+    // The largest problems first (fewest resident worlds per SM, last to finish): measured on box stacking, 386 ms per step in this
+    // order, 398 ms from the middle class outwards, 438 ms smallest first; the single-block solver's launch therefore comes last.
+    // DDB_PGS_WARP_MAX=<rows> in the environment sends smaller problems
     // to the scalar kernel as well: that path is otherwise only reached by worlds of more than 64 contacts (tests)
     int warpMax = kPgsWarpMax;
     if (const char* env = getenv("DDB_PGS_WARP_MAX")) { const int m = atoi(env); if (m >= 0 && m < warpMax) warpMax = m; }
@@ -515,9 +615,15 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
     }
     for (int c = kPgsClasses - 1; c >= 0; c--) {
       const int nLow = c ? kPgsCaps[c - 1] : 0;
-      if (nLow >= kmax || nLow >= warpMax) continue;
+      if (nLow >= kmax || nLow >= warpMax || (warpMax >= 32 && kPgsCaps[c] <= 32)) continue;
       const int cap = kPgsCaps[c] < warpMax ? kPgsCaps[c] : warpMax;
       if ((e = onHelper([&](cudaStream_t hs) { return launchPgsWarp(hs, N, kmax, nLow, cap, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs); })) != cudaSuccess) return e;
+    }
+    if (warpMax >= 32) {  // one block of rows: the register-resident solver
+      if ((e = onHelper([&](cudaStream_t hs) {
+             k_pgs_small<<<N, 32, 0, hs>>>(N, kmax, ctrl, lcp_d, lcp_i, ans_x, ans_ok, pgs);
+             return cudaGetLastError();
+           })) != cudaSuccess) return e;
     }
     for (int i = 0; i < kPgsStreams; i++) {
       if (!used[i]) continue;
