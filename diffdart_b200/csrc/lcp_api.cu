@@ -10,10 +10,17 @@
 #ifndef DDB_KC_MINB
 #define DDB_KC_MINB 1
 #endif
+#ifndef DDB_KCB_BLOCK
+#define DDB_KCB_BLOCK 256  // threads per CTA of k_contact_backward (one world per warp; see k_contact about the CTA size): measured 64 -> 256
+#endif                     // walker 25.5 -> 16.9 ms, half-cheetah 6.2 -> 3.9 ms, box stacking 50.7 -> 43.9 ms per backward pass
+#ifndef DDB_KC_BLOCK
+#define DDB_KC_BLOCK 128  // threads per CTA of k_contact (one world per warp) for worlds of more than kContactWideRows rows; 256 below
+#endif
 #ifndef DDB_KCB_MINB
 #define DDB_KCB_MINB 1
 #endif
 using namespace ddb;
+constexpr int kContactWideRows = 64;
 
 namespace {
 
@@ -414,7 +421,13 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
 // broadcasts, stores coincide), so a batch of N worlds keeps N warps in flight instead of N / 32. The stage is a chain of
 // dependent memory accesses (pivoting solvers, Householder sweeps); what bounds it is how many of those chains the SMs
 // can overlap, not arithmetic, and the redundant lanes cost nothing that matters (FP64 issue stays far below the pipe).
-__global__ void __launch_bounds__(128, DDB_KC_MINB)
+// CTA size: the stage is 54 000 instructions of which a world touches 24 000 once or twice - more than half of a warp's stall
+// cycles are instruction fetches (ncu: stall_no_instruction 8.7 of 16 cycles per issue, profiles/README.md). Warps of one CTA
+// start together and run the same code at about the same time, so they share the fetched lines: 8 warps per CTA (the whole SM
+// at 252 registers) instead of 4 is 10-19 % faster for the walkers; box stacking, whose worlds differ by 10x in solver time,
+// loses 3 % to the CTA's wait for its slowest warp and keeps 4 (contactLaunch chooses by the row capacity).
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK, DDB_KC_MINB)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
           int* __restrict__ n_cache, int* __restrict__ counts, int* __restrict__ active_out, double* __restrict__ work_d,
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
@@ -446,7 +459,7 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
 
 // BackpropSnapshot::backprop through the contact solution of the step retained in this slot, one world per thread
 template <int NB>
-__global__ void __launch_bounds__(64, DDB_KCB_MINB)
+__global__ void __launch_bounds__(DDB_KCB_BLOCK, DDB_KCB_MINB)
 k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL, double* __restrict__ snap, const double* __restrict__ keep_d,
                    const int* __restrict__ keep_i, const double* __restrict__ gqn, const double* __restrict__ gqdn, double* __restrict__ gq,
                    double* __restrict__ gqd, double* __restrict__ gtau, double* __restrict__ work_d, int* __restrict__ work_i,
@@ -583,7 +596,9 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
   if (e != cudaSuccess) return e;
   // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
   for (int pass = 0; pass <= kPgsRequests; pass++) {
-    k_contact<<<(int)(((size_t)N * 32 + 127) / 128), 128, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+    if (kmax <= kContactWideRows) k_contact<256><<<(int)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+                                           keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
+    else k_contact<DDB_KC_BLOCK><<<(int)(((size_t)N * 32 + DDB_KC_BLOCK - 1) / DDB_KC_BLOCK), DDB_KC_BLOCK, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
                                            keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) (*launches)++;
@@ -654,8 +669,8 @@ cudaError_t contactBackwardLaunch(cudaStream_t s, int N, int nb, int nd, int cma
   ContactBwdLayout BL{nb, nd, kmax};
   Limits lim{lim6, lim6 ? lim6 + nd : nullptr, lim6 ? lim6 + 2 * nd : nullptr, lim6 ? lim6 + 3 * nd : nullptr, lim6 ? lim6 + 4 * nd : nullptr,
              lim6 ? lim6 + 5 * nd : nullptr};
-  const int grid = (int)(((size_t)N * 32 + 63) / 64);
-#define DDB_CB(NBV) k_contact_backward<NBV><<<grid, 64, 0, s>>>(N, layout, KL, BL, snap, keep_d, keep_i, gqn, gqdn, gq, gqd, gtau, work_d, work_i, lcp_d, lcp_i, lim, status)
+  const int grid = (int)(((size_t)N * 32 + DDB_KCB_BLOCK - 1) / DDB_KCB_BLOCK);
+#define DDB_CB(NBV) k_contact_backward<NBV><<<grid, DDB_KCB_BLOCK, 0, s>>>(N, layout, KL, BL, snap, keep_d, keep_i, gqn, gqdn, gq, gqd, gtau, work_d, work_i, lcp_d, lcp_i, lim, status)
   if (nb <= 8) DDB_CB(8);
   else if (nb <= 16) DDB_CB(16);
   else if (nb <= 32) DDB_CB(32);
