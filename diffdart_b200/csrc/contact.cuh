@@ -72,9 +72,31 @@ struct ContactWork {
   int* i;
   ContactLayout L;
   long long* prof = nullptr;  // optional: clock64 ticks per section, summed over worlds (DDB_CONTACT_PROFILE=1)
+  // optional (k_contact with 8 warps per CTA): the section each warp of the CTA has reached, in shared memory. The stage is bound
+  // by instruction fetches and warps at the same place of the code share them, so at the end of a section a warp lets the others
+  // catch up - for a bounded time: this is a scheduling hint, nothing depends on it (a warp that left the stage reads as "ahead").
+  volatile int* convoy = nullptr;
+  int convoyWarps = 0;
+  mutable int convoyGroup = 0, convoySection = 0, convoyLast = 0;  // (sections completed in this group; last meeting point published)
+  DDB_LCP_DI void convoyWait(int id) const {
+#ifdef __CUDA_ARCH__
+    if (id <= convoyLast) return;  // (meeting points are published in increasing order)
+    convoyLast = id;
+    convoy[threadIdx.x >> 5] = id;
+    __syncwarp();
+    for (int spins = 0; spins < 4000; spins++) {
+      int behind = 0;
+      for (int k = 0; k < convoyWarps; k++) behind |= convoy[k] < id;
+      if (!behind) break;
+      __nanosleep(100);
+    }
+    __syncwarp();
+#endif
+  }
   DDB_LCP_DI void mark(int section, long long& t) const {
 #ifdef __CUDA_ARCH__
     if (prof) { const long long now = clock64(); atomicAdd(reinterpret_cast<unsigned long long*>(prof) + section, (unsigned long long)(now - t)); t = now; }
+    if (convoy) { convoySection = section + 1; convoyWait(convoyGroup * 8 + convoySection); }
 #endif
   }
   DDB_LCP_DI double* contact(int c) const { return d + L.oContacts() + (size_t)c * 26; }
@@ -428,6 +450,7 @@ DDB_LCP_DI ContactStepOut contactStage(const Snap& sn, const ContactWork& cw, do
     defer->resumeKind = kind;
   };
   for (int g = resuming ? sv[0] : 0; g < ng; g++) {
+    cw.convoyGroup = g;
     const bool resumeHere = resuming && g == sv[0];
     // rows of this group
     int n = 0;

@@ -343,12 +343,15 @@ k_jacobians(int N, double* __restrict__ snap, double* __restrict__ posPos, doubl
   const double* mu = ws.mu;
   const size_t base = (size_t)w * n * n;
   auto reader = [&]() {  // chains small enough keep the snapshot in shared memory for the n pull-backs (ChainResident)
+#ifndef DDB_HOST_EMULATION
     if constexpr (CHAIN != 0 && kJacResident<NB, CHAIN, BLOCK>) {
       extern __shared__ double2 ddb_stage[];
       ChainResident<NB, BLOCK> r;
       r.load(sn, ddb_stage);
       return r;
-    } else {
+    } else
+#endif
+    {
       return ChainPlain{{}, sn};
     }
   };

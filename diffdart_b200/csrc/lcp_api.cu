@@ -13,6 +13,9 @@
 #ifndef DDB_KCB_BLOCK
 #define DDB_KCB_BLOCK 256  // threads per CTA of k_contact_backward (one world per warp; see k_contact about the CTA size): measured 64 -> 256
 #endif                     // walker 25.5 -> 16.9 ms, half-cheetah 6.2 -> 3.9 ms, box stacking 50.7 -> 43.9 ms per backward pass
+#ifndef DDB_KC_CONVOY
+#define DDB_KC_CONVOY 1  // 0: the warps of a 256-thread k_contact CTA do not wait for each other at the ends of the stage's sections
+#endif
 #ifndef DDB_KC_BLOCK
 #define DDB_KC_BLOCK 128  // threads per CTA of k_contact (one world per warp) for worlds of more than kContactWideRows rows; 256 below
 #endif
@@ -433,10 +436,17 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
           int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok, long long* __restrict__ prof) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= N) return;
-  if (ctrl && ctrl[8 * w]) return;  // this world's stage has been committed by an earlier pass
+  constexpr bool kConvoy = BLOCK >= 256 && DDB_KC_CONVOY;
+  __shared__ int reached[BLOCK / 32];  // kConvoy: ContactWork::mark
+  const bool live = w < N && !(ctrl && ctrl[8 * w]);  // (else: past the batch, or committed by an earlier pass)
+  if (kConvoy) {
+    reached[threadIdx.x >> 5] = live ? 0 : 0x7fffffff;
+    __syncthreads();
+  }
+  if (!live) return;
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactWork cw{work_d + (size_t)w * L.doubles(), work_i + (size_t)w * L.ints(), L, prof};
+  if (kConvoy) { cw.convoy = reached; cw.convoyWarps = BLOCK / 32; }
   const ContactSnapLayout KL{L.nd, L.cmax, L.kmax};
   double* ld = lcp_d + (size_t)w * lcpScratchDoubles(L.kmax);
   int* li = lcp_i + (size_t)w * lcpScratchInts(L.kmax);
@@ -447,6 +457,7 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
                                   keep_d ? keep_d + (size_t)w * KL.doubles() : nullptr, keep_i ? keep_i + (size_t)w * KL.ints() : nullptr,
                                   ctrl ? &df : nullptr, 1);
   __syncwarp();  // every lane has read the control words before any lane rewrites them
+  if (kConvoy) reached[threadIdx.x >> 5] = 0x7fffffff;
   if (o.pending) { ctrl[8 * w + 2] = df.pendingN; ctrl[8 * w + 4] = df.resumeKind; return; }  // the reduced problem waits in this world's LCP view
   if (ctrl) { ctrl[8 * w] = 1; ctrl[8 * w + 2] = 0; }
   n_cache[w] = nc;
