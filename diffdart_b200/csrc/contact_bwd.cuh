@@ -204,6 +204,38 @@ struct ContactBwdLocals {  // one object: see the note on BwdScratch (stack colo
   SV dA[NB];
 };
 
+// Meeting points of the warps of a CTA (k_contact_backward with 8 warps per CTA; see ContactWork::mark in contact.cuh): the kernel is
+// bound by instruction fetches and warps at the same place of the code share them. A per-warp progress word in shared memory and a
+// bounded spin: a scheduling hint, nothing depends on it; a warp that has left reads as "ahead".
+#ifndef DDB_CONVOY_SLEEP
+#define DDB_CONVOY_SLEEP 100
+#endif
+constexpr int kConvoyMinRows = 8;
+struct BwdConvoy {
+  volatile int* reached = nullptr;
+  int warps = 0;
+  DDB_DI void leave() {  // this warp does not take part (any more): it reads as "ahead" of every meeting point
+#ifndef DDB_HOST_EMULATION
+    if (reached) reached[threadIdx.x >> 5] = 0x7fffffff;
+    reached = nullptr;
+#endif
+  }
+  DDB_DI void meet(int id) const {
+#ifndef DDB_HOST_EMULATION
+    if (!reached) return;
+    reached[threadIdx.x >> 5] = id;
+    __syncwarp();
+    for (int spins = 0; spins < 4000; spins++) {
+      int behind = 0;
+      for (int k = 0; k < warps; k++) behind |= reached[k] < id;
+      if (!behind) break;
+      __nanosleep(DDB_CONVOY_SLEEP);
+    }
+    __syncwarp();
+#endif
+  }
+};
+
 // status bits written per world: 1 = contact rows present, 2 = pseudo-inverse branch (rank-deficient Q).
 // One world per warp (lcpStride == 1): the tree sweeps run redundantly on the 32 lanes; the loops over independent rows, matrix
 // entries and DOFs (constraint-force columns, Q, the n-vectors, the contact-geometry term of every classified row) are split across
@@ -212,7 +244,7 @@ struct ContactBwdLocals {  // one object: see the note on BwdScratch (stack colo
 template <int NB>
 DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, const double* keepD, const int* keepI, const ContactBwdWork& bw,
                                 double* lcpD, int* lcpI, const double* gqn, const double* gqdn, double* gq, double* gqd, double* gtau,
-                                int layout, int N, int w, int lcpStride = 32) {
+                                int layout, int N, int w, int lcpStride = 32, BwdConvoy convoy = BwdConvoy()) {
   const int nb = c_topo.nb, nd = c_topo.nd;
   const double dt = c_topo.dt;
   const ContactTopo& ctp = c_ctopo;
@@ -245,6 +277,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       bw.cv(CV_E)[u] = (fabs(xall[r] - upper) < fabs(xall[r] - lower)) ? mu : -mu;
       u++;
     }
+  if (c + u < kConvoyMinRows) convoy.leave();  // (a world of one or two contacts is through before a meeting pays off)
   double* lamT = bw.nv(NV_LAMT);
   for (int d = 0; d < nd; d++) lamT[d] = gqdn[vidx(layout, N, nd, w, d)];
   bool pinv = false, fcDiffers = false, bounced = false;
@@ -293,9 +326,11 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
         stSVp(bw.sP(b.dof), s);
       }
     }
+    convoy.meet(10);
     // ---- world force and constraint-force column of every classified row (clamping slots 0..c-1, upper-bound slots c..c+u-1) ----
     coopSyncWarp(coopN);
     for (int sbase = 0; sbase < c + u; sbase += coopN) {
+      if (sbase) convoy.meet(10 + (sbase / coopN < 9 ? sbase / coopN : 9));
       const int slot = sbase + coopLane;
       if (slot >= c + u) continue;
       const int r = slot < c ? bw.clampRow()[slot] : bw.ubRow()[slot - c];
@@ -317,6 +352,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
         }
       }
     }
+    convoy.meet(20);
     // ---- M^-1 A columns, b_c, f_c, a = A^T M^-1 lambda ----
     double *va = bw.cv(CV_A), *vb = bw.cv(CV_B), *vfc = bw.cv(CV_F), *y1 = bw.cv(CV_Y1), *r1 = bw.cv(CV_R1);
     double *y2 = bw.cv(CV_Y2), *r2 = bw.cv(CV_R2), *y3 = bw.cv(CV_Y3), *r3 = bw.cv(CV_R3);
@@ -339,6 +375,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       const double Bj = 1.0 + restOfRow[bw.clampRow()[j]];
       vb[j] = -(Bj * sb); va[j] = sa; vfc[j] = xall[bw.clampRow()[j]];
     }
+    convoy.meet(30);
     // ---- Q = A_c^T M^-1 A and the pseudo-inverse products ----
     LcpView v;
     v.init(lcpD, lcpI, c, ctp.kmax, lcpStride);
@@ -356,7 +393,9 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
       v.db[(size_t)(v.oL + i * c + j) * v.st] = s;
     }
     coopSyncWarp(coopN);
+    convoy.meet(31);
     const int rank = codFactorDev(v, c);
+    convoy.meet(32);
     codApplyDev(v, c, rank, true, [&](int i) { return va[i]; }, [&](int i, double x) { y1[i] = x; });
     codApplyDev(v, c, rank, false, [&](int i) { return vb[i]; }, [&](int i, double x) { r1[i] = x; });
     pinv = rank < c;
@@ -379,6 +418,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     double fcScale = 0.0, fcDiff = 0.0;
     for (int j = 0; j < c; j++) { fcScale = fmax(fcScale, fabs(vfc[j])); fcDiff = fmax(fcDiff, fabs(vfc[j] - r1[j])); }
     fcDiffers = fcDiff > 1e-13 * fmax(1.0, fcScale);
+    convoy.meet(40);
     // ---- lambda~ and the n-vectors m1..m7, delta-acceleration ----
     double *m1 = bw.nv(NV_M1), *m2 = bw.nv(NV_M2), *m3 = bw.nv(NV_M3), *m4 = bw.nv(NV_M4), *m5 = bw.nv(NV_M5), *m6 = bw.nv(NV_M6), *m7 = bw.nv(NV_M7);
     double* da = bw.nv(NV_DA);
@@ -404,11 +444,13 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     }
     coopSyncWarp(coopN);
   }
+  convoy.meet(50);
   // ---- mu~ = M^-1 lambda~, dL/dtau ----
   double* muT = bw.nv(NV_MUT);
   solveInvMass<NB, false>(sn, nb, [&](int d) { return lamT[d]; }, ws, [&](int d, double m) { muT[d] = m; });
   for (int i = 0; i < nb; i++) if (c_topo.b[i].ndof == 1) muT[c_topo.b[i].dof] = ws.mu[i];
   for (int d = 0; d < nd; d++) gtau[vidx(layout, N, nd, w, d)] = dt * muT[d];
+  convoy.meet(60);
   // ---- reverse sweep over the inverse dynamics with the post-contact acceleration ----
   if (c > 0) twistsFromRates<NB>(sn, nb, [&](int d) { return bw.nv(NV_DA)[d]; }, dA, nullptr);
   else for (int i = 0; i < nb; i++) dA[i] = svzero();
@@ -432,9 +474,11 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     }
   });
   if (c == 0) return status;
+  convoy.meet(70);
   // ---- extra mass-matrix pairs: dL/dq -= mu_a^T (dM/dq) a_b ----
   if (bounced) for (int d = 0; d < nd; d++) bw.nv(NV_DA)[d] *= dt;  // M^-1 A f_c (the reverse sweep above is done with it)
   for (int pair = 0; pair < 4; pair++) {
+    if (pair) convoy.meet(70 + pair);
     if (pair == 0 && !fcDiffers) continue;
     if ((pair == 1 || pair == 2) && !pinv) continue;
     if (pair == 3 && !bounced) continue;
@@ -448,6 +492,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
                                 for (int k = 0; k < 6; k++) gq[vidx(layout, N, nd, w, d0 + k)] -= dq6[k];
                               });
   }
+  convoy.meet(80);
   // ---- contact geometry: dL/dq += sum_rows (dA_row/dq)^T V_row ----
   {
     const double *y1 = bw.cv(CV_Y1), *r1 = bw.cv(CV_R1), *y2 = bw.cv(CV_Y2), *r2 = bw.cv(CV_R2), *y3 = bw.cv(CV_Y3), *r3 = bw.cv(CV_R3), *vfc = bw.cv(CV_F);
@@ -459,6 +504,7 @@ DDB_DI int contactBackwardWorld(const Snap& sn, const ContactSnapLayout& KL, con
     // rows in rounds of coopN: lane L works out the contribution of row base + L into its private buffer, then the lanes add the
     // buffers DOF by DOF in row order (a row touches a DOF at most once: its two bodies belong to different skeletons)
     for (int sbase = 0; sbase < c + u; sbase += coopN) {
+      if (sbase) convoy.meet(80 + (sbase / coopN < 9 ? sbase / coopN : 9));
       const int slot = sbase + coopLane;
       double* V = bw.privV(coopLane);
       double* G = bw.privG(coopLane);

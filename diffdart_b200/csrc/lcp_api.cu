@@ -13,6 +13,9 @@
 #ifndef DDB_KCB_BLOCK
 #define DDB_KCB_BLOCK 256  // threads per CTA of k_contact_backward (one world per warp; see k_contact about the CTA size): measured 64 -> 256
 #endif                     // walker 25.5 -> 16.9 ms, half-cheetah 6.2 -> 3.9 ms, box stacking 50.7 -> 43.9 ms per backward pass
+#ifndef DDB_KCB_CONVOY
+#define DDB_KCB_CONVOY 1  // likewise in k_contact_backward
+#endif
 #ifndef DDB_KC_CONVOY
 #define DDB_KC_CONVOY 1  // 0: the warps of a 256-thread k_contact CTA do not wait for each other at the ends of the stage's sections
 #endif
@@ -476,13 +479,22 @@ k_contact_backward(int N, int layout, ContactSnapLayout KL, ContactBwdLayout BL,
                    double* __restrict__ gqd, double* __restrict__ gtau, double* __restrict__ work_d, int* __restrict__ work_i,
                    double* __restrict__ lcp_d, int* __restrict__ lcp_i, Limits lim, int* __restrict__ status) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one world per warp, lanes redundant (see k_contact)
+  constexpr bool kConvoy = DDB_KCB_BLOCK >= 256 && DDB_KCB_CONVOY;
+  __shared__ int reached[DDB_KCB_BLOCK / 32];
+  if (kConvoy) {
+    reached[threadIdx.x >> 5] = w < N ? 0 : 0x7fffffff;
+    __syncthreads();
+  }
   if (w >= N) return;
+  BwdConvoy convoy;
+  if (kConvoy) { convoy.reached = reached; convoy.warps = DDB_KCB_BLOCK / 32; }
   Snap sn{reinterpret_cast<double2*>(snap), N, w};
   ContactBwdWork bw{work_d + (size_t)w * BL.doubles(), work_i + (size_t)w * BL.ints(), BL};
   double* ld = lcp_d + (size_t)w * lcpScratchDoubles(BL.kmax);
   int* li = lcp_i + (size_t)w * lcpScratchInts(BL.kmax);
   const int st = contactBackwardWorld<NB>(sn, KL, keep_d + (size_t)w * KL.doubles(), keep_i + (size_t)w * KL.ints(), bw, ld, li, gqn, gqdn, gq,
-                                          gqd, gtau, layout, N, w, 1);
+                                          gqd, gtau, layout, N, w, 1, convoy);
+  if (kConvoy) reached[threadIdx.x >> 5] = 0x7fffffff;
   if (status) status[w] = st;
   // clipLossGradientsToBounds belongs to backprop() only (BackpropSnapshot.cpp:374-428); the Jacobian getters pass no limits
   if (c_topo.has_limits && lim.pos_lo) {
