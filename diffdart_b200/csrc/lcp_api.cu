@@ -26,7 +26,13 @@
 #define DDB_KCB_MINB 1
 #endif
 using namespace ddb;
-constexpr int kContactWideRows = 64;
+#ifndef DDB_KC_WIDE_ROWS
+#define DDB_KC_WIDE_ROWS 64
+#endif
+#ifndef DDB_KC_CONVOY_MIN_BLOCK
+#define DDB_KC_CONVOY_MIN_BLOCK 256
+#endif
+constexpr int kContactWideRows = DDB_KC_WIDE_ROWS;
 
 namespace {
 
@@ -439,7 +445,7 @@ k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double*
           int* __restrict__ work_i, double* __restrict__ lcp_d, int* __restrict__ lcp_i, PgsOptions pgs, double* __restrict__ keep_d,
           int* __restrict__ keep_i, int* __restrict__ ctrl, const double* __restrict__ ans_x, const int* __restrict__ ans_ok, long long* __restrict__ prof) {
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  constexpr bool kConvoy = BLOCK >= 256 && DDB_KC_CONVOY;
+  constexpr bool kConvoy = BLOCK >= DDB_KC_CONVOY_MIN_BLOCK && DDB_KC_CONVOY;
   __shared__ int reached[BLOCK / 32];  // kConvoy: ContactWork::mark
   const bool live = w < N && !(ctrl && ctrl[8 * w]);  // (else: past the batch, or committed by an earlier pass)
   if (kConvoy) {
