@@ -29,6 +29,9 @@ using namespace ddb;
 #ifndef DDB_KC_WIDE_ROWS
 #define DDB_KC_WIDE_ROWS 64
 #endif
+#ifndef DDB_KC_WIDE_BODIES
+#define DDB_KC_WIDE_BODIES 64
+#endif
 #ifndef DDB_KC_CONVOY_MIN_BLOCK
 #define DDB_KC_CONVOY_MIN_BLOCK 256
 #endif
@@ -625,7 +628,7 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
   if (e != cudaSuccess) return e;
   // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
   for (int pass = 0; pass <= kPgsRequests; pass++) {
-    if (kmax <= kContactWideRows) k_contact<256><<<(int)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+    if (kmax <= kContactWideRows && nb <= DDB_KC_WIDE_BODIES) k_contact<256><<<(int)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
                                            keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
     else k_contact<DDB_KC_BLOCK><<<(int)(((size_t)N * 32 + DDB_KC_BLOCK - 1) / DDB_KC_BLOCK), DDB_KC_BLOCK, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
                                            keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
