@@ -11,16 +11,17 @@
 #define DDB_KC_MINB 1
 #endif
 #ifndef DDB_KCB_BLOCK
-#define DDB_KCB_BLOCK 256  // threads per CTA of k_contact_backward (one world per warp; see k_contact about the CTA size): measured 64 -> 256
-#endif                     // walker 25.5 -> 16.9 ms, half-cheetah 6.2 -> 3.9 ms, box stacking 50.7 -> 43.9 ms per backward pass
+#define DDB_KCB_BLOCK 512  // threads per CTA of k_contact_backward (one world per warp; see k_contact about the CTA size): measured 64 -> 256
+#endif                     // walker 25.5 -> 16.9 ms, half-cheetah 6.2 -> 3.9 ms, box stacking 50.7 -> 43.9 ms per backward pass; 512 with the
+                           // meeting points: 8.5 / 3.3 / 19.7 ms
 #ifndef DDB_KCB_CONVOY
 #define DDB_KCB_CONVOY 1  // likewise in k_contact_backward
 #endif
 #ifndef DDB_KC_CONVOY
-#define DDB_KC_CONVOY 1  // 0: the warps of a 256-thread k_contact CTA do not wait for each other at the ends of the stage's sections
+#define DDB_KC_CONVOY 1  // 0: the warps of a wide k_contact CTA do not wait for each other at the ends of the stage's sections
 #endif
 #ifndef DDB_KC_BLOCK
-#define DDB_KC_BLOCK 128  // threads per CTA of k_contact (one world per warp) for worlds of more than kContactWideRows rows; 256 below
+#define DDB_KC_BLOCK 128  // threads per CTA of k_contact (one world per warp) for worlds of more than kContactWideRows rows; DDB_KC_WIDE_BLOCK below
 #endif
 #ifndef DDB_KCB_MINB
 #define DDB_KCB_MINB 1
@@ -29,6 +30,9 @@ using namespace ddb;
 #ifndef DDB_KC_WIDE_ROWS
 #define DDB_KC_WIDE_ROWS 64
 #endif
+#ifndef DDB_KC_WIDE_BLOCK
+#define DDB_KC_WIDE_BLOCK 512  // threads per CTA of k_contact for worlds of up to DDB_KC_WIDE_ROWS rows: 16 warps at 128 registers (1.5 KB of
+#endif                         // spills) beat 8 at 252 - walker 22.1 -> 17.0 ms, half-cheetah 4.0 -> 3.1 ms; 24 and 32 warps spill too much
 #ifndef DDB_KC_WIDE_BODIES
 #define DDB_KC_WIDE_BODIES 64
 #endif
@@ -628,7 +632,7 @@ cudaError_t contactLaunch(cudaStream_t s, int N, int nb, int nd, int cmax, int k
   if (e != cudaSuccess) return e;
   // pass p answers the PGS solves asked for in passes < p; a world is committed in the first pass that runs through
   for (int pass = 0; pass <= kPgsRequests; pass++) {
-    if (kmax <= kContactWideRows && nb <= DDB_KC_WIDE_BODIES) k_contact<256><<<(int)(((size_t)N * 32 + 255) / 256), 256, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
+    if (kmax <= kContactWideRows && nb <= DDB_KC_WIDE_BODIES) k_contact<DDB_KC_WIDE_BLOCK><<<(int)(((size_t)N * 32 + DDB_KC_WIDE_BLOCK - 1) / DDB_KC_WIDE_BLOCK), DDB_KC_WIDE_BLOCK, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
                                            keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
     else k_contact<DDB_KC_BLOCK><<<(int)(((size_t)N * 32 + DDB_KC_BLOCK - 1) / DDB_KC_BLOCK), DDB_KC_BLOCK, 0, s>>>(N, layout, L, snap, qd, lcp_cache, n_cache, counts, active_out, work_d, work_i, lcp_d, lcp_i, pgs,
                                            keep_d, keep_i, ctrl, ans_x, ans_ok, contactProfileBuffer());
