@@ -442,9 +442,11 @@ k_pgs_thread(int N, int kmax, int nLow, int* __restrict__ ctrl, double* __restri
 // can overlap, not arithmetic, and the redundant lanes cost nothing that matters (FP64 issue stays far below the pipe).
 // CTA size: the stage is 54 000 instructions of which a world touches 24 000 once or twice - more than half of a warp's stall
 // cycles are instruction fetches (ncu: stall_no_instruction 8.7 of 16 cycles per issue, profiles/README.md). Warps of one CTA
-// start together and run the same code at about the same time, so they share the fetched lines: 8 warps per CTA (the whole SM
-// at 252 registers) instead of 4 is 10-19 % faster for the walkers; box stacking, whose worlds differ by 10x in solver time,
-// loses 3 % to the CTA's wait for its slowest warp and keeps 4 (contactLaunch chooses by the row capacity).
+// start together and run the same code at about the same time, so they share the fetched lines: 8 warps per CTA instead of 4
+// was 10-19 % faster for the walkers, meeting points at the ends of the stage's sections (ContactWork::mark) another 10 %, and with
+// the fetches shared 16 warps at 128 registers beat 8 at 252 (DDB_KC_WIDE_BLOCK). Box stacking, whose worlds differ by 10x in
+// solver time, loses to the CTA's wait for its slowest warp and keeps 4 warps at 252 registers (contactLaunch chooses by the row
+// capacity). Measurements: DESIGN.md 4b.
 template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK, DDB_KC_MINB)
 k_contact(int N, int layout, ContactLayout L, double* __restrict__ snap, double* __restrict__ qd, double* __restrict__ lcp_cache,
